@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — Poseidon hashes/s building the depth-24 indexed Merkle tree (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--depth D] [--impl reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one full build (leaf hashing H3(val,next_val,next_idx) + every level) of the depth-D tree over synthetic
+leaves. With N ranks the tree is sharded by subtree: each rank builds 2^D / N leaves, the N subtree roots cross
+NVLink in one NCCL all-gather, and every rank builds the log2(N) cap levels (strong scaling: D is fixed).
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MACS_PER_HASH = 163_200          # 2 perms x 600 Montgomery muls x 136 32x32->64 MACs
+METRIC = "poseidon_hashes_per_s_depth24_tree_build"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--depth", type=int, default=24)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_build_rate(depth_hint_seconds, threads=None):
+    """Times the oracle's restatement of the reference CPU path — leaf hashing (IMT:662-671) + level-by-level build
+    (utils.rs:41-51) — on a bounded sample. Returns (hashes/s, threads, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import imt_b200
+    from imt_b200 import synth
+    th = threads or O.max_threads()
+    d = 10
+    pre = synth.random_preimages(1 << d)
+    t0 = time.perf_counter()
+    O.build_from_preimages(pre, th)
+    dt = time.perf_counter() - t0
+    rate = (2 * (1 << d) - 1) / dt
+    # pick the depth whose build fits the budget
+    d = max(10, min(20, int((rate * depth_hint_seconds / 2)).bit_length() - 1))
+    pre = synth.random_preimages(1 << d)
+    t0 = time.perf_counter()
+    O.build_from_preimages(pre, th)
+    dt = time.perf_counter() - t0
+    hashes = 2 * (1 << d) - 1
+    return hashes / dt, th, f"depth-{d} build ({hashes} hashes) in {dt:.2f}s, {th} threads", d, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU implementation of the path. The Rust crate cannot be built here
+    (no cargo/rustc, un-vendored git deps), so this is the oracle PORT of it, with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import imt_b200
+    from imt_b200 import synth
+    th = O.max_threads()
+    # a step = a bounded sample of the depth-24 workload: one depth-S build, S sized for ~3 s per step
+    rate, _, _, _, _ = cpu_build_rate(1.0, th)
+    S = max(10, min(24, int(rate * 3.0 / 2).bit_length() - 1))
+    pre = synth.random_preimages(1 << S)
+    hashes = 2 * (1 << S) - 1
+    for _ in range(a.warmup):
+        O.build_from_preimages(pre, th)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        O.build_from_preimages(pre, th)
+    dt = time.perf_counter() - t0
+    v = hashes * a.steps / dt
+    sample = f"each step = depth-{S} build ({hashes} hashes) of the depth-{a.depth} workload, {th} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "hashes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery(cpu: u64x4)",
+        "data": "synthetic", "config": {"workload": f"depth-{a.depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57",
+                                        "depth": a.depth, "sample_depth": S},
+        "cpu_baseline": {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C port of the reference's Rust CPU path (oracle/imt_oracle.c): the crate itself is unbuildable here",
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    import imt_b200
+    from imt_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    depth = a.depth
+    n_total = 1 << depth
+    n = n_total // world
+    eng = imt_b200.Engine(local_rank, "montgomery")   # Montgomery = halo2curves' in-memory form: zero-copy from Rust
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic leaves, generated on the device (setup, untimed): rank r owns leaves [r n, (r+1) n)
+    d_pre = synth.field_elements_torch(3 * n, synth.DEFAULT_SEED, first=3 * n * rank, device=dev).view(n, 3, 4)
+    h_pre = torch.empty((n, 3, 4), dtype=torch.int64, pin_memory=True)
+    h_pre.copy_(d_pre)
+    torch.cuda.synchronize(dev)
+    tree = eng.build_from_leaves_dev(d_pre, n)
+    send = torch.zeros(4, dtype=torch.int64, device=dev)
+    recv = torch.zeros((world, 4), dtype=torch.int64, device=dev)
+    h_root = torch.zeros(4, dtype=torch.int64, pin_memory=True)
+
+    def exchange():
+        if world > 1:
+            tree.root_dev(send)                                         # this rank's subtree root -> send buffer
+            dist.all_gather_into_tensor(recv, send)                      # N x 32 B over NVLink
+            tree.attach_cap_dev(rank, world, recv)                       # log2(N) cap levels, replicated
+
+    def step_resident():
+        tree.rebuild_from_leaves_dev(d_pre)
+        exchange()
+
+    def step_e2e():
+        tree.rebuild_from_leaves_ptr(h_pre.data_ptr())                   # pinned host -> device inside the call
+        exchange()
+        tree.root_dev(send)
+        h_root.copy_(send, non_blocking=True)                            # the step's result back on the host
+        stream.synchronize()
+
+    hashes_per_step = world * (2 * n - 1) + (world - 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launches
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.launches - l0
+
+    # ---- value: inputs resident in HBM. Per-kernel device times come from the library's own event pairs.
+    eng.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    for _ in range(a.warmup):
+        step_resident()
+    eng.reset_timing()
+    sampler.start()
+    ms_total, launches = timed(step_resident, a.steps, 0)
+    clocks = sampler.stop()
+    k3_ms, k3_launches, k3_hashes = eng.kernel_time(3)
+    k2_ms, k2_launches, k2_hashes = eng.kernel_time(2)
+    eng.enable_timing(False)
+    value = hashes_per_step * a.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the reference-facing call with HOST buffers (H2D of the leaves + D2H of the root inside the timed region)
+    ms_e2e, _ = timed(step_e2e, a.steps, a.warmup)
+    e2e = hashes_per_step * a.steps / (ms_e2e * 1e-3)
+    root_hex = "".join(f"{int(x) & 0xFFFFFFFFFFFFFFFF:016x}" for x in reversed(h_root.tolist()))
+
+    # ---- roofline of the dominant kernel (leaf hashing: half of all hashes in one launch)
+    imad_rate, imad_mhz = eng.calibrate_imad(150.0)
+    k3_per_launch_ms = k3_ms / max(k3_launches, 1)
+    achieved = (k3_hashes / max(k3_launches, 1)) * MACS_PER_HASH / (k3_per_launch_ms * 1e-3) if k3_ms else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    leaf_bytes = 128.0  # 96 B preimage read + 32 B hash written per leaf hash
+    roofline = {
+        "bound": "imad", "kernel": "k_hash<3> (leaf hashing)", "achieved": achieved / 1e9, "peak": imad_rate / 1e9, "unit": "GMAC/s",
+        "frac": achieved / imad_rate if imad_rate else None, "traffic": None,
+        "peak_source": f"calibrated in this run: independent IMAD.WIDE.U32 chains on all SMs (imt_calibrate_imad), SM clock {imad_mhz:.0f} MHz; "
+                       "MEASURED_PEAKS.json has no integer peak",
+        "algorithmic_macs_per_hash": MACS_PER_HASH, "kernel_ms_per_launch": k3_per_launch_ms,
+        "kernel_share_of_step": (k3_ms / a.steps) / (ms_total / a.steps) if ms_total else None,
+        "node_kernel_ms_per_step": k2_ms / a.steps, "node_kernel_launches_per_step": k2_launches / a.steps,
+        "hbm": {"achieved_gbs": (k3_hashes / max(k3_launches, 1)) * leaf_bytes / (k3_per_launch_ms * 1e-3) / 1e9 if k3_ms else None,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "hashes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x8-montgomery", "data": "synthetic",
+        "config": {"workload": f"depth-{depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57",
+                   "depth": depth, "leaves": n_total, "leaves_per_gpu": n, "hashes_per_step": hashes_per_step,
+                   "sharding": f"subtree x{world} + all-gather of {world} roots" if world > 1 else "single GPU",
+                   "l2_policy": f"inputs larger than L2 ({n * 96 / 2**20:.0f} MiB of leaves per GPU per step)", "seed": synth.DEFAULT_SEED,
+                   "fe_format": "montgomery"},
+        "e2e": {"value": e2e, "unit": "hashes/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n_total * 96,
+                "d2h_bytes_per_step": 32 * world},
+        "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex,
+    }
+    if rank == 0 and not a.no_cpu_baseline:
+        v, th, sample, _, _ = cpu_build_rate(a.cpu_seconds)
+        out["cpu_baseline"] = {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+/*
+ * imt_b200 — C-ABI of the B200-native BN254-Poseidon / indexed-Merkle-tree engine.
+ *
+ * Drop-in boundary for the hot path of aerius-labs/indexed-merkle-tree-halo2. Every entry point names the
+ * reference interface it replaces (paths relative to /root/reference). The reference has no FFI of its own (it is
+ * pure Rust); INTEGRATION.md shows the `extern "C"` block + build.rs a maintainer adds so that
+ * `IndexedMerkleTree::new / get_root / get_proof / verify_proof` (src/utils.rs) and the witness loading in front
+ * of `insert_leaf` / `verify_non_inclusion` (src/indexed_merkle_tree.rs:444-474) call into this library.
+ *
+ * Conventions
+ *  - A field element (FE) is 32 bytes: BN254 Fr, little-endian. Format is per context:
+ *      IMT_FE_CANONICAL   canonical integer < p          (== halo2curves `to_repr()` bytes)
+ *      IMT_FE_MONTGOMERY  value * 2^256 mod p, < p       (== halo2curves' in-memory [u64; 4]; zero-copy from Rust)
+ *    Inputs that are >= p are rejected with IMT_ERR_NON_CANONICAL.
+ *  - A leaf preimage is 3 FE in the reference's struct order  val, next_val, next_idx  (src/utils.rs:12-17;
+ *    hash order src/indexed_merkle_tree.rs:667).
+ *  - Paths: siblings bottom-up; helper = 1 when the current node is the LEFT child (src/utils.rs:70, 79).
+ *  - All arrays are dense, caller-allocated. `*_dev` variants take DEVICE pointers (same layout) and do not copy.
+ *  - Every function returns an imt_status; nothing aborts the process. A context is not thread-safe (the
+ *    reference's hasher is a `&mut` borrow: src/utils.rs:7, 21, 87). Calls are synchronous on return.
+ *  - There is no CPU fallback: without a CUDA device imt_ctx_create fails with IMT_ERR_CUDA.
+ */
+#ifndef IMT_B200_H
+#define IMT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct imt_ctx imt_ctx;
+typedef struct imt_tree imt_tree;
+
+typedef enum imt_status {
+    IMT_OK = 0,
+    IMT_ERR_EMPTY = 1,         /* "Cannot create Merkle Tree with no leaves"            src/utils.rs:24-26 */
+    IMT_ERR_ODD = 2,           /* "Leaves must be even"                                 src/utils.rs:34-36 */
+    IMT_ERR_NOT_POW2 = 3,      /* even but not a power of two: the reference panics at  src/utils.rs:45    */
+    IMT_ERR_INDEX_OOB = 4,     /* index >= leaf count: the reference panics at          src/utils.rs:76    */
+    IMT_ERR_NON_CANONICAL = 5, /* an input field element is >= p                                           */
+    IMT_ERR_INVALID_ARG = 6,   /* null pointer, bad arity/format/level, tree without preimages, ...        */
+    IMT_ERR_TREE_FULL = 7,     /* insert batch does not fit into the remaining empty slots                  */
+    IMT_ERR_NOT_WELL_FORMED = 8, /* preimages are not a consistent indexed (sorted linked list) tree        */
+    IMT_ERR_CUDA = 100         /* CUDA runtime / driver failure; text in imt_last_error()                   */
+} imt_status;
+
+typedef enum imt_fe_format { IMT_FE_CANONICAL = 0, IMT_FE_MONTGOMERY = 1 } imt_fe_format;
+
+#define IMT_FE_BYTES 32
+#define IMT_STATES_PER_HASH 132 /* 2 permutations x (1 + R_F + R_P) states of 3 FE: SURVEY.md 8a row 9 */
+
+/* ---------------------------------------------------------------- context ------------------------------------ */
+/* Replaces Poseidon::<Fr,3,2>::new(8, 57) (src/indexed_merkle_tree.rs:370, 663, 681, 807): derives the parameter
+ * set (Grain LFSR, Cauchy MDS, optimized constants, sparse matrices) and uploads it to the device. */
+imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx** out);
+void imt_ctx_destroy(imt_ctx* ctx);
+/* Text of the last failure on this context ("" if none). Valid until the next call on the context. */
+const char* imt_last_error(const imt_ctx* ctx);
+/* The message the reference returns for a status (exact strings of src/utils.rs:25, 35), or a description. */
+const char* imt_status_string(imt_status st);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+uint64_t imt_ctx_launch_count(const imt_ctx* ctx);
+/* Launch on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of the context's own;
+ * NULL restores the internal stream. Lets callers bracket calls with their own events / order them with NCCL. */
+imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream);
+/* Per-kernel device timing: when enabled every hash launch is bracketed by CUDA events on its stream.
+ * imt_ctx_kernel_time returns, for hash kernels of the given arity (2 = node levels, 3 = leaf hashing), the summed
+ * device time in ms, the launch count and the number of hashes since the last reset. */
+imt_status imt_ctx_enable_timing(imt_ctx* ctx, int enabled);
+imt_status imt_ctx_kernel_time(imt_ctx* ctx, int arity, double* total_ms, uint64_t* launches, uint64_t* hashes);
+imt_status imt_ctx_reset_timing(imt_ctx* ctx);
+
+/* ---------------------------------------------------------------- batched hashing ---------------------------- */
+/* out[i] = H(in[2i], in[2i+1]): update(&[l, r]) + squeeze_and_reset()   (src/utils.rs:46-47, 96-100)           */
+imt_status imt_poseidon_hash2(imt_ctx* ctx, const void* in, size_t n, void* out);
+/* out[i] = H(in[3i], in[3i+1], in[3i+2]): leaf hashing, order val,next_val,next_idx
+ * (src/indexed_merkle_tree.rs:373-376, 407-415, 510-518, 662-671)                                              */
+imt_status imt_poseidon_hash3(imt_ctx* ctx, const void* in, size_t n, void* out);
+imt_status imt_poseidon_hash2_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out);
+imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out);
+
+/* Witness trace of `hash_fix_len_array` (src/indexed_merkle_tree.rs:92, 194, 271, 299): for each of the n hashes
+ * of `arity` (2 or 3) inputs, the 132 x 3 FE states (per permutation: after the pre-constant add, then after the
+ * linear layer of each of the 4 + 57 + 4 rounds) and the digest. states may be NULL. */
+imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests);
+imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests);
+
+/* ---------------------------------------------------------------- native tree -------------------------------- */
+/* IndexedMerkleTree::new(hasher, leaves)  (src/utils.rs:20-57): all levels, bottom-up, kept on the device.
+ * n == 0 -> IMT_ERR_EMPTY, n == 1 -> tree = [leaf], odd n -> IMT_ERR_ODD, other non powers of two -> NOT_POW2. */
+imt_status imt_tree_build_from_hashes(imt_ctx* ctx, const void* leaf_hashes, size_t n, imt_tree** out);
+/* Leaf hashing (src/indexed_merkle_tree.rs:662-671) fused in front of the build; keeps the preimages on the
+ * device so that low-leaf lookups and inserts can follow. */
+imt_status imt_tree_build_from_leaves(imt_ctx* ctx, const void* preimages, size_t n, imt_tree** out);
+imt_status imt_tree_build_from_hashes_dev(imt_ctx* ctx, const void* d_leaf_hashes, size_t n, imt_tree** out);
+imt_status imt_tree_build_from_leaves_dev(imt_ctx* ctx, const void* d_preimages, size_t n, imt_tree** out);
+/* Re-run the build into an existing tree of the same size (no allocation): the steady-state call bench.py times. */
+imt_status imt_tree_rebuild_from_leaves(imt_tree* tree, const void* preimages);
+imt_status imt_tree_rebuild_from_leaves_dev(imt_tree* tree, const void* d_preimages);
+void imt_tree_destroy(imt_tree* tree);
+
+size_t imt_tree_num_leaves(const imt_tree* tree);
+unsigned imt_tree_depth(const imt_tree* tree); /* number of sibling levels = log2(n) */
+/* get_root()  (src/utils.rs:59-61) */
+imt_status imt_tree_root(imt_tree* tree, void* out_fe);
+/* The same into a DEVICE buffer of 32 bytes (context format); asynchronous on the context's stream. */
+imt_status imt_tree_root_dev(imt_tree* tree, void* d_out_fe);
+/* tree[level] (src/utils.rs:8): level 0 = leaf hashes, level depth = [root]. Copies (n >> level) FE. */
+imt_status imt_tree_level(imt_tree* tree, unsigned level, void* out);
+/* Current preimages (n x 3 FE) of a tree built from leaves. */
+imt_status imt_tree_preimages(imt_tree* tree, void* out);
+
+/* get_proof(index) batched  (src/utils.rs:63-85): siblings[q][depth] FE, helpers[q][depth] bytes (1 = left). */
+imt_status imt_tree_get_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers);
+/* The same helpers as field elements, as the reference returns them (F::from(1) / F::from(0), src/utils.rs:79). */
+imt_status imt_tree_get_proofs_fe(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, void* helpers_fe);
+
+/* verify_proof(leaf, index, root, proof) batched  (src/utils.rs:87-107): ok[i] = 1 iff the fold equals roots[i].
+ * roots holds q FE (one per query). */
+imt_status imt_verify_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots,
+                             const void* siblings, size_t q, unsigned depth, uint8_t* ok);
+
+/* Witness trace of compute_merkle_root (src/indexed_merkle_tree.rs:78-96): for each query the `depth` hashes of
+ * the fold, in order, each as 132 x 3 FE; plus the computed roots. states[q][depth][132][3] FE. */
+imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* siblings,
+                                   size_t q, unsigned depth, void* states, void* roots);
+
+/* ---------------------------------------------------------------- indexed-leaf logic ------------------------- */
+/* Low-leaf (predecessor) lookup, the read-only half of update_idx_leaf (src/indexed_merkle_tree.rs:632-660):
+ * low_idx[i] = first slot with  val < v && (next_val > v || next_val == 0)  (or slot 0 for the very first insert).
+ * matched[i] = 0 where no slot qualifies (v == 0 or v already present with no empty slot): the reference then
+ * returns index 0 and leaves the leaves unchanged. Requires a tree built from leaves whose occupied slots form a
+ * prefix and a consistent sorted linked list (IMT_ERR_NOT_WELL_FORMED otherwise). */
+imt_status imt_low_leaf_lookup(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched);
+/* Non-inclusion witnesses for verify_non_inclusion (src/indexed_merkle_tree.rs:127-137): lookup + the low leaf's
+ * preimage (3 FE), its path, and is_largest = (low.next_val == 0). Any output pointer may be NULL. */
+imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                   void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest);
+
+/* Sequential inserts with per-insert witnesses — the native half of test_insert_leaf_multiple_round
+ * (src/indexed_merkle_tree.rs:710-741) — computed with O(depth) hashes per insert instead of a full re-hash and
+ * rebuild. Insert i puts new_vals[i] into slot first_idx + i. Outputs (any may be NULL), per insert:
+ *   old_roots FE, low_idx u64, low_leaves 3 FE (OLD preimage), low_siblings depth FE + low_helpers (OLD tree),
+ *   new_roots FE, new_leaves 3 FE, new_siblings depth FE + new_helpers (NEW tree), is_largest u8.
+ * The tree is updated in place. */
+typedef struct imt_insert_witness {
+    void* old_roots;
+    uint64_t* low_idx;
+    void* low_leaves;
+    void* low_siblings;
+    uint8_t* low_helpers;
+    void* new_roots;
+    void* new_leaves;
+    void* new_siblings;
+    uint8_t* new_helpers;
+    uint8_t* is_largest;
+} imt_insert_witness;
+imt_status imt_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w);
+
+/* ---------------------------------------------------------------- subtree sharding (one process per GPU) ----- */
+/* A depth-d tree over N = 2^k ranks: rank g owns leaves [g n/N, (g+1) n/N) and builds that subtree with the calls
+ * above (n = leaves per rank). The N subtree roots are exchanged by the caller (ncclAllGather / torch.distributed
+ * all_gather of N x 32 bytes) and attached here; the k cap levels are then built on this rank's device.
+ * Afterwards root / get_proofs / depth refer to the GLOBAL tree: indices passed to get_proofs are global and must
+ * fall inside this rank's range. `d_subtree_root` from imt_tree_subtree_root_dev is a device pointer to this
+ * rank's root (Montgomery-format contexts only), usable directly as the all-gather send buffer. A rebuild makes the
+ * attached cap stale: root()/depth() then refer to the subtree again until the new roots are attached. */
+imt_status imt_tree_subtree_root_dev(imt_tree* tree, const void** d_subtree_root);
+imt_status imt_tree_attach_cap(imt_tree* tree, unsigned rank, unsigned world, const void* subtree_roots);
+imt_status imt_tree_attach_cap_dev(imt_tree* tree, unsigned rank, unsigned world, const void* d_subtree_roots);
+
+/* ---------------------------------------------------------------- calibration -------------------------------- */
+/* Integer-multiply roofline calibration: runs independent IMAD.WIDE.U32 chains on every SM for about `ms`
+ * milliseconds and returns sustained 32x32->64 multiply-accumulates per second (and the SM clock seen). */
+imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_mac_per_s, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMT_B200_H */

@@ -1,0 +1,707 @@
+// C-ABI of the engine (include/imt_b200.h). Host-side orchestration only: allocation, staging, launches.
+// All arithmetic runs in the sm_100a kernels of kernels.cuh; there is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "imt_b200.h"
+#include "kernels.cuh"
+#include "poseidon_params.h"
+
+using namespace imt;
+
+struct imt_ctx {
+    int device = 0;
+    int fmt = kFmtCanonical;
+    cudaStream_t stream = nullptr;       // compute (own_stream unless the caller supplied one)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
+    uint32_t* d_err = nullptr;           // bit 0: non-canonical input, bit 1: index out of bounds
+    uint32_t* h_err = nullptr;           // pinned mirror
+    uint64_t launches = 0;
+    std::string last_error;
+    // optional per-launch device timing of the hash kernels
+    bool timing = false;
+    struct Timed {
+        cudaEvent_t a, b;
+        int arity;
+        size_t hashes;
+    };
+    std::vector<Timed> pending;
+    double kernel_ms[4] = {0, 0, 0, 0};
+    uint64_t kernel_launches[4] = {0, 0, 0, 0};
+    uint64_t kernel_hashes[4] = {0, 0, 0, 0};
+};
+
+struct imt_tree {
+    imt_ctx* ctx = nullptr;
+    size_t n = 0;            // leaves on this rank
+    unsigned depth = 0;      // log2(n)
+    Fr* d_levels = nullptr;  // 2n - 1 FE, Montgomery, level 0 first
+    Fr* d_pre = nullptr;     // 3n FE in the context format (only when built from leaves)
+    bool owns_pre = false;
+    // subtree sharding
+    unsigned rank = 0, world = 1, cap_depth = 0;
+    Fr* d_cap = nullptr;  // 2*world - 1 FE, Montgomery
+    unsigned cap_alloc_world = 0;
+    bool cap_valid = false;  // a rebuild makes the attached cap stale until the roots are exchanged again
+    // lazily built sorted index over the occupied leaves (low-leaf lookups)
+    bool index_valid = false;
+    size_t occupied = 0;
+    Fr* d_sorted_keys = nullptr;       // canonical values, ascending
+    uint32_t* d_sorted_slots = nullptr;  // slot of each key
+};
+
+namespace {
+
+#define IMT_TRY_CUDA(ctx, expr)                                                                         \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
+            return IMT_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+#define IMT_TRY(expr)                      \
+    do {                                   \
+        imt_status s_ = (expr);            \
+        if (s_ != IMT_OK) return s_;       \
+    } while (0)
+
+inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+imt_status fail(imt_ctx* ctx, imt_status st, const char* what) {
+    ctx->last_error = what;
+    return st;
+}
+
+// RAII device buffer
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T>
+    T* as() { return static_cast<T*>(p); }
+};
+
+imt_status clear_err(imt_ctx* ctx) {
+    IMT_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(uint32_t), ctx->stream));
+    return IMT_OK;
+}
+void drain_timing(imt_ctx* ctx) {
+    for (auto& t : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            ctx->kernel_ms[t.arity] += ms;
+            ctx->kernel_launches[t.arity] += 1;
+            ctx->kernel_hashes[t.arity] += t.hashes;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    ctx->pending.clear();
+}
+// waits for the compute stream and turns the device error flag into a status
+imt_status finish(imt_ctx* ctx) {
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    if (!ctx->pending.empty()) drain_timing(ctx);
+    const uint32_t e = *ctx->h_err;
+    if (e & 2u) return fail(ctx, IMT_ERR_INDEX_OOB, "index out of bounds");
+    if (e & 1u) return fail(ctx, IMT_ERR_NON_CANONICAL, "input field element >= p");
+    return IMT_OK;
+}
+
+imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
+    if (n == 0) return fail(ctx, IMT_ERR_EMPTY, imt_status_string(IMT_ERR_EMPTY));
+    if (n == 1) return IMT_OK;
+    if (n & 1) return fail(ctx, IMT_ERR_ODD, imt_status_string(IMT_ERR_ODD));
+    if (n & (n - 1)) return fail(ctx, IMT_ERR_NOT_POW2, imt_status_string(IMT_ERR_NOT_POW2));
+    return IMT_OK;
+}
+
+template <int ARITY>
+imt_status launch_hash(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+    if (n == 0) return IMT_OK;
+    imt_ctx::Timed tm{nullptr, nullptr, ARITY, n};
+    if (ctx->timing) {
+        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.a));
+        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
+        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
+    }
+    k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
+                                                                  ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    if (ctx->timing) {
+        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.b, s));
+        ctx->pending.push_back(tm);
+    }
+    return IMT_OK;
+}
+
+// all levels above level 0 (which must already hold the Montgomery leaf hashes)
+imt_status build_upper_levels(imt_tree* t) {
+    imt_ctx* ctx = t->ctx;
+    for (unsigned l = 0; l < t->depth; ++l) {
+        const Fr* src = t->d_levels + level_offset(t->n, l);
+        Fr* dst = t->d_levels + level_offset(t->n, l + 1);
+        IMT_TRY(launch_hash<2>(ctx, src, dst, t->n >> (l + 1), kFmtMontgomery, kFmtMontgomery, ctx->stream));
+    }
+    return IMT_OK;
+}
+
+imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
+    imt_tree* t = new (std::nothrow) imt_tree();
+    if (!t) return fail(ctx, IMT_ERR_CUDA, "out of host memory");
+    t->ctx = ctx;
+    t->n = n;
+    t->depth = 0;
+    while (((size_t)1 << t->depth) < n) ++t->depth;
+    cudaError_t e = cudaMalloc((void**)&t->d_levels, (2 * n - 1) * sizeof(Fr));
+    if (e == cudaSuccess && with_pre) {
+        e = cudaMalloc((void**)&t->d_pre, 3 * n * sizeof(Fr));
+        t->owns_pre = true;
+    }
+    if (e != cudaSuccess) {
+        ctx->last_error = std::string("cudaMalloc(tree): ") + cudaGetErrorString(e);
+        imt_tree_destroy(t);
+        return IMT_ERR_CUDA;
+    }
+    *out = t;
+    return IMT_OK;
+}
+
+void invalidate_index(imt_tree* t) {
+    t->index_valid = false;
+    if (t->d_sorted_keys) cudaFree(t->d_sorted_keys), t->d_sorted_keys = nullptr;
+    if (t->d_sorted_slots) cudaFree(t->d_sorted_slots), t->d_sorted_slots = nullptr;
+}
+
+// Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed.
+imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
+    imt_ctx* ctx = t->ctx;
+    const size_t chunk = (size_t)1 << 19;  // 512 Ki leaves = 48 MiB per copy
+    const char* src = static_cast<const char*>(preimages);
+    std::vector<cudaEvent_t> evs;
+    imt_status st = IMT_OK;
+    for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk) {
+        const size_t cnt = (t->n - off < chunk) ? t->n - off : chunk;
+        cudaEvent_t ev;
+        IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        evs.push_back(ev);
+        cudaError_t e = cudaMemcpyAsync(t->d_pre + 3 * off, src + 3 * off * sizeof(Fr), 3 * cnt * sizeof(Fr),
+                                        cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+        if (e != cudaSuccess) {
+            ctx->last_error = std::string("leaf staging: ") + cudaGetErrorString(e);
+            st = IMT_ERR_CUDA;
+            break;
+        }
+        st = launch_hash<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, ctx->stream);
+    }
+    if (st != IMT_OK) cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t ev : evs) {
+        if (st == IMT_OK) cudaEventSynchronize(ev);
+        cudaEventDestroy(ev);
+    }
+    return st;
+}
+
+imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
+    imt_ctx* ctx = t->ctx;
+    if (!preimages) return fail(ctx, IMT_ERR_INVALID_ARG, "null preimages");
+    if (!t->d_pre && !device_src) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    invalidate_index(t);
+    t->cap_valid = false;
+    IMT_TRY(clear_err(ctx));
+    if (device_src) {
+        if (t->owns_pre && t->d_pre && preimages != t->d_pre)
+            IMT_TRY_CUDA(ctx, cudaMemcpyAsync(t->d_pre, preimages, 3 * t->n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        const void* src = (t->owns_pre && t->d_pre) ? (const void*)t->d_pre : preimages;
+        IMT_TRY(launch_hash<3>(ctx, src, t->d_levels, t->n, ctx->fmt, kFmtMontgomery, ctx->stream));
+    } else {
+        IMT_TRY(hash_leaves_from_host(t, preimages));
+    }
+    IMT_TRY(build_upper_levels(t));
+    return finish(ctx);
+}
+
+// copies q*elems FE device->host after converting Montgomery -> context format in place
+imt_status copy_out_fe(imt_ctx* ctx, const Fr* d_src, size_t count, void* h_dst, bool convert_from_mont) {
+    if (count == 0) return IMT_OK;
+    if (convert_from_mont && ctx->fmt == kFmtCanonical) {
+        DevBuf tmp;
+        IMT_TRY_CUDA(ctx, tmp.alloc(count * sizeof(Fr)));
+        k_convert<<<grid_for(count, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, tmp.as<uint4>(), count, kFmtMontgomery,
+                                                              kFmtCanonical, ctx->d_err);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h_dst, tmp.p, count * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IMT_OK;
+    }
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, count * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- context
+extern "C" const char* imt_status_string(imt_status st) {
+    switch (st) {
+        case IMT_OK: return "ok";
+        case IMT_ERR_EMPTY: return "Cannot create Merkle Tree with no leaves";  // src/utils.rs:25
+        case IMT_ERR_ODD: return "Leaves must be even";                         // src/utils.rs:35
+        case IMT_ERR_NOT_POW2: return "leaf count is not a power of two";
+        case IMT_ERR_INDEX_OOB: return "index out of bounds";
+        case IMT_ERR_NON_CANONICAL: return "input field element >= p";
+        case IMT_ERR_INVALID_ARG: return "invalid argument";
+        case IMT_ERR_TREE_FULL: return "not enough empty slots";
+        case IMT_ERR_NOT_WELL_FORMED: return "preimages are not a well-formed indexed tree";
+        case IMT_ERR_CUDA: return "CUDA error";
+    }
+    return "unknown status";
+}
+
+extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx** out) {
+    if (!out || (format != IMT_FE_CANONICAL && format != IMT_FE_MONTGOMERY)) return IMT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return IMT_ERR_CUDA;
+    imt_ctx* ctx = new (std::nothrow) imt_ctx();
+    if (!ctx) return IMT_ERR_CUDA;
+    ctx->device = device;
+    ctx->fmt = (int)format;
+    static PoseidonParams host_params;  // derived once per process
+    static bool have_params = false;
+    if (!have_params) {
+        poseidon_params_generate(&host_params);
+        have_params = true;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    ctx->stream = ctx->own_stream;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_err, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_err, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "imt_ctx_create: %s\n", cudaGetErrorString(e));
+        imt_ctx_destroy(ctx);
+        return IMT_ERR_CUDA;
+    }
+    *out = ctx;
+    return IMT_OK;
+}
+
+extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    drain_timing(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    delete ctx;
+}
+
+extern "C" const char* imt_last_error(const imt_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+extern "C" uint64_t imt_ctx_launch_count(const imt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return IMT_OK;
+}
+extern "C" imt_status imt_ctx_enable_timing(imt_ctx* ctx, int enabled) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    ctx->timing = enabled != 0;
+    return IMT_OK;
+}
+extern "C" imt_status imt_ctx_reset_timing(imt_ctx* ctx) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timing(ctx);
+    for (int i = 0; i < 4; ++i) ctx->kernel_ms[i] = 0, ctx->kernel_launches[i] = 0, ctx->kernel_hashes[i] = 0;
+    return IMT_OK;
+}
+extern "C" imt_status imt_ctx_kernel_time(imt_ctx* ctx, int arity, double* total_ms, uint64_t* launches, uint64_t* hashes) {
+    if (!ctx || arity < 2 || arity > 3) return IMT_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timing(ctx);
+    if (total_ms) *total_ms = ctx->kernel_ms[arity];
+    if (launches) *launches = ctx->kernel_launches[arity];
+    if (hashes) *hashes = ctx->kernel_hashes[arity];
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- hashing
+template <int ARITY>
+static imt_status hash_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (n && (!d_in || !d_out)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_hash<ARITY>(ctx, d_in, d_out, n, ctx->fmt, ctx->fmt, ctx->stream));
+    return finish(ctx);
+}
+template <int ARITY>
+static imt_status hash_host(imt_ctx* ctx, const void* in, size_t n, void* out) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (n && (!in || !out)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf din, dout;
+    IMT_TRY_CUDA(ctx, din.alloc(n * ARITY * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dout.alloc(n * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * ARITY * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_hash<ARITY>(ctx, din.p, dout.p, n, ctx->fmt, ctx->fmt, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+extern "C" imt_status imt_poseidon_hash2(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_host<2>(ctx, in, n, out); }
+extern "C" imt_status imt_poseidon_hash3(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_host<3>(ctx, in, n, out); }
+extern "C" imt_status imt_poseidon_hash2_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<2>(ctx, in, n, out); }
+extern "C" imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<3>(ctx, in, n, out); }
+
+extern "C" imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (arity != 2 && arity != 3) return fail(ctx, IMT_ERR_INVALID_ARG, "arity must be 2 or 3");
+    if (n && !d_in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    if (arity == 2)
+        k_trace_hash<2><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states,
+                                                                                  (uint4*)d_digests, n, ctx->fmt, ctx->d_err);
+    else
+        k_trace_hash<3><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states,
+                                                                                  (uint4*)d_digests, n, ctx->fmt, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return finish(ctx);
+}
+extern "C" imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (arity != 2 && arity != 3) return fail(ctx, IMT_ERR_INVALID_ARG, "arity must be 2 or 3");
+    if (n && !in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
+    DevBuf din, dst, ddg;
+    IMT_TRY_CUDA(ctx, din.alloc(n * arity * sizeof(Fr)));
+    if (states) IMT_TRY_CUDA(ctx, dst.alloc(n * state_fe * sizeof(Fr)));
+    if (digests) IMT_TRY_CUDA(ctx, ddg.alloc(n * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * arity * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(imt_trace_hashes_dev(ctx, din.p, arity, n, states ? dst.p : nullptr, digests ? ddg.p : nullptr));
+    if (states) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, n * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (digests) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(digests, ddg.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- tree
+static imt_status build_from_hashes(imt_ctx* ctx, const void* leaf_hashes, size_t n, bool device_src, imt_tree** out) {
+    if (!ctx || !out) return IMT_ERR_INVALID_ARG;
+    *out = nullptr;
+    IMT_TRY(check_leaf_count(ctx, n));
+    if (!leaf_hashes) return fail(ctx, IMT_ERR_INVALID_ARG, "null leaves");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    imt_tree* t = nullptr;
+    IMT_TRY(tree_alloc(ctx, n, false, &t));
+    imt_status st = clear_err(ctx);
+    DevBuf staged;
+    const void* d_src = leaf_hashes;
+    if (st == IMT_OK && !device_src) {
+        if (staged.alloc(n * sizeof(Fr)) != cudaSuccess ||
+            cudaMemcpyAsync(staged.p, leaf_hashes, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+            st = fail(ctx, IMT_ERR_CUDA, "staging leaf hashes failed");
+        d_src = staged.p;
+    }
+    if (st == IMT_OK) {  // level 0 = the given hashes, validated and converted to Montgomery form
+        k_convert<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, (uint4*)t->d_levels, n, ctx->fmt,
+                                                          kFmtMontgomery, ctx->d_err);
+        ++ctx->launches;
+        st = build_upper_levels(t);
+    }
+    if (st == IMT_OK) st = finish(ctx);
+    if (st != IMT_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        imt_tree_destroy(t);
+        return st;
+    }
+    *out = t;
+    return IMT_OK;
+}
+extern "C" imt_status imt_tree_build_from_hashes(imt_ctx* ctx, const void* h, size_t n, imt_tree** out) {
+    return build_from_hashes(ctx, h, n, false, out);
+}
+extern "C" imt_status imt_tree_build_from_hashes_dev(imt_ctx* ctx, const void* h, size_t n, imt_tree** out) {
+    return build_from_hashes(ctx, h, n, true, out);
+}
+
+static imt_status build_from_leaves(imt_ctx* ctx, const void* preimages, size_t n, bool device_src, imt_tree** out) {
+    if (!ctx || !out) return IMT_ERR_INVALID_ARG;
+    *out = nullptr;
+    IMT_TRY(check_leaf_count(ctx, n));
+    if (!preimages) return fail(ctx, IMT_ERR_INVALID_ARG, "null preimages");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    imt_tree* t = nullptr;
+    IMT_TRY(tree_alloc(ctx, n, true, &t));
+    imt_status st = rebuild(t, preimages, device_src);
+    if (st != IMT_OK) {
+        imt_tree_destroy(t);
+        return st;
+    }
+    *out = t;
+    return IMT_OK;
+}
+extern "C" imt_status imt_tree_build_from_leaves(imt_ctx* ctx, const void* p, size_t n, imt_tree** out) {
+    return build_from_leaves(ctx, p, n, false, out);
+}
+extern "C" imt_status imt_tree_build_from_leaves_dev(imt_ctx* ctx, const void* p, size_t n, imt_tree** out) {
+    return build_from_leaves(ctx, p, n, true, out);
+}
+extern "C" imt_status imt_tree_rebuild_from_leaves(imt_tree* t, const void* p) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    return rebuild(t, p, false);
+}
+extern "C" imt_status imt_tree_rebuild_from_leaves_dev(imt_tree* t, const void* p) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    return rebuild(t, p, true);
+}
+
+extern "C" void imt_tree_destroy(imt_tree* t) {
+    if (!t) return;
+    if (t->ctx) cudaSetDevice(t->ctx->device);
+    if (t->d_levels) cudaFree(t->d_levels);
+    if (t->d_pre && t->owns_pre) cudaFree(t->d_pre);
+    if (t->d_cap) cudaFree(t->d_cap);
+    if (t->d_sorted_keys) cudaFree(t->d_sorted_keys);
+    if (t->d_sorted_slots) cudaFree(t->d_sorted_slots);
+    delete t;
+}
+
+extern "C" size_t imt_tree_num_leaves(const imt_tree* t) { return t ? (t->cap_valid ? t->n * t->world : t->n) : 0; }
+extern "C" unsigned imt_tree_depth(const imt_tree* t) { return t ? t->depth + (t->cap_valid ? t->cap_depth : 0) : 0; }
+
+extern "C" imt_status imt_tree_root(imt_tree* t, void* out_fe) {
+    if (!t || !out_fe) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Fr* d_root = t->cap_valid ? t->d_cap + level_offset(t->world, t->cap_depth) : t->d_levels + level_offset(t->n, t->depth);
+    return copy_out_fe(ctx, d_root, 1, out_fe, true);
+}
+
+extern "C" imt_status imt_tree_root_dev(imt_tree* t, void* d_out_fe) {
+    if (!t || !d_out_fe) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Fr* d_root = t->cap_valid ? t->d_cap + level_offset(t->world, t->cap_depth) : t->d_levels + level_offset(t->n, t->depth);
+    k_convert<<<1, 32, 0, ctx->stream>>>((const uint4*)d_root, (uint4*)d_out_fe, 1, kFmtMontgomery, ctx->fmt, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_tree_level(imt_tree* t, unsigned level, void* out) {
+    if (!t || !out) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (level <= t->depth) return copy_out_fe(ctx, t->d_levels + level_offset(t->n, level), t->n >> level, out, true);
+    if (t->cap_valid && level <= t->depth + t->cap_depth) {
+        const unsigned cl = level - t->depth;
+        return copy_out_fe(ctx, t->d_cap + level_offset(t->world, cl), t->world >> cl, out, true);
+    }
+    return fail(ctx, IMT_ERR_INVALID_ARG, "level out of range");
+}
+
+extern "C" imt_status imt_tree_preimages(imt_tree* t, void* out) {
+    if (!t || !out) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    return copy_out_fe(ctx, t->d_pre, 3 * t->n, out, false);
+}
+
+static imt_status get_proofs(imt_tree* t, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers, void* helpers_fe) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!indices || !siblings)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
+    const unsigned depth = t->depth + cap_depth;
+    if (q == 0 || depth == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf didx, dsib, dhel, dhfe;
+    IMT_TRY_CUDA(ctx, didx.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dsib.alloc(q * depth * sizeof(Fr)));
+    if (helpers) IMT_TRY_CUDA(ctx, dhel.alloc(q * depth));
+    if (helpers_fe) IMT_TRY_CUDA(ctx, dhfe.alloc(q * depth * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(didx.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_gather_proofs<<<grid_for(q * depth, 256), 256, 0, ctx->stream>>>(
+        (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, didx.as<uint64_t>(), q,
+        ctx->fmt, dsib.as<uint4>(), helpers ? dhel.as<uint8_t>() : nullptr, helpers_fe ? dhfe.as<uint4>() : nullptr, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(siblings, dsib.p, q * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (helpers) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(helpers, dhel.p, q * depth, cudaMemcpyDeviceToHost, ctx->stream));
+    if (helpers_fe) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(helpers_fe, dhfe.p, q * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+extern "C" imt_status imt_tree_get_proofs(imt_tree* t, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers) {
+    return get_proofs(t, indices, q, siblings, helpers, nullptr);
+}
+extern "C" imt_status imt_tree_get_proofs_fe(imt_tree* t, const uint64_t* indices, size_t q, void* siblings, void* helpers_fe) {
+    return get_proofs(t, indices, q, siblings, nullptr, helpers_fe);
+}
+
+static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots, const void* siblings,
+                             size_t q, unsigned depth, uint8_t* ok, void* roots_out, void* states) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (q && (!leaves || !indices || (depth && !siblings) || (ok && !roots))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
+    DevBuf dl, di, dr, ds, dok, dro, dst;
+    IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, ds.alloc(q * depth * sizeof(Fr)));
+    if (ok) {
+        IMT_TRY_CUDA(ctx, dr.alloc(q * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, dok.alloc(q));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dr.p, roots, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (roots_out) IMT_TRY_CUDA(ctx, dro.alloc(q * sizeof(Fr)));
+    if (states) IMT_TRY_CUDA(ctx, dst.alloc(q * depth * state_fe * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dl.p, leaves, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ds.p, siblings, q * depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_fold_paths<<<grid_for(q, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+        dl.as<uint4>(), di.as<uint64_t>(), ds.as<uint4>(), ok ? dr.as<uint4>() : nullptr, q, depth, ctx->fmt,
+        ok ? dok.as<uint8_t>() : nullptr, roots_out ? dro.as<uint4>() : nullptr, states ? dst.as<uint4>() : nullptr, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    if (ok) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ok, dok.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (roots_out) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(roots_out, dro.p, q * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (states)
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, q * depth * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+extern "C" imt_status imt_verify_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots,
+                                        const void* siblings, size_t q, unsigned depth, uint8_t* ok) {
+    if (q && !ok) return ctx ? fail(ctx, IMT_ERR_INVALID_ARG, "null buffer") : IMT_ERR_INVALID_ARG;
+    return fold_paths(ctx, leaves, indices, roots, siblings, q, depth, ok, nullptr, nullptr);
+}
+extern "C" imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* siblings,
+                                              size_t q, unsigned depth, void* states, void* roots) {
+    return fold_paths(ctx, leaves, indices, nullptr, siblings, q, depth, nullptr, roots, states);
+}
+
+// ------------------------------------------------------------------------------------------------- sharding
+extern "C" imt_status imt_tree_subtree_root_dev(imt_tree* t, const void** d_subtree_root) {
+    if (!t || !d_subtree_root) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (ctx->fmt != kFmtMontgomery) return fail(ctx, IMT_ERR_INVALID_ARG, "device-side root exchange needs the Montgomery format");
+    *d_subtree_root = t->d_levels + level_offset(t->n, t->depth);
+    return IMT_OK;
+}
+static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const void* roots, bool device_src) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (!roots || world == 0 || (world & (world - 1)) || rank >= world) return fail(ctx, IMT_ERR_INVALID_ARG, "bad rank/world");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    t->cap_valid = false;
+    if (t->cap_alloc_world != world) {
+        if (t->d_cap) cudaFree(t->d_cap), t->d_cap = nullptr;
+        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_cap, (2 * (size_t)world - 1) * sizeof(Fr)));
+        t->cap_alloc_world = world;
+    }
+    t->rank = rank;
+    t->world = world;
+    t->cap_depth = 0;
+    while ((1u << t->cap_depth) < world) ++t->cap_depth;
+    DevBuf staged;
+    const void* d_src = roots;
+    if (!device_src) {
+        IMT_TRY_CUDA(ctx, staged.alloc(world * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, roots, world * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        d_src = staged.p;
+    }
+    IMT_TRY(clear_err(ctx));
+    k_convert<<<grid_for(world, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, (uint4*)t->d_cap, world, ctx->fmt, kFmtMontgomery,
+                                                          ctx->d_err);
+    ++ctx->launches;
+    for (unsigned l = 0; l < t->cap_depth; ++l)
+        IMT_TRY(launch_hash<2>(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1),
+                               kFmtMontgomery, kFmtMontgomery, ctx->stream));
+    IMT_TRY(finish(ctx));
+    t->cap_valid = true;
+    return IMT_OK;
+}
+extern "C" imt_status imt_tree_attach_cap(imt_tree* t, unsigned rank, unsigned world, const void* roots) {
+    return attach_cap(t, rank, world, roots, false);
+}
+extern "C" imt_status imt_tree_attach_cap_dev(imt_tree* t, unsigned rank, unsigned world, const void* d_roots) {
+    return attach_cap(t, rank, world, d_roots, true);
+}
+
+// ------------------------------------------------------------------------------------------------- calibration
+extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_mac_per_s, double* sm_clock_mhz) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    IMT_TRY_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    DevBuf out, cyc;
+    IMT_TRY_CUDA(ctx, out.alloc((size_t)blocks * threads * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, cyc.alloc(sizeof(long long)));
+    cudaEvent_t e0, e1;
+    IMT_TRY_CUDA(ctx, cudaEventCreate(&e0));
+    IMT_TRY_CUDA(ctx, cudaEventCreate(&e1));
+    int iters = 2000;
+    float t_ms = 0.f;
+    long long cycles = 0;
+    for (int round = 0; round < 6; ++round) {  // grow the loop until one launch lasts long enough to time
+        cudaEventRecord(e0, ctx->stream);
+        k_imad_probe<<<blocks, threads, 0, ctx->stream>>>(out.as<uint64_t>(), 12345u + round, iters, cyc.as<long long>());
+        ++ctx->launches;
+        cudaEventRecord(e1, ctx->stream);
+        IMT_TRY_CUDA(ctx, cudaEventSynchronize(e1));
+        IMT_TRY_CUDA(ctx, cudaEventElapsedTime(&t_ms, e0, e1));
+        IMT_TRY_CUDA(ctx, cudaMemcpy(&cycles, cyc.p, sizeof(long long), cudaMemcpyDeviceToHost));
+        if (round > 0 && t_ms >= ms) break;
+        if (t_ms < ms) iters = (int)(iters * (t_ms > 0.05 ? (ms / t_ms) * 1.2 : 8.0)) + 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double macs = (double)blocks * threads * (double)iters * 64.0;
+    if (wide_mac_per_s) *wide_mac_per_s = macs / (t_ms * 1e-3);
+    // 8 resident blocks per SM run concurrently, so block 0's cycle count spans (almost) the whole launch
+    if (sm_clock_mhz) *sm_clock_mhz = (double)cycles / (t_ms * 1e-3) / 1e6;
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- indexed-leaf logic
+#include "imt_indexed.inl"

@@ -1,0 +1,250 @@
+// sm_100a kernels for the Poseidon / indexed-Merkle-tree hot path. One thread = one hash (two permutations,
+// ~138k IMAD-pipe instructions); the integer-multiply pipe is the bound, HBM is ~500x away (96-128 B per hash),
+// so the memory side only needs vectorised 128-bit accesses. See DESIGN.md for the per-kernel rooflines.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "poseidon.cuh"
+
+namespace imt {
+
+__constant__ PoseidonParams c_params;
+
+constexpr int kFmtCanonical = 0;
+constexpr int kFmtMontgomery = 1;
+constexpr int kHashThreads = 128;
+
+__device__ __forceinline__ void load_fe(uint32_t* x, const uint4* p) {
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
+    x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+}
+__device__ __forceinline__ void store_fe(uint4* p, const uint32_t* x) {
+    p[0] = make_uint4(x[0], x[1], x[2], x[3]);
+    p[1] = make_uint4(x[4], x[5], x[6], x[7]);
+}
+// user format -> Montgomery (semi-reduced). Returns false when the input is not < p.
+__device__ __forceinline__ bool ingest(uint32_t* x, int fmt) {
+    const bool ok = is_canonical(x);
+    if (fmt == kFmtCanonical) to_mont(x, x);
+    return ok;
+}
+// Montgomery canonical -> user format
+__device__ __forceinline__ void egress(uint32_t* x, int fmt) {
+    if (fmt == kFmtCanonical) from_mont(x, x);
+}
+
+// out[i] = H(in[ARITY*i .. ARITY*i + ARITY)). in_fmt/out_fmt select canonical <-> Montgomery conversion at the
+// edges; tree levels are Montgomery on both sides.
+template <int ARITY>
+__global__ void __launch_bounds__(kHashThreads) k_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
+                                                       int in_fmt, int out_fmt, uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[ARITY][8], d[8];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < ARITY; ++j) {
+        load_fe(x[j], in + 2 * (ARITY * i + j));
+        ok &= ingest(x[j], in_fmt);
+    }
+    if (!ok) atomicOr(err, 1u);
+    NoTrace nt;
+    hash_fixed<ARITY>(d, x, c_params, nt);
+    egress(d, out_fmt);
+    store_fe(out + 2 * i, d);
+}
+
+// Writes every traced state as 3 FE in the user format. One thread owns one hash: 132 x 96 contiguous bytes.
+struct TraceSink {
+    uint4* dst;
+    int fmt;
+    __device__ __forceinline__ void emit(const uint32_t (*s)[8]) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            uint32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = s[j][i];
+            if (fmt == kFmtCanonical) from_mont(t, t);
+            else canonicalize(t);
+            store_fe(dst, t);
+            dst += 2;
+        }
+    }
+};
+
+template <int ARITY>
+__global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __restrict__ in, uint4* __restrict__ states,
+                                                             uint4* __restrict__ digests, size_t n, int fmt,
+                                                             uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[ARITY][8], d[8];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < ARITY; ++j) {
+        load_fe(x[j], in + 2 * (ARITY * i + j));
+        ok &= ingest(x[j], fmt);
+    }
+    if (!ok) atomicOr(err, 1u);
+    if (states) {
+        TraceSink sink{states + i * (size_t)(kStatesPerHash * 3 * 2), fmt};
+        hash_fixed<ARITY>(d, x, c_params, sink);
+    } else {
+        NoTrace nt;
+        hash_fixed<ARITY>(d, x, c_params, nt);
+    }
+    egress(d, fmt);
+    if (digests) store_fe(digests + 2 * i, d);
+}
+
+// FE offset of level `lvl` inside the concatenated level buffer of an n-leaf tree (n a power of two)
+__host__ __device__ __forceinline__ size_t level_offset(size_t n, unsigned lvl) { return 2 * n - 2 * (n >> lvl); }
+
+// Batched get_proof: one thread per (query, level). For a sharded tree the top `cap_depth` levels come from the
+// replicated cap (built over the gathered subtree roots) and `rank` locates this subtree inside it.
+__global__ void k_gather_proofs(const uint4* __restrict__ levels, const uint4* __restrict__ cap, size_t n_local,
+                                unsigned depth_local, unsigned cap_depth, unsigned rank, const uint64_t* __restrict__ idx,
+                                size_t q, int fmt, uint4* __restrict__ siblings, uint8_t* __restrict__ helpers,
+                                uint4* __restrict__ helpers_fe, uint32_t* __restrict__ err) {
+    const unsigned depth = depth_local + cap_depth;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= q * depth) return;
+    const size_t qi = t / depth;
+    const unsigned lvl = (unsigned)(t % depth);
+    const uint64_t g = idx[qi];
+    const uint64_t base = (uint64_t)rank * n_local;
+    if (g < base || g >= base + n_local) {
+        atomicOr(err, 2u);
+        return;
+    }
+    const uint64_t local = g - base;
+    uint32_t x[8];
+    unsigned left;
+    if (lvl < depth_local) {
+        const uint64_t node = local >> lvl;
+        left = (node & 1) == 0;
+        load_fe(x, levels + 2 * (level_offset(n_local, lvl) + (node ^ 1)));
+    } else {
+        const unsigned cl = lvl - depth_local;
+        const uint64_t node = (uint64_t)rank >> cl;
+        left = (node & 1) == 0;
+        load_fe(x, cap + 2 * (level_offset((size_t)1 << cap_depth, cl) + (node ^ 1)));
+    }
+    egress(x, fmt);
+    store_fe(siblings + 2 * t, x);
+    if (helpers) helpers[t] = (uint8_t)left;
+    if (helpers_fe) {
+        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (left) {
+            if (fmt == kFmtCanonical) h[0] = 1;
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = c_params.one.l[i];
+            }
+        }
+        store_fe(helpers_fe + 2 * t, h);
+    }
+}
+
+// Batched verify_proof / compute_merkle_root: one thread folds one path. With `states` it also writes the
+// witness trace of every hash of the fold.
+__global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __restrict__ leaves, const uint64_t* __restrict__ idx,
+                                                             const uint4* __restrict__ siblings, const uint4* __restrict__ roots,
+                                                             size_t q, unsigned depth, int fmt, uint8_t* __restrict__ ok_out,
+                                                             uint4* __restrict__ roots_out, uint4* __restrict__ states,
+                                                             uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= q) return;
+    uint32_t x[2][8], h[8];
+    load_fe(h, leaves + 2 * i);
+    bool ok = ingest(h, fmt);
+    uint64_t index = idx[i];
+#pragma unroll 1
+    for (unsigned l = 0; l < depth; ++l) {
+        uint32_t s[8];
+        load_fe(s, siblings + 2 * (i * depth + l));
+        ok &= ingest(s, fmt);
+        const bool left = (index & 1) == 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[0][k] = left ? h[k] : s[k];
+            x[1][k] = left ? s[k] : h[k];
+        }
+        if (states) {
+            TraceSink sink{states + (i * depth + l) * (size_t)(kStatesPerHash * 3 * 2), fmt};
+            hash_fixed<2>(h, x, c_params, sink);
+        } else {
+            NoTrace nt;
+            hash_fixed<2>(h, x, c_params, nt);
+        }
+        index >>= 1;
+    }
+    if (!ok) atomicOr(err, 1u);
+    canonicalize(h);  // depth 0: the leaf itself, possibly semi-reduced after ingest
+    if (ok_out) {
+        uint32_t r[8];
+        load_fe(r, roots + 2 * i);
+        ok &= ingest(r, fmt);
+        canonicalize(r);
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) same &= r[k] == h[k];
+        ok_out[i] = (uint8_t)same;
+    }
+    if (roots_out) {
+        egress(h, fmt);
+        store_fe(roots_out + 2 * i, h);
+    }
+}
+
+// Format conversion of a dense FE array (used for roots / levels / preimages crossing the boundary)
+__global__ void k_convert(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int from_fmt, int to_fmt,
+                          uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[8];
+    load_fe(x, in + 2 * i);
+    if (!is_canonical(x)) atomicOr(err, 1u);
+    if (from_fmt != to_fmt) {
+        if (to_fmt == kFmtMontgomery) {
+            to_mont(x, x);
+            canonicalize(x);
+        } else {
+            from_mont(x, x);
+        }
+    }
+    store_fe(out + 2 * i, x);
+}
+
+// Integer-multiply roofline probe: 8 independent 32x32+64 multiply-accumulate chains per thread.
+__global__ void __launch_bounds__(256) k_imad_probe(uint64_t* __restrict__ out, uint32_t seed, int iters, long long* cycles) {
+    uint64_t acc[8];
+    uint32_t a[8];
+    const uint32_t b = seed * 2654435761u + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] = (uint64_t)seed + j;
+        a[j] = seed + 977u * j + blockIdx.x;
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(b));
+                a[j] = (uint32_t)acc[j];  // the multiplier follows the accumulator: the product is not loop invariant
+            }
+        }
+    }
+    const long long t1 = clock64();
+    uint64_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x ^= acc[j];
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = t1 - t0;
+}
+
+}  // namespace imt

@@ -1,0 +1,299 @@
+"""Batched, numpy-facing wrapper of the C-ABI: Engine (one context = one GPU) and Tree (device-resident levels).
+
+Field elements are rows of 4 little-endian uint64 words (32 bytes) in the engine's format (canonical by default).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+
+P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+STATES_PER_HASH = 132
+
+
+class ImtError(Exception):
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _fe_array(a, inner):
+    """contiguous uint64 array whose trailing dims are `inner` + (4,)"""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape((-1,) + tuple(inner) + (4,))
+
+
+def fe_from_int(x):
+    x = int(x)
+    if not 0 <= x < (1 << 256):
+        raise ValueError("field element out of range")
+    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def fe_to_int(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(a[i]) << (64 * i) for i in range(4))
+
+
+def fes_from_ints(xs):
+    return np.stack([fe_from_int(x) for x in xs]) if len(xs) else np.zeros((0, 4), np.uint64)
+
+
+def fes_to_ints(a):
+    return [fe_to_int(r) for r in np.asarray(a, dtype=np.uint64).reshape(-1, 4)]
+
+
+def _dev_ptr(t):
+    """device pointer of a torch CUDA tensor (or a raw int)"""
+    if isinstance(t, int):
+        return ctypes.c_void_p(t)
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One imt_ctx: Poseidon::<Fr,3,2>::new(8,57) + a GPU. Not thread-safe (mirrors the reference's &mut hasher)."""
+
+    def __init__(self, device=0, fmt="canonical"):
+        self._lib = _ffi.load()
+        self.fmt = {"canonical": _ffi.FE_CANONICAL, "montgomery": _ffi.FE_MONTGOMERY}[fmt]
+        h = ctypes.c_void_p()
+        st = self._lib.imt_ctx_create(int(device), self.fmt, ctypes.byref(h))
+        if st != _ffi.OK:
+            raise ImtError(st, f"imt_ctx_create(device={device}) failed with status {st}: a CUDA device is required, "
+                               "there is no CPU fallback")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.imt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != _ffi.OK:
+            msg = self._lib.imt_last_error(self._h).decode() or self._lib.imt_status_string(st).decode()
+            raise ImtError(st, msg)
+
+    @property
+    def launches(self):
+        return int(self._lib.imt_ctx_launch_count(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        """launch on a caller-owned cudaStream_t (int; 0/None = the engine's own stream)"""
+        self._check(self._lib.imt_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def enable_timing(self, on=True):
+        self._check(self._lib.imt_ctx_enable_timing(self._h, 1 if on else 0))
+
+    def reset_timing(self):
+        self._check(self._lib.imt_ctx_reset_timing(self._h))
+
+    def kernel_time(self, arity):
+        """(total device ms, launches, hashes) of the hash kernels of this arity since the last reset"""
+        ms, ln, hs = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._lib.imt_ctx_kernel_time(self._h, arity, ctypes.byref(ms), ctypes.byref(ln), ctypes.byref(hs)))
+        return ms.value, ln.value, hs.value
+
+    # ---- batched hashing
+    def hash2(self, pairs):
+        a = _fe_array(pairs, (2,))
+        out = np.empty((a.shape[0], 4), np.uint64)
+        self._check(self._lib.imt_poseidon_hash2(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def hash3(self, triples):
+        a = _fe_array(triples, (3,))
+        out = np.empty((a.shape[0], 4), np.uint64)
+        self._check(self._lib.imt_poseidon_hash3(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def hash2_dev(self, d_in, n, d_out):
+        self._check(self._lib.imt_poseidon_hash2_dev(self._h, _dev_ptr(d_in), n, _dev_ptr(d_out)))
+
+    def hash3_dev(self, d_in, n, d_out):
+        self._check(self._lib.imt_poseidon_hash3_dev(self._h, _dev_ptr(d_in), n, _dev_ptr(d_out)))
+
+    def trace_hashes(self, inputs, arity, want_states=True):
+        a = _fe_array(inputs, (arity,))
+        n = a.shape[0]
+        states = np.empty((n, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
+        digests = np.empty((n, 4), np.uint64)
+        self._check(self._lib.imt_trace_hashes(self._h, _ptr(a), arity, n, _ptr(states), _ptr(digests)))
+        return digests, states
+
+    def trace_hashes_dev(self, d_in, arity, n, d_states, d_digests):
+        self._check(self._lib.imt_trace_hashes_dev(self._h, _dev_ptr(d_in), arity, n,
+                                                   _dev_ptr(d_states) if d_states is not None else None,
+                                                   _dev_ptr(d_digests) if d_digests is not None else None))
+
+    # ---- trees
+    def _tree(self, fn, buf, n):
+        h = ctypes.c_void_p()
+        self._check(fn(self._h, buf, n, ctypes.byref(h)))
+        return Tree(self, h)
+
+    def build_from_hashes(self, leaf_hashes):
+        a = _fe_array(leaf_hashes, ())
+        return self._tree(self._lib.imt_tree_build_from_hashes, _ptr(a), a.shape[0])
+
+    def build_from_leaves(self, preimages):
+        a = _fe_array(preimages, (3,))
+        return self._tree(self._lib.imt_tree_build_from_leaves, _ptr(a), a.shape[0])
+
+    def build_from_leaves_dev(self, d_preimages, n):
+        return self._tree(self._lib.imt_tree_build_from_leaves_dev, _dev_ptr(d_preimages), n)
+
+    def build_from_hashes_dev(self, d_hashes, n):
+        return self._tree(self._lib.imt_tree_build_from_hashes_dev, _dev_ptr(d_hashes), n)
+
+    # ---- path folding
+    def verify_proofs(self, leaves, indices, roots, siblings):
+        lv = _fe_array(leaves, ())
+        q = lv.shape[0]
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(q)
+        sib = _fe_array(siblings, ()).reshape(q, -1, 4) if q else np.zeros((0, 0, 4), np.uint64)
+        depth = sib.shape[1]
+        rt = _fe_array(roots, ())
+        if rt.shape[0] == 1 and q != 1:
+            rt = np.ascontiguousarray(np.broadcast_to(rt, (q, 4)))
+        ok = np.zeros(q, np.uint8)
+        self._check(self._lib.imt_verify_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(rt), _ptr(sib), q, depth, _ptr(ok)))
+        return ok.astype(bool)
+
+    def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True):
+        lv = _fe_array(leaves, ())
+        q = lv.shape[0]
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(q)
+        sib = _fe_array(siblings, ()).reshape(q, -1, 4)
+        depth = sib.shape[1]
+        states = np.empty((q, depth, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
+        roots = np.empty((q, 4), np.uint64)
+        self._check(self._lib.imt_trace_merkle_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(sib), q, depth, _ptr(states), _ptr(roots)))
+        return roots, states
+
+    def calibrate_imad(self, ms=200.0):
+        rate, mhz = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.imt_calibrate_imad(self._h, float(ms), ctypes.byref(rate), ctypes.byref(mhz)))
+        return rate.value, mhz.value
+
+
+class Tree:
+    """imt_tree: every level of the tree, resident on the GPU (utils.rs:5-10's `tree: Vec<Vec<F>>`)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self._lib = engine._lib
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.imt_tree_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_leaves(self):
+        return int(self._lib.imt_tree_num_leaves(self._h))
+
+    @property
+    def depth(self):
+        return int(self._lib.imt_tree_depth(self._h))
+
+    def root(self):
+        out = np.empty(4, np.uint64)
+        self.engine._check(self._lib.imt_tree_root(self._h, _ptr(out)))
+        return out
+
+    def root_dev(self, d_out):
+        self.engine._check(self._lib.imt_tree_root_dev(self._h, _dev_ptr(d_out)))
+
+    def attach_cap_dev(self, rank, world, d_roots):
+        self.engine._check(self._lib.imt_tree_attach_cap_dev(self._h, rank, world, _dev_ptr(d_roots)))
+
+    def level(self, lvl, count):
+        out = np.empty((count, 4), np.uint64)
+        self.engine._check(self._lib.imt_tree_level(self._h, lvl, _ptr(out)))
+        return out
+
+    def preimages(self, n_local):
+        out = np.empty((n_local, 3, 4), np.uint64)
+        self.engine._check(self._lib.imt_tree_preimages(self._h, _ptr(out)))
+        return out
+
+    def rebuild_from_leaves(self, preimages):
+        a = _fe_array(preimages, (3,))
+        self.engine._check(self._lib.imt_tree_rebuild_from_leaves(self._h, _ptr(a)))
+
+    def rebuild_from_leaves_ptr(self, host_ptr):
+        """host pointer (e.g. a pinned torch tensor's data_ptr()) to n x 3 FE"""
+        self.engine._check(self._lib.imt_tree_rebuild_from_leaves(self._h, ctypes.c_void_p(host_ptr)))
+
+    def rebuild_from_leaves_dev(self, d_preimages):
+        self.engine._check(self._lib.imt_tree_rebuild_from_leaves_dev(self._h, _dev_ptr(d_preimages)))
+
+    def get_proofs(self, indices, helpers_as_fe=False):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q, d = idx.shape[0], self.depth
+        sib = np.empty((q, d, 4), np.uint64)
+        if helpers_as_fe:
+            hel = np.empty((q, d, 4), np.uint64)
+            self.engine._check(self._lib.imt_tree_get_proofs_fe(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
+        else:
+            hel = np.empty((q, d), np.uint8)
+            self.engine._check(self._lib.imt_tree_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
+        return sib, hel
+
+    def low_leaf_lookup(self, values):
+        v = _fe_array(values, ())
+        q = v.shape[0]
+        low = np.empty(q, np.uint64)
+        matched = np.empty(q, np.uint8)
+        self.engine._check(self._lib.imt_low_leaf_lookup(self._h, _ptr(v), q, _ptr(low), _ptr(matched)))
+        return low, matched.astype(bool)
+
+    def non_inclusion_paths(self, values):
+        v = _fe_array(values, ())
+        q, d = v.shape[0], self.depth
+        o = dict(low_idx=np.empty(q, np.uint64), matched=np.empty(q, np.uint8), low_leaves=np.empty((q, 3, 4), np.uint64),
+                 siblings=np.empty((q, d, 4), np.uint64), helpers=np.empty((q, d), np.uint8), is_largest=np.empty(q, np.uint8))
+        self.engine._check(self._lib.imt_non_inclusion_paths(self._h, _ptr(v), q, _ptr(o["low_idx"]), _ptr(o["matched"]),
+                                                             _ptr(o["low_leaves"]), _ptr(o["siblings"]), _ptr(o["helpers"]),
+                                                             _ptr(o["is_largest"])))
+        return o
+
+    def insert_batch(self, new_vals, first_idx):
+        v = _fe_array(new_vals, ())
+        b, d = v.shape[0], self.depth
+        o = dict(old_roots=np.empty((b, 4), np.uint64), low_idx=np.empty(b, np.uint64), low_leaves=np.empty((b, 3, 4), np.uint64),
+                 low_siblings=np.empty((b, d, 4), np.uint64), low_helpers=np.empty((b, d), np.uint8),
+                 new_roots=np.empty((b, 4), np.uint64), new_leaves=np.empty((b, 3, 4), np.uint64),
+                 new_siblings=np.empty((b, d, 4), np.uint64), new_helpers=np.empty((b, d), np.uint8), is_largest=np.empty(b, np.uint8))
+        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        self.engine._check(self._lib.imt_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
+        return o
+
+    # ---- subtree sharding
+    def attach_cap(self, rank, world, subtree_roots):
+        """after (re)building: exchange the N subtree roots (root() of each rank) and attach them here"""
+        r = _fe_array(subtree_roots, ())
+        if r.shape[0] != world:
+            raise ValueError("need one subtree root per rank")
+        self.engine._check(self._lib.imt_tree_attach_cap(self._h, rank, world, _ptr(r)))

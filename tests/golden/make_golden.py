@@ -1,0 +1,55 @@
+"""Regenerates tests/golden/golden.json from the ORACLE (oracle/imt_oracle.c + oracle/poseidon_ref.py).
+
+The reference itself cannot run here (Rust, un-vendored deps, no toolchain), so these vectors come from the oracle,
+which is pinned to the reference's single numeric known-answer (indexed_merkle_tree.rs:247-251) and cross-checked
+between two independent implementations (tests/test_oracle.py). Usage: python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+
+import numpy as np  # noqa: E402
+import oracle as O  # noqa: E402
+import poseidon_ref as R  # noqa: E402
+import imt_b200  # noqa: E402  (synthetic-input definitions only; no GPU is touched)
+from imt_b200 import synth  # noqa: E402
+
+
+def main():
+    th = O.max_threads()
+    g = {"seed": synth.DEFAULT_SEED, "kat_h3_zero": str(R.KAT_H3_ZERO)}
+    g["h2_0_0"] = str(R.hash2(0, 0))
+    g["h2_1_2"] = str(R.hash2(1, 2))
+    g["h3_1_2_3"] = str(R.hash3(1, 2, 3))
+    g["empty_depth3_root"] = str(R.IndexedMerkleTree(R.hash_preimages([[0, 0, 0]] * 8)).root)
+    rounds, pre = R.insert_rounds(3, [30, 10, 20, 5, 50, 35])
+    g["scenario_inserts"] = [30, 10, 20, 5, 50, 35]
+    g["scenario_low_idx"] = [r["low_idx"] for r in rounds]
+    g["scenario_roots"] = [str(r["new_root"]) for r in rounds]
+    g["scenario_final_preimages"] = [[str(v) for v in leaf] for leaf in pre]
+    # first and last state of the H3(0,0,0) trace and a checksum of all 132
+    d, tr = R.hash_trace([0, 0, 0])
+    g["trace_h3_zero_first"] = [str(v) for v in tr[0]]
+    g["trace_h3_zero_last"] = [str(v) for v in tr[-1]]
+    g["trace_h3_zero_xor"] = str(int(np.bitwise_xor.reduce([v for s in tr for v in s])) if False else __import__("functools").reduce(lambda a, b: a ^ b, [v for s in tr for v in s]))
+    roots = {}
+    for depth in (3, 10, 16, 20):
+        n = 1 << depth
+        t0 = time.time()
+        r1 = O.build_from_preimages(synth.random_preimages(n), th)
+        r2 = O.build_from_preimages(synth.indexed_preimages(n), th)
+        roots[str(depth)] = {"random": str(O.to_int(r1)), "indexed": str(O.to_int(r2))}
+        print(f"depth {depth}: {time.time() - t0:.1f}s", flush=True)
+    g["build_roots"] = roots
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(g, f, indent=1)
+    print("wrote golden.json")
+
+
+if __name__ == "__main__":
+    main()

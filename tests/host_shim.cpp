@@ -1,0 +1,74 @@
+// TEST-ONLY: compiles the product's field/Poseidon headers in HOST mode (emulated carry flag) so that the exact
+// algorithm the GPU kernels run can be checked against big-integer arithmetic without a GPU.
+// Built on demand by tests/test_host_field.py into tests/_build/; never part of the shipped library.
+#include <cstring>
+
+#include "poseidon_params.h"
+
+using namespace imt;
+
+static PoseidonParams g_params;
+static bool g_ready = false;
+static const PoseidonParams& params() {
+    if (!g_ready) {
+        poseidon_params_generate(&g_params);
+        g_ready = true;
+    }
+    return g_params;
+}
+
+extern "C" {
+void shim_params(void* out) { std::memcpy(out, &params(), sizeof(PoseidonParams)); }
+unsigned shim_params_size() { return sizeof(PoseidonParams); }
+void shim_mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul(r, a, b); }
+void shim_mont_sqr(uint32_t* r, const uint32_t* a) { mont_sqr(r, a); }
+void shim_to_mont(uint32_t* r, const uint32_t* a) { to_mont(r, a); }
+void shim_from_mont(uint32_t* r, const uint32_t* a) { from_mont(r, a); }
+void shim_add_semi(uint32_t* r, const uint32_t* a, const uint32_t* b) { add_semi(r, a, b); }
+void shim_dot3(uint32_t* r, const uint32_t* u, const uint32_t* m) { dot3(r, u, u + 8, u + 16, m, m + 8, m + 16); }
+void shim_mul_add(uint32_t* r, const uint32_t* u, const uint32_t* m, const uint32_t* s) { mul_add(r, u, m, s); }
+void shim_sqr_wide(uint32_t* out16, const uint32_t* a) {
+    Wide w;
+    wide_zero(w);
+    sqr_wide(w, a);
+    std::memcpy(out16, w.e, 64);
+}
+void shim_mul_wide_merged(uint32_t* out16, const uint32_t* a, const uint32_t* b) {
+    Wide w;
+    wide_zero(w);
+    mul_wide(w, a, b);
+    uint64_t c = 0;
+    for (int pos = 0; pos < 16; ++pos) {
+        c += (uint64_t)w.e[pos] + (pos ? w.o[pos - 1] : 0);
+        out16[pos] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+struct Collect {
+    uint32_t* dst;
+    void emit(const uint32_t (*s)[8]) {
+        for (int i = 0; i < 3; ++i) {
+            uint32_t t[8];
+            for (int j = 0; j < 8; ++j) t[j] = s[i][j];
+            from_mont(dst, t);
+            dst += 8;
+        }
+    }
+};
+// canonical in (arity x 8 words) -> canonical digest; states (132 x 3 x 8 words, canonical) optional
+void shim_hash(uint32_t* out, const uint32_t* in, int arity, uint32_t* states) {
+    uint32_t m[3][8], d[8];
+    for (int i = 0; i < arity; ++i) {
+        to_mont(m[i], in + 8 * i);
+        cond_sub_p(m[i]);
+    }
+    if (states) {
+        Collect c{states};
+        if (arity == 3) hash_fixed<3>(d, m, params(), c); else hash_fixed<2>(d, m, params(), c);
+    } else {
+        NoTrace n;
+        if (arity == 3) hash_fixed<3>(d, m, params(), n); else hash_fixed<2>(d, m, params(), n);
+    }
+    from_mont(out, d);
+}
+}

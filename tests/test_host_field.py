@@ -1,0 +1,157 @@
+"""CPU check of the PRODUCT's field / Poseidon source (csrc/fr.cuh, poseidon.cuh, poseidon_params.cpp) compiled in
+host mode, where the PTX carry primitives are emulated with a thread-local flag. It proves the algorithm the
+kernels run (even/odd wide accumulators, separate reduction, dedicated squaring, lazy [0,2p) ranges, the
+carry-flag invariant) against Python big integers — without a GPU. The emulation is test-only."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import poseidon_ref as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "indexed-merkle-tree-halo2_b200", "csrc")
+P = R.P
+RM = 1 << 256
+RINV = pow(RM, -1, P)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    out = os.path.join(ROOT, "tests", "_build", "libhost_shim.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(ROOT, "tests", "host_shim.cpp"), os.path.join(CSRC, "poseidon_params.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("fr.cuh", "poseidon.cuh", "poseidon_params.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, "-x", "c++", *srcs, "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+def w(x, n=8):
+    return np.array([(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)], dtype=np.uint32)
+
+
+def iv(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+def p_(a):
+    return a.ctypes.data_as(u32p)
+
+
+EDGE = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P - 2, 0xFFFFFFFF, (1 << 255) % (2 * P), int("ffffffff" * 8, 16) % (2 * P)]
+
+
+def rnd(rng):
+    r = rng.random()
+    if r < 0.2:
+        return rng.choice(EDGE)
+    if r < 0.35:
+        v = 0
+        for i in range(8):
+            v |= rng.choice([0, 0xFFFFFFFF, rng.getrandbits(32)]) << (32 * i)
+        return v % (2 * P)
+    return rng.randrange(2 * P)
+
+
+def test_field_ops_semi_reduced(shim):
+    rng = random.Random(7)
+    r = np.zeros(8, np.uint32)
+    o = np.zeros(16, np.uint32)
+    for _ in range(6000):
+        a, b = rnd(rng), rnd(rng)
+        A, B = w(a), w(b)
+        shim.shim_mont_mul(p_(r), p_(A), p_(B))
+        v = iv(r)
+        assert v % P == a * b * RINV % P and v < 2 * P
+        shim.shim_mont_sqr(p_(r), p_(A))
+        v = iv(r)
+        assert v % P == a * a * RINV % P and v < 2 * P
+        shim.shim_add_semi(p_(r), p_(A), p_(B))
+        v = iv(r)
+        assert v % P == (a + b) % P and v < 2 * P
+        u = [rnd(rng) for _ in range(3)]
+        m = [rng.choice([P - 1, rng.randrange(P)]) for _ in range(3)]
+        U = np.concatenate([w(x) for x in u])
+        M = np.concatenate([w(x) for x in m])
+        shim.shim_dot3(p_(r), p_(U), p_(M))
+        v = iv(r)
+        assert v % P == sum(x * y for x, y in zip(u, m)) * RINV % P and v < 2 * P
+        s = rnd(rng)
+        shim.shim_mul_add(p_(r), p_(w(u[0])), p_(w(m[0])), p_(w(s)))
+        v = iv(r)
+        assert v % P == (u[0] * m[0] * RINV + s) % P and v < 2 * P
+
+
+def test_wide_products_full_range(shim):
+    rng = random.Random(11)
+    o = np.zeros(16, np.uint32)
+    full = (1 << 256) - 1
+    cases = [(full, full), (full, 1), (0, full), (1 << 255, 1 << 255)]
+    for _ in range(4000):
+        cases.append((rng.getrandbits(256), rng.choice([rng.getrandbits(256), full, rng.getrandbits(32) << 224])))
+    for a, b in cases:
+        shim.shim_mul_wide_merged(p_(o), p_(w(a)), p_(w(b)))
+        assert iv(o) == a * b
+        shim.shim_sqr_wide(p_(o), p_(w(b)))
+        assert iv(o) == b * b
+
+
+def test_montgomery_conversions(shim):
+    rng = random.Random(3)
+    r = np.zeros(8, np.uint32)
+    for x in [0, 1, P - 1] + [rng.randrange(P) for _ in range(500)]:
+        shim.shim_to_mont(p_(r), p_(w(x)))
+        m = iv(r)
+        assert m % P == x * RM % P
+        shim.shim_from_mont(p_(r), p_(w(m)))
+        assert iv(r) == x
+
+
+def test_params_match_reference_derivation(shim):
+    sz = shim.shim_params_size()
+    buf = np.zeros(sz // 4, np.uint32)
+    shim.shim_params(p_(buf))
+    sp = R.spec()
+    exp = []
+    for r_ in range(3):
+        exp += sp.start[r_ + 1]
+    exp += sp.start[4]
+    for r_ in range(3):
+        exp += sp.end[r_]
+    exp += [0, 0, 0]
+    exp += sp.start[0]
+    for row in sp.mds:
+        exp += row
+    for row in sp.pre_sparse:
+        exp += row
+    for k in range(57):
+        exp += [sp.partial[k]] + list(sp.sparse[k][0]) + list(sp.sparse[k][1])
+    exp += [1 << 64, 1]
+    assert sz == 32 * len(exp)
+    got = [iv(buf[8 * i:8 * i + 8]) for i in range(len(exp))]
+    assert all(g < P for g in got)  # canonical Montgomery
+    assert [g * RINV % P for g in got] == exp
+
+
+def test_hash_and_trace(shim):
+    rng = random.Random(5)
+    cases = [(3, [0, 0, 0]), (2, [0, 0]), (2, [1, 2]), (3, [1, 2, 3]), (2, [P - 1, P - 2]), (3, [P - 1] * 3)]
+    cases += [(3, [rng.randrange(P) for _ in range(3)]) for _ in range(3)] + [(2, [rng.randrange(P) for _ in range(2)]) for _ in range(3)]
+    for ar, x in cases:
+        I = np.concatenate([w(v) for v in x])
+        out = np.zeros(8, np.uint32)
+        st = np.zeros(132 * 3 * 8, np.uint32)
+        shim.shim_hash(p_(out), p_(I), ar, p_(st))
+        d, tr = R.hash_trace(x)
+        assert iv(out) == d
+        assert [iv(st[8 * i:8 * i + 8]) for i in range(396)] == [v for s_ in tr for v in s_]
+        shim.shim_hash(p_(out), p_(I), ar, None)
+        assert iv(out) == d
+    I = np.concatenate([w(0)] * 3)
+    shim.shim_hash(p_(out), p_(I), 3, None)
+    assert iv(out) == R.KAT_H3_ZERO  # /root/reference/src/indexed_merkle_tree.rs:247-251
