@@ -256,8 +256,8 @@ def main():
     roofline = {
         "bound": "imad", "kernel": "k_hash<3> (leaf hashing)", "achieved": achieved / 1e9, "peak": imad_rate / 1e9, "unit": "GMAC/s",
         "frac": achieved / imad_rate if imad_rate else None, "traffic": None,
-        "peak_source": f"calibrated in this run: independent IMAD.WIDE.U32 chains on all SMs (imt_calibrate_imad), SM clock {imad_mhz:.0f} MHz; "
-                       "MEASURED_PEAKS.json has no integer peak",
+        "peak_source": f"calibrated in this run: IMAD.WIDE.U32.X carry chains saturating all SMs (imt_calibrate_imad); = 32 wide MACs/clk/SM at "
+                       f"{imad_mhz:.0f} MHz. MEASURED_PEAKS.json has no integer peak",
         "algorithmic_macs_per_hash": MACS_PER_HASH, "kernel_ms_per_launch": k3_per_launch_ms,
         "kernel_share_of_step": (k3_ms / a.steps) / (ms_total / a.steps) if ms_total else None,
         "node_kernel_ms_per_step": k2_ms / a.steps, "node_kernel_launches_per_step": k2_launches / a.steps,

@@ -172,8 +172,10 @@ imt_status imt_tree_attach_cap(imt_tree* tree, unsigned rank, unsigned world, co
 imt_status imt_tree_attach_cap_dev(imt_tree* tree, unsigned rank, unsigned world, const void* d_subtree_roots);
 
 /* ---------------------------------------------------------------- calibration -------------------------------- */
-/* Integer-multiply roofline calibration: runs independent IMAD.WIDE.U32 chains on every SM for about `ms`
- * milliseconds and returns sustained 32x32->64 multiply-accumulates per second (and the SM clock seen). */
+/* Integer-multiply roofline calibration: saturates every SM with IMAD.WIDE.U32.X carry chains (the instruction the
+ * field arithmetic issues) for about `ms` milliseconds per launch and returns the sustained 32x32->64
+ * multiply-accumulates per second; implied_clock_mhz = rate / (32 lanes x SMs), i.e. the SM clock this rate
+ * corresponds to if the pipe retires its nominal 32 wide MACs per clock per SM. */
 imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_mac_per_s, double* sm_clock_mhz);
 
 #ifdef __cplusplus

@@ -673,33 +673,37 @@ extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_m
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     IMT_TRY_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    DevBuf out, cyc;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;  // 64 resident warps per SM
+    DevBuf out;
     IMT_TRY_CUDA(ctx, out.alloc((size_t)blocks * threads * sizeof(uint64_t)));
-    IMT_TRY_CUDA(ctx, cyc.alloc(sizeof(long long)));
     cudaEvent_t e0, e1;
     IMT_TRY_CUDA(ctx, cudaEventCreate(&e0));
     IMT_TRY_CUDA(ctx, cudaEventCreate(&e1));
     int iters = 2000;
-    float t_ms = 0.f;
-    long long cycles = 0;
-    for (int round = 0; round < 6; ++round) {  // grow the loop until one launch lasts long enough to time
+    float t_ms = 0.f, best_ms = 0.f;
+    int best_iters = iters;
+    for (int round = 0; round < 8; ++round) {  // grow the loop until one launch lasts `ms`, then keep the best of 3
         cudaEventRecord(e0, ctx->stream);
-        k_imad_probe<<<blocks, threads, 0, ctx->stream>>>(out.as<uint64_t>(), 12345u + round, iters, cyc.as<long long>());
+        k_imad_probe<<<blocks, threads, 0, ctx->stream>>>(out.as<uint64_t>(), 12345u + round, iters);
         ++ctx->launches;
         cudaEventRecord(e1, ctx->stream);
         IMT_TRY_CUDA(ctx, cudaEventSynchronize(e1));
         IMT_TRY_CUDA(ctx, cudaEventElapsedTime(&t_ms, e0, e1));
-        IMT_TRY_CUDA(ctx, cudaMemcpy(&cycles, cyc.p, sizeof(long long), cudaMemcpyDeviceToHost));
-        if (round > 0 && t_ms >= ms) break;
-        if (t_ms < ms) iters = (int)(iters * (t_ms > 0.05 ? (ms / t_ms) * 1.2 : 8.0)) + 1;
+        if (t_ms >= ms * 0.8) {
+            if (best_ms == 0.f || t_ms / iters < best_ms / best_iters) best_ms = t_ms, best_iters = iters;
+            if (round >= 4) break;
+        } else {
+            iters = (int)(iters * (t_ms > 0.05 ? (ms / t_ms) * 1.1 : 8.0)) + 1;
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    const double macs = (double)blocks * threads * (double)iters * 64.0;
-    if (wide_mac_per_s) *wide_mac_per_s = macs / (t_ms * 1e-3);
-    // 8 resident blocks per SM run concurrently, so block 0's cycle count spans (almost) the whole launch
-    if (sm_clock_mhz) *sm_clock_mhz = (double)cycles / (t_ms * 1e-3) / 1e6;
+    if (best_ms == 0.f) best_ms = t_ms, best_iters = iters;
+    const double macs = (double)blocks * threads * (double)best_iters * 64.0;
+    const double rate = macs / (best_ms * 1e-3);
+    if (wide_mac_per_s) *wide_mac_per_s = rate;
+    // the pipe issues one IMAD.WIDE per 4 cycles per SM sub-partition = 32 lanes per clock per SM: the clock this rate implies
+    if (sm_clock_mhz) *sm_clock_mhz = rate / (32.0 * prop.multiProcessorCount) / 1e6;
     return IMT_OK;
 }
 

@@ -217,34 +217,31 @@ __global__ void k_convert(const uint4* __restrict__ in, uint4* __restrict__ out,
     store_fe(out + 2 * i, x);
 }
 
-// Integer-multiply roofline probe: 8 independent 32x32+64 multiply-accumulate chains per thread.
-__global__ void __launch_bounds__(256) k_imad_probe(uint64_t* __restrict__ out, uint32_t seed, int iters, long long* cycles) {
-    uint64_t acc[8];
-    uint32_t a[8];
+// Integer-multiply roofline probe: the exact instruction form the field arithmetic issues — IMAD.WIDE.U32.X, each
+// one accumulating a 32x32->64 product into a 64-bit register pair with the carry chained through the flag — as one
+// long dependent chain per thread. With enough resident warps this saturates the multiply pipe: it measures the
+// sustained wide multiply-accumulates per second that ANY schedule of such instructions can reach on this chip.
+__global__ void __launch_bounds__(256) k_imad_probe(uint64_t* __restrict__ out, uint32_t seed, int iters) {
+    uint32_t lo[8], hi[8];
     const uint32_t b = seed * 2654435761u + threadIdx.x;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        acc[j] = (uint64_t)seed + j;
-        a[j] = seed + 977u * j + blockIdx.x;
+        lo[j] = seed + 977u * j + blockIdx.x;
+        hi[j] = j;
     }
-    const long long t0 = clock64();
+    cc::clear();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < 8; ++rep) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(b));
-                a[j] = (uint32_t)acc[j];  // the multiplier follows the accumulator: the product is not loop invariant
-            }
+            for (int j = 0; j < 8; ++j) cc::madwc_cc(lo[j], hi[j], lo[(j + 3) & 7], b);  // multiplier varies: nothing is loop invariant
         }
     }
-    const long long t1 = clock64();
     uint64_t x = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x ^= acc[j];
+    for (int j = 0; j < 8; ++j) x ^= ((uint64_t)hi[j] << 32) | lo[j];
     out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = t1 - t0;
 }
 
 }  // namespace imt
