@@ -134,6 +134,8 @@ imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint6
  * returns index 0 and leaves the leaves unchanged. Requires a tree built from leaves whose occupied slots form a
  * prefix and a consistent sorted linked list (IMT_ERR_NOT_WELL_FORMED otherwise). */
 imt_status imt_low_leaf_lookup(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched);
+/* Number of occupied slots (they form the prefix [0, occupied)): the slot the next insert goes to (IMT:733). */
+imt_status imt_tree_occupied(imt_tree* tree, size_t* occupied);
 /* Non-inclusion witnesses for verify_non_inclusion (src/indexed_merkle_tree.rs:127-137): lookup + the low leaf's
  * preimage (3 FE), its path, and is_largest = (low.next_val == 0). Any output pointer may be NULL. */
 imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
@@ -144,7 +146,9 @@ imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q,
  * rebuild. Insert i puts new_vals[i] into slot first_idx + i. Outputs (any may be NULL), per insert:
  *   old_roots FE, low_idx u64, low_leaves 3 FE (OLD preimage), low_siblings depth FE + low_helpers (OLD tree),
  *   new_roots FE, new_leaves 3 FE, new_siblings depth FE + new_helpers (NEW tree), is_largest u8.
- * The tree is updated in place. */
+ * first_idx must equal imt_tree_occupied(). The batch is validated first (IMT_ERR_INVALID_ARG for a value that is 0,
+ * already in the tree or repeated; IMT_ERR_TREE_FULL): on a validation error nothing is modified. The tree, its
+ * preimages and its sorted index are updated in place. */
 typedef struct imt_insert_witness {
     void* old_roots;
     uint64_t* low_idx;

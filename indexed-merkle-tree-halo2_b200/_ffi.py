@@ -57,6 +57,7 @@ SIGNATURES = {
     "imt_verify_proofs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "imt_trace_merkle_proofs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
     "imt_low_leaf_lookup": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_tree_occupied": (c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
     "imt_non_inclusion_paths": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "imt_insert_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, ctypes.POINTER(InsertWitness)]),
     "imt_tree_subtree_root_dev": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),

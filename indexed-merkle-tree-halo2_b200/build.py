@@ -7,8 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
-SOURCES = ["imt_capi.cu", "poseidon_params.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "poseidon.cuh", "fr.cuh", "poseidon_params.h", "imt_indexed.inl"]
+SOURCES = ["imt_capi.cu", "imt_indexed.cu", "poseidon_params.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "imt_internal.h", "poseidon.cuh", "fr.cuh", "poseidon_params.h"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _nvcc():
@@ -27,17 +28,26 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """one nvcc -c per translation unit, in parallel, then a link step: sm_100a only, -lineinfo for ncu's source page"""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
     # the image's CC/CXX wrappers lack some specs; let nvcc find the system g++
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    subprocess.run(cmd, check=True, env=env)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-diag-suppress", "550", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if verbose:
+        flags.append("-Xptxas=-v")
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        subprocess.run([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj], check=True, env=env)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-o", LIB], check=True, env=env)
     return LIB
 
 

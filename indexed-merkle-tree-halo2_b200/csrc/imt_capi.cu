@@ -9,93 +9,19 @@
 #include <vector>
 
 #include "imt_b200.h"
+#include "imt_internal.h"
 #include "kernels.cuh"
 #include "poseidon_params.h"
 
 using namespace imt;
 
-struct imt_ctx {
-    int device = 0;
-    int fmt = kFmtCanonical;
-    cudaStream_t stream = nullptr;       // compute (own_stream unless the caller supplied one)
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
-    uint32_t* d_err = nullptr;           // bit 0: non-canonical input, bit 1: index out of bounds
-    uint32_t* h_err = nullptr;           // pinned mirror
-    uint64_t launches = 0;
-    std::string last_error;
-    // optional per-launch device timing of the hash kernels
-    bool timing = false;
-    struct Timed {
-        cudaEvent_t a, b;
-        int arity;
-        size_t hashes;
-    };
-    std::vector<Timed> pending;
-    double kernel_ms[4] = {0, 0, 0, 0};
-    uint64_t kernel_launches[4] = {0, 0, 0, 0};
-    uint64_t kernel_hashes[4] = {0, 0, 0, 0};
-};
-
-struct imt_tree {
-    imt_ctx* ctx = nullptr;
-    size_t n = 0;            // leaves on this rank
-    unsigned depth = 0;      // log2(n)
-    Fr* d_levels = nullptr;  // 2n - 1 FE, Montgomery, level 0 first
-    Fr* d_pre = nullptr;     // 3n FE in the context format (only when built from leaves)
-    bool owns_pre = false;
-    // subtree sharding
-    unsigned rank = 0, world = 1, cap_depth = 0;
-    Fr* d_cap = nullptr;  // 2*world - 1 FE, Montgomery
-    unsigned cap_alloc_world = 0;
-    bool cap_valid = false;  // a rebuild makes the attached cap stale until the roots are exchanged again
-    // lazily built sorted index over the occupied leaves (low-leaf lookups)
-    bool index_valid = false;
-    size_t occupied = 0;
-    Fr* d_sorted_keys = nullptr;       // canonical values, ascending
-    uint32_t* d_sorted_slots = nullptr;  // slot of each key
-};
-
-namespace {
-
-#define IMT_TRY_CUDA(ctx, expr)                                                                         \
-    do {                                                                                                \
-        cudaError_t e_ = (expr);                                                                        \
-        if (e_ != cudaSuccess) {                                                                        \
-            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
-            return IMT_ERR_CUDA;                                                                        \
-        }                                                                                               \
-    } while (0)
-
-#define IMT_TRY(expr)                      \
-    do {                                   \
-        imt_status s_ = (expr);            \
-        if (s_ != IMT_OK) return s_;       \
-    } while (0)
-
-inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
-
-imt_status fail(imt_ctx* ctx, imt_status st, const char* what) {
-    ctx->last_error = what;
-    return st;
-}
-
-// RAII device buffer
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <class T>
-    T* as() { return static_cast<T*>(p); }
-};
+namespace imt_host {
 
 imt_status clear_err(imt_ctx* ctx) {
     IMT_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(uint32_t), ctx->stream));
     return IMT_OK;
 }
-void drain_timing(imt_ctx* ctx) {
+static void drain_timing(imt_ctx* ctx) {
     for (auto& t : ctx->pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
@@ -108,17 +34,23 @@ void drain_timing(imt_ctx* ctx) {
     }
     ctx->pending.clear();
 }
-// waits for the compute stream and turns the device error flag into a status
 imt_status finish(imt_ctx* ctx) {
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     if (!ctx->pending.empty()) drain_timing(ctx);
     const uint32_t e = *ctx->h_err;
-    if (e & 2u) return fail(ctx, IMT_ERR_INDEX_OOB, "index out of bounds");
-    if (e & 1u) return fail(ctx, IMT_ERR_NON_CANONICAL, "input field element >= p");
+    if (e & kErrIndexOob) return fail(ctx, IMT_ERR_INDEX_OOB, "index out of bounds");
+    if (e & kErrNonCanonical) return fail(ctx, IMT_ERR_NON_CANONICAL, "input field element >= p");
+    if (e & kErrNotWellFormed) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, imt_status_string(IMT_ERR_NOT_WELL_FORMED));
+    if (e & kErrBadInsert) return fail(ctx, IMT_ERR_INVALID_ARG, "insert value is zero, already in the tree, or repeated in the batch");
     return IMT_OK;
 }
+
+}  // namespace imt_host
+using namespace imt_host;
+
+namespace {
 
 imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
     if (n == 0) return fail(ctx, IMT_ERR_EMPTY, imt_status_string(IMT_ERR_EMPTY));
@@ -129,7 +61,7 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
 }
 
 template <int ARITY>
-imt_status launch_hash(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
     if (n == 0) return IMT_OK;
     imt_ctx::Timed tm{nullptr, nullptr, ARITY, n};
     if (ctx->timing) {
@@ -154,7 +86,7 @@ imt_status build_upper_levels(imt_tree* t) {
     for (unsigned l = 0; l < t->depth; ++l) {
         const Fr* src = t->d_levels + level_offset(t->n, l);
         Fr* dst = t->d_levels + level_offset(t->n, l + 1);
-        IMT_TRY(launch_hash<2>(ctx, src, dst, t->n >> (l + 1), kFmtMontgomery, kFmtMontgomery, ctx->stream));
+        IMT_TRY(launch_hash_t<2>(ctx, src, dst, t->n >> (l + 1), kFmtMontgomery, kFmtMontgomery, ctx->stream));
     }
     return IMT_OK;
 }
@@ -180,12 +112,6 @@ imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
     return IMT_OK;
 }
 
-void invalidate_index(imt_tree* t) {
-    t->index_valid = false;
-    if (t->d_sorted_keys) cudaFree(t->d_sorted_keys), t->d_sorted_keys = nullptr;
-    if (t->d_sorted_slots) cudaFree(t->d_sorted_slots), t->d_sorted_slots = nullptr;
-}
-
 // Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed.
 imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
     imt_ctx* ctx = t->ctx;
@@ -207,7 +133,7 @@ imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
             st = IMT_ERR_CUDA;
             break;
         }
-        st = launch_hash<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, ctx->stream);
+        st = launch_hash_t<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, ctx->stream);
     }
     if (st != IMT_OK) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t ev : evs) {
@@ -229,7 +155,7 @@ imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
         if (t->owns_pre && t->d_pre && preimages != t->d_pre)
             IMT_TRY_CUDA(ctx, cudaMemcpyAsync(t->d_pre, preimages, 3 * t->n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
         const void* src = (t->owns_pre && t->d_pre) ? (const void*)t->d_pre : preimages;
-        IMT_TRY(launch_hash<3>(ctx, src, t->d_levels, t->n, ctx->fmt, kFmtMontgomery, ctx->stream));
+        IMT_TRY(launch_hash_t<3>(ctx, src, t->d_levels, t->n, ctx->fmt, kFmtMontgomery, ctx->stream));
     } else {
         IMT_TRY(hash_leaves_from_host(t, preimages));
     }
@@ -256,6 +182,31 @@ imt_status copy_out_fe(imt_ctx* ctx, const Fr* d_src, size_t count, void* h_dst,
 }
 
 }  // namespace
+
+namespace imt_host {
+imt_status launch_hash(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+    return arity == 3 ? launch_hash_t<3>(ctx, d_in, d_out, n, in_fmt, out_fmt, s) : launch_hash_t<2>(ctx, d_in, d_out, n, in_fmt, out_fmt, s);
+}
+imt_status launch_convert(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int from_fmt, int to_fmt) {
+    if (n == 0) return IMT_OK;
+    k_convert<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_out, n, from_fmt, to_fmt, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe) {
+    imt_ctx* ctx = t->ctx;
+    const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
+    const unsigned depth = t->depth + cap_depth;
+    if (q == 0 || depth == 0) return IMT_OK;
+    k_gather_proofs<<<grid_for(q * depth, 256), 256, 0, ctx->stream>>>(
+        (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, d_idx, q, ctx->fmt,
+        (uint4*)d_siblings, d_helpers, (uint4*)d_helpers_fe, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+}  // namespace imt_host
 
 // ------------------------------------------------------------------------------------------------- context
 extern "C" const char* imt_status_string(imt_status st) {
@@ -296,6 +247,7 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
+    if (e == cudaSuccess) e = upload_params_indexed(&host_params);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "imt_ctx_create: %s\n", cudaGetErrorString(e));
@@ -357,7 +309,7 @@ static imt_status hash_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out
     if (n && (!d_in || !d_out)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     IMT_TRY(clear_err(ctx));
-    IMT_TRY(launch_hash<ARITY>(ctx, d_in, d_out, n, ctx->fmt, ctx->fmt, ctx->stream));
+    IMT_TRY(launch_hash_t<ARITY>(ctx, d_in, d_out, n, ctx->fmt, ctx->fmt, ctx->stream));
     return finish(ctx);
 }
 template <int ARITY>
@@ -371,7 +323,7 @@ static imt_status hash_host(imt_ctx* ctx, const void* in, size_t n, void* out) {
     IMT_TRY_CUDA(ctx, dout.alloc(n * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * ARITY * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY(clear_err(ctx));
-    IMT_TRY(launch_hash<ARITY>(ctx, din.p, dout.p, n, ctx->fmt, ctx->fmt, ctx->stream));
+    IMT_TRY(launch_hash_t<ARITY>(ctx, din.p, dout.p, n, ctx->fmt, ctx->fmt, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
 }
@@ -555,11 +507,7 @@ static imt_status get_proofs(imt_tree* t, const uint64_t* indices, size_t q, voi
     if (helpers_fe) IMT_TRY_CUDA(ctx, dhfe.alloc(q * depth * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(didx.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY(clear_err(ctx));
-    k_gather_proofs<<<grid_for(q * depth, 256), 256, 0, ctx->stream>>>(
-        (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, didx.as<uint64_t>(), q,
-        ctx->fmt, dsib.as<uint4>(), helpers ? dhel.as<uint8_t>() : nullptr, helpers_fe ? dhfe.as<uint4>() : nullptr, ctx->d_err);
-    ++ctx->launches;
-    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(launch_gather_proofs(t, didx.as<uint64_t>(), q, dsib.p, helpers ? dhel.as<uint8_t>() : nullptr, helpers_fe ? dhfe.p : nullptr));
     IMT_TRY(finish(ctx));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(siblings, dsib.p, q * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (helpers) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(helpers, dhel.p, q * depth, cudaMemcpyDeviceToHost, ctx->stream));
@@ -654,7 +602,7 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
                                                           ctx->d_err);
     ++ctx->launches;
     for (unsigned l = 0; l < t->cap_depth; ++l)
-        IMT_TRY(launch_hash<2>(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1),
+        IMT_TRY(launch_hash_t<2>(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1),
                                kFmtMontgomery, kFmtMontgomery, ctx->stream));
     IMT_TRY(finish(ctx));
     t->cap_valid = true;
@@ -707,5 +655,3 @@ extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_m
     return IMT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------- indexed-leaf logic
-#include "imt_indexed.inl"

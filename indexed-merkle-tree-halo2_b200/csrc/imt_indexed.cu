@@ -1,0 +1,692 @@
+// Indexed-leaf logic on the device: sorted-key index, low-leaf (predecessor) lookups, non-inclusion witnesses and
+// batched inserts with per-insert roots.
+//
+// Replaces the O(n)-per-call test helpers of the reference:
+//   update_idx_leaf                  /root/reference/src/indexed_merkle_tree.rs:632-660   (linear scan + list rewiring)
+//   insert orchestration             /root/reference/src/indexed_merkle_tree.rs:710-741   (re-hash ALL leaves + rebuild per insert)
+// with (a) a sorted array of the occupied leaves' canonical values + binary search per query, and (b) a
+// level-synchronous versioned update: a batch of B inserts is 2B single-leaf writes at times t = 0..2B-1 (t = 2k:
+// the low leaf of insert k, t = 2k+1: its new leaf); every (write, level) pair is one hash whose sibling operand is
+// the latest earlier write to the sibling node, else the stored tree. All 2B hashes of a level run in one launch, so
+// a batch costs `depth` launches instead of B full rebuilds, and yields the same roots and paths as the reference's
+// sequence of rebuilds (checked against the oracle's restatement of that sequence).
+#include <cub/device/device_merge_sort.cuh>
+
+#include <algorithm>
+#include <new>
+
+#include "imt_internal.h"
+#include "kernels_common.cuh"
+
+using namespace imt;
+using namespace imt_host;
+
+namespace {
+
+constexpr size_t kInsertChunk = 4096;  // inserts resolved together (the pairwise scans below are O(chunk^2))
+
+__device__ __forceinline__ int cmp256(const uint32_t* a, const uint32_t* b) {
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    }
+    return 0;
+}
+__device__ __forceinline__ bool zero256(const uint32_t* a) { return (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0; }
+__device__ __forceinline__ void copy256(uint32_t* d, const uint32_t* s) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = s[i];
+}
+// context-format FE -> canonical integer (`Fr: Ord` compares canonical values, IMT:647). false when the input is >= p
+__device__ __forceinline__ bool to_int(uint32_t* x, int fmt) {
+    const bool ok = is_canonical(x);
+    if (fmt == kFmtMontgomery) from_mont(x, x);
+    return ok;
+}
+// canonical integer -> context-format FE
+__device__ __forceinline__ void from_int(uint32_t* x, int fmt) {
+    if (fmt == kFmtMontgomery) {
+        to_mont(x, x);
+        canonicalize(x);
+    }
+}
+__device__ __forceinline__ void slot_to_int(uint32_t* x, uint64_t slot) {
+    x[0] = (uint32_t)slot, x[1] = (uint32_t)(slot >> 32);
+#pragma unroll
+    for (int i = 2; i < 8; ++i) x[i] = 0;
+}
+
+struct KeyLess {
+    __device__ __forceinline__ bool operator()(const Fr& a, const Fr& b) const { return cmp256(a.l, b.l) < 0; }
+};
+
+// first j in [0, m) with keys[j] >= v, else m
+__device__ __forceinline__ size_t lower_bound(const uint4* __restrict__ keys, size_t m, const uint32_t* v) {
+    size_t lo = 0, hi = m;
+    while (lo < hi) {
+        const size_t mid = lo + ((hi - lo) >> 1);
+        uint32_t k[8];
+        load_fe(k, keys + 2 * mid);
+        if (cmp256(k, v) < 0) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------- index build
+// keys[i] = canonical val of slot i, slots[i] = i; stats[0] = first empty slot (min), stats[1] = last occupied slot
+// (max). Slot 0 is the head and always counts as occupied; any other slot is occupied iff val != 0.
+__global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__ pre, size_t n, int fmt, uint4* __restrict__ keys,
+                                                       uint32_t* __restrict__ slots, unsigned long long* __restrict__ stats,
+                                                       uint32_t* __restrict__ head_next_zero, uint32_t* __restrict__ err) {
+    __shared__ unsigned long long s_min, s_max;
+    if (threadIdx.x == 0) s_min = ~0ull, s_max = 0ull;
+    __syncthreads();
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t v[8], a[8], b[8];
+        load_fe(v, pre + 2 * (3 * i));
+        load_fe(a, pre + 2 * (3 * i + 1));
+        load_fe(b, pre + 2 * (3 * i + 2));
+        if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
+        store_fe(keys + 2 * i, v);
+        slots[i] = (uint32_t)i;
+        const bool occ = i == 0 || !zero256(v);
+        if (occ) atomicMax(&s_max, (unsigned long long)i);
+        else {
+            atomicMin(&s_min, (unsigned long long)i);
+            if (!zero256(a) || !zero256(b)) atomicOr(err, kErrNotWellFormed);  // an empty slot is {0, 0, 0}
+        }
+        if (i == 0) *head_next_zero = zero256(a) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_min != ~0ull) atomicMin(&stats[0], s_min);
+        atomicMax(&stats[1], s_max);
+    }
+}
+
+// the sorted order must be the linked list: next_val / next_idx of the j-th smallest point at the (j+1)-th smallest,
+// the largest points at (0, 0), values are distinct
+__global__ void __launch_bounds__(256) k_index_check(const uint4* __restrict__ pre, int fmt, const uint4* __restrict__ keys,
+                                                     const uint32_t* __restrict__ slots, size_t m, uint32_t* __restrict__ err) {
+    const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const size_t s = slots[j];
+    uint32_t nv[8], ni[8];
+    load_fe(nv, pre + 2 * (3 * s + 1));
+    load_fe(ni, pre + 2 * (3 * s + 2));
+    bool ok = to_int(nv, fmt);
+    ok &= to_int(ni, fmt);
+    if (!ok) atomicOr(err, kErrNonCanonical);
+    bool good;
+    if (j + 1 < m) {
+        uint32_t k0[8], k1[8], want[8];
+        load_fe(k0, keys + 2 * j);
+        load_fe(k1, keys + 2 * (j + 1));
+        slot_to_int(want, slots[j + 1]);
+        good = cmp256(k0, k1) < 0 && cmp256(nv, k1) == 0 && cmp256(ni, want) == 0;
+    } else {
+        good = zero256(nv) && zero256(ni);
+    }
+    if (!good) atomicOr(err, kErrNotWellFormed);
+}
+
+// ------------------------------------------------------------------------------------------------- lookups
+// The read-only half of update_idx_leaf (IMT:638-647) answered from the sorted index. In a well-formed tree the
+// scan's predicate  val < v && (next_val > v || next_val == 0)  holds for exactly one occupied slot — the
+// predecessor of v — unless v is 0 or already present; then the scan falls through to the first EMPTY slot
+// (val 0 < v, next_val 0), or matches nothing.
+__global__ void __launch_bounds__(256) k_low_leaf_lookup(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
+                                                         size_t n, uint32_t head_next_zero, const uint4* __restrict__ values, size_t q,
+                                                         int fmt, uint64_t* __restrict__ low_idx, uint8_t* __restrict__ matched,
+                                                         uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    uint32_t v[8];
+    load_fe(v, values + 2 * i);
+    if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
+    uint64_t low = 0;
+    uint8_t hit = 0;
+    if (head_next_zero) {  // IMT:640: `node.next_val == 0 && i == 0` matches before anything is compared
+        hit = 1;
+    } else {
+        const size_t j = lower_bound(keys, m, v);
+        bool present = false;
+        if (j < m) {
+            uint32_t k[8];
+            load_fe(k, keys + 2 * j);
+            present = cmp256(k, v) == 0;
+        }
+        if (j >= 1 && !present) {
+            low = slots[j - 1];
+            hit = 1;
+        } else if (!zero256(v) && m < n) {
+            low = m;
+            hit = 1;
+        }
+    }
+    low_idx[i] = low;
+    if (matched) matched[i] = hit;
+}
+
+__global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__ pre, const uint64_t* __restrict__ idx, size_t q,
+                                                       uint4* __restrict__ leaves, uint8_t* __restrict__ is_largest) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const size_t s = idx[i];
+    uint4 w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] = __ldg(pre + 6 * s + k);
+    if (leaves) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) leaves[6 * i + k] = w[k];
+    }
+    if (is_largest) is_largest[i] = ((w[2].x | w[2].y | w[2].z | w[2].w | w[3].x | w[3].y | w[3].z | w[3].w) == 0) ? 1 : 0;  // IMT:736-741
+}
+
+// ------------------------------------------------------------------------------------------------- inserts
+// whole-batch validation on the sorted batch: no zero, no repeats, none already in the tree
+__global__ void __launch_bounds__(256) k_ins_validate(const uint4* __restrict__ sorted_vals, size_t b, const uint4* __restrict__ keys, size_t m,
+                                                      uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    uint32_t v[8];
+    load_fe(v, sorted_vals + 2 * i);
+    bool bad = zero256(v);
+    if (i + 1 < b) {
+        uint32_t w[8];
+        load_fe(w, sorted_vals + 2 * (i + 1));
+        bad |= cmp256(v, w) == 0;
+    }
+    const size_t j = lower_bound(keys, m, v);
+    if (j < m) {
+        uint32_t k[8];
+        load_fe(k, keys + 2 * j);
+        bad |= cmp256(k, v) == 0;
+    }
+    bad |= j == 0;  // nothing below v: the tree has no head {0, ..}
+    if (bad) atomicOr(err, kErrBadInsert);
+}
+
+// Insert k of the chunk: its predecessor / successor among (indexed leaves) U (chunk values 0..k-1), i.e. the state
+// the reference's scan sees at that point, and from them the four preimages IMT:648-654 reads and writes.
+//   x[2k] = low slot, x[2k+1] = new slot;  upd[2k] = low leaf AFTER, upd[2k+1] = new leaf;  low_old[k] = low leaf BEFORE
+__global__ void __launch_bounds__(128) k_ins_resolve(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
+                                                     const uint4* __restrict__ vals, size_t b, uint64_t first_idx, int fmt,
+                                                     uint64_t* __restrict__ x, uint4* __restrict__ upd, uint4* __restrict__ low_old,
+                                                     uint8_t* __restrict__ is_largest) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= b) return;
+    uint32_t v[8], pred[8], succ[8];
+    load_fe(v, vals + 2 * k);
+    const size_t j = lower_bound(keys, m, v);  // validated: j >= 1 and keys[j] != v
+    load_fe(pred, keys + 2 * (j - 1));
+    uint64_t pred_slot = slots[j - 1], succ_slot = 0;
+    bool has_succ = j < m;
+    if (has_succ) {
+        load_fe(succ, keys + 2 * j);
+        succ_slot = slots[j];
+    }
+    for (size_t i = 0; i < k; ++i) {  // warp-uniform address: one broadcast load per step
+        uint32_t w[8];
+        load_fe(w, vals + 2 * i);
+        if (cmp256(w, v) < 0) {
+            if (cmp256(w, pred) > 0) copy256(pred, w), pred_slot = first_idx + i;
+        } else if (!has_succ || cmp256(w, succ) < 0) {
+            copy256(succ, w), succ_slot = first_idx + i, has_succ = true;
+        }
+    }
+    if (!has_succ) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) succ[i] = 0;
+    }
+    const uint64_t new_slot = first_idx + k;
+    x[2 * k] = pred_slot;
+    x[2 * k + 1] = new_slot;
+    is_largest[k] = has_succ ? 0 : 1;
+    uint32_t fv[8], fp[8], fs[8], fsi[8], fni[8];
+    copy256(fv, v), from_int(fv, fmt);
+    copy256(fp, pred), from_int(fp, fmt);
+    copy256(fs, succ), from_int(fs, fmt);
+    slot_to_int(fsi, succ_slot), from_int(fsi, fmt);
+    slot_to_int(fni, new_slot), from_int(fni, fmt);
+    uint4* lo = low_old + 6 * k;  // {pred, succ, succ_slot}
+    store_fe(lo, fp), store_fe(lo + 2, fs), store_fe(lo + 4, fsi);
+    uint4* u0 = upd + 6 * (2 * k);  // {pred, v, new_slot}
+    store_fe(u0, fp), store_fe(u0 + 2, fv), store_fe(u0 + 4, fni);
+    uint4* u1 = upd + 6 * (2 * k + 1);  // {v, succ, succ_slot}
+    store_fe(u1, fv), store_fe(u1 + 2, fs), store_fe(u1 + 4, fsi);
+}
+
+// For write t and level l (l fastest): prev = latest earlier write whose level-l node is the SIBLING of t's node
+// (-1: none, take the stored tree); last = no later write touches t's own level-l node (t's version is the final one).
+__global__ void __launch_bounds__(256) k_ins_links(const uint64_t* __restrict__ x, unsigned writes, unsigned depth, int* __restrict__ prev,
+                                                   uint8_t* __restrict__ last) {
+    const unsigned levels = depth + 1;
+    const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (id >= (size_t)writes * levels) return;
+    const unsigned t = (unsigned)(id / levels), l = (unsigned)(id % levels);
+    const uint64_t node = x[t] >> l;
+    int p = -1;
+    for (int u = (int)t - 1; u >= 0; --u) {
+        if (((x[u] >> l) ^ 1) == node) {
+            p = u;
+            break;
+        }
+    }
+    bool fin = true;
+    for (unsigned u = t + 1; u < writes; ++u) {
+        if ((x[u] >> l) == node) {
+            fin = false;
+            break;
+        }
+    }
+    prev[id] = p;
+    last[id] = fin ? 1 : 0;
+}
+
+// One level of all writes: ver[(l+1) * writes + t] = H(own child version, sibling) ; the sibling operand is also
+// the witness path element of that write (low path of insert t/2 in the OLD tree for even t, new-leaf path in the
+// NEW tree for odd t — see the header of this file).
+__global__ void __launch_bounds__(kHashThreads) k_ins_level(uint4* __restrict__ ver, const uint4* __restrict__ tree_levels, size_t n,
+                                                            unsigned l, const uint64_t* __restrict__ x, const int* __restrict__ prev,
+                                                            unsigned writes, unsigned depth, int fmt, uint4* __restrict__ sib_low,
+                                                            uint4* __restrict__ sib_new) {
+    const unsigned t = blockIdx.x * kHashThreads + threadIdx.x;
+    if (t >= writes) return;
+    const uint64_t node = x[t] >> l;
+    const int p = prev[(size_t)t * (depth + 1) + l];
+    uint32_t in[2][8], own[8], sib[8], h[8];
+    const uint4* cur = ver + 2 * ((size_t)l * writes);
+    // versions are written by earlier launches of this kernel: plain loads (not the read-only path)
+    {
+        const uint4 a = cur[2 * t], c = cur[2 * t + 1];
+        own[0] = a.x, own[1] = a.y, own[2] = a.z, own[3] = a.w, own[4] = c.x, own[5] = c.y, own[6] = c.z, own[7] = c.w;
+    }
+    if (p >= 0) {
+        const uint4 a = cur[2 * p], c = cur[2 * p + 1];
+        sib[0] = a.x, sib[1] = a.y, sib[2] = a.z, sib[3] = a.w, sib[4] = c.x, sib[5] = c.y, sib[6] = c.z, sib[7] = c.w;
+    } else {
+        load_fe(sib, tree_levels + 2 * (level_offset(n, l) + (node ^ 1)));
+    }
+    uint4* wit = (t & 1) ? sib_new : sib_low;
+    if (wit) {
+        uint32_t s2[8];
+        copy256(s2, sib);
+        egress(s2, fmt);
+        store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), s2);
+    }
+    const bool left = (node & 1) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        in[0][i] = left ? own[i] : sib[i];
+        in[1][i] = left ? sib[i] : own[i];
+    }
+    NoTrace nt;
+    hash_fixed<2>(h, in, c_params, nt);
+    store_fe(ver + 2 * ((size_t)(l + 1) * writes + t), h);
+}
+
+// per insert: roots before / after, helper bits of both paths
+__global__ void __launch_bounds__(256) k_ins_outputs(const uint4* __restrict__ ver, const uint4* __restrict__ tree_levels, size_t n,
+                                                     const uint64_t* __restrict__ x, unsigned b, unsigned depth, int fmt,
+                                                     uint4* __restrict__ old_roots, uint4* __restrict__ new_roots,
+                                                     uint8_t* __restrict__ low_helpers, uint8_t* __restrict__ new_helpers,
+                                                     uint64_t* __restrict__ low_idx) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= b) return;
+    const unsigned writes = 2 * b;
+    const uint4* top = ver + 2 * ((size_t)depth * writes);
+    uint32_t r[8];
+    if (old_roots) {
+        if (k == 0) load_fe(r, tree_levels + 2 * level_offset(n, depth));
+        else load_fe(r, top + 2 * (2 * k - 1));
+        egress(r, fmt);
+        store_fe(old_roots + 2 * k, r);
+    }
+    if (new_roots) {
+        load_fe(r, top + 2 * (2 * k + 1));
+        egress(r, fmt);
+        store_fe(new_roots + 2 * k, r);
+    }
+    const uint64_t lo = x[2 * k], nw = x[2 * k + 1];
+    if (low_idx) low_idx[k] = lo;
+    for (unsigned l = 0; l < depth; ++l) {
+        if (low_helpers) low_helpers[(size_t)k * depth + l] = ((lo >> l) & 1) == 0;  // 1 = current node is LEFT (utils.rs:70)
+        if (new_helpers) new_helpers[(size_t)k * depth + l] = ((nw >> l) & 1) == 0;
+    }
+}
+
+// final versions into the stored tree and preimages
+__global__ void __launch_bounds__(256) k_ins_commit(const uint4* __restrict__ ver, const uint4* __restrict__ upd, const uint64_t* __restrict__ x,
+                                                    const uint8_t* __restrict__ last, unsigned writes, unsigned depth, size_t n,
+                                                    uint4* __restrict__ tree_levels, uint4* __restrict__ pre) {
+    const unsigned levels = depth + 1;
+    const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (id >= (size_t)writes * levels) return;
+    if (!last[id]) return;
+    const unsigned t = (unsigned)(id / levels), l = (unsigned)(id % levels);
+    const uint64_t node = x[t] >> l;
+    const uint4* v = ver + 2 * ((size_t)l * writes + t);
+    uint4* dst = tree_levels + 2 * (level_offset(n, l) + node);
+    dst[0] = v[0], dst[1] = v[1];
+    if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pre[6 * node + k] = upd[6 * (size_t)t + k];
+    }
+}
+
+// merge of two sorted, disjoint key arrays by ranking: every element's output position is its own rank plus the
+// number of smaller elements in the other array
+__global__ void __launch_bounds__(256) k_merge_rank(const uint4* __restrict__ ka, const uint32_t* __restrict__ sa, size_t na,
+                                                    const uint4* __restrict__ kb, const uint32_t* __restrict__ sb, size_t nb,
+                                                    uint4* __restrict__ ko, uint32_t* __restrict__ so) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= na + nb) return;
+    uint32_t v[8];
+    size_t pos;
+    uint32_t slot;
+    if (i < na) {
+        load_fe(v, ka + 2 * i);
+        pos = i + lower_bound(kb, nb, v);
+        slot = sa[i];
+    } else {
+        const size_t j = i - na;
+        load_fe(v, kb + 2 * j);
+        pos = j + lower_bound(ka, na, v);
+        slot = sb[j];
+    }
+    store_fe(ko + 2 * pos, v);
+    so[pos] = slot;
+}
+
+__global__ void k_iota_slots(uint32_t* s, size_t b, uint64_t first) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < b) s[i] = (uint32_t)(first + i);
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+imt_status sort_pairs(imt_ctx* ctx, Fr* d_keys, uint32_t* d_slots, size_t count) {
+    if (count < 2) return IMT_OK;
+    size_t temp_bytes = 0;
+    IMT_TRY_CUDA(ctx, cub::DeviceMergeSort::SortPairs(nullptr, temp_bytes, d_keys, d_slots, (long long)count, KeyLess(), ctx->stream));
+    DevBuf temp;
+    IMT_TRY_CUDA(ctx, temp.alloc(temp_bytes));
+    IMT_TRY_CUDA(ctx, cub::DeviceMergeSort::SortPairs(temp.p, temp_bytes, d_keys, d_slots, (long long)count, KeyLess(), ctx->stream));
+    ctx->launches += 2;  // block sort + merge passes (at least)
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // temp is freed on return
+    return IMT_OK;
+}
+
+imt_status ensure_index(imt_tree* t) {
+    imt_ctx* ctx = t->ctx;
+    if (t->index_valid) return IMT_OK;
+    if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves: no preimages to index");
+    if (t->n > 0xffffffffull) return fail(ctx, IMT_ERR_INVALID_ARG, "index supports at most 2^32 slots");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!t->d_sorted_keys || t->index_capacity < t->n) {
+        if (t->d_sorted_keys) cudaFree(t->d_sorted_keys), t->d_sorted_keys = nullptr;
+        if (t->d_sorted_slots) cudaFree(t->d_sorted_slots), t->d_sorted_slots = nullptr;
+        t->index_capacity = 0;
+        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_keys, t->n * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_slots, t->n * sizeof(uint32_t)));
+        t->index_capacity = t->n;
+    }
+    DevBuf stats;  // [0] first empty, [1] last occupied, then the head flag
+    IMT_TRY_CUDA(ctx, stats.alloc(3 * sizeof(unsigned long long)));
+    const unsigned long long init[3] = {(unsigned long long)t->n, 0ull, 0ull};
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(stats.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_index_extract<<<grid_for(t->n, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, ctx->fmt, (uint4*)t->d_sorted_keys,
+                                                                 t->d_sorted_slots, stats.as<unsigned long long>(),
+                                                                 (uint32_t*)(stats.as<unsigned long long>() + 2), ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    unsigned long long got[3];
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(got, stats.p, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY(finish(ctx));
+    const size_t m = (size_t)got[0];
+    if (got[1] >= m) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, "occupied slots do not form a prefix");
+    if (m == 0) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, imt_status_string(IMT_ERR_NOT_WELL_FORMED));
+    IMT_TRY(sort_pairs(ctx, t->d_sorted_keys, t->d_sorted_slots, m));
+    IMT_TRY(clear_err(ctx));
+    k_index_check<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, ctx->fmt, (const uint4*)t->d_sorted_keys,
+                                                             t->d_sorted_slots, m, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    t->occupied = m;
+    t->head_next_zero = (uint32_t)got[2] != 0;
+    t->index_valid = true;
+    return IMT_OK;
+}
+
+imt_status lookup_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low, uint8_t* d_matched) {
+    imt_ctx* ctx = t->ctx;
+    k_low_leaf_lookup<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied, t->n,
+                                                                 t->head_next_zero ? 1u : 0u, (const uint4*)d_values, q, ctx->fmt, d_low,
+                                                                 d_matched, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+
+bool sharded(const imt_tree* t) { return t->cap_valid || t->world > 1; }
+
+}  // namespace
+
+namespace imt_host {
+cudaError_t upload_params_indexed(const PoseidonParams* host_params) { return cudaMemcpyToSymbol(c_params, host_params, sizeof(PoseidonParams)); }
+void invalidate_index(imt_tree* t) {  // the buffers are kept for the next build of the index
+    t->index_valid = false;
+    t->occupied = 0;
+}
+}  // namespace imt_host
+
+extern "C" imt_status imt_tree_occupied(imt_tree* t, size_t* occupied) {
+    if (!t || !occupied) return IMT_ERR_INVALID_ARG;
+    IMT_TRY(ensure_index(t));
+    *occupied = t->occupied;
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_low_leaf_lookup(imt_tree* t, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!values || !low_idx)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (sharded(t)) return fail(ctx, IMT_ERR_INVALID_ARG, "low-leaf lookups on a sharded tree go through the per-rank candidate call");
+    IMT_TRY(ensure_index(t));
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dv, dl, dm;
+    IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dm.alloc(q));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(lookup_dev(t, dv.p, q, dl.as<uint64_t>(), dm.as<uint8_t>()));
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_idx, dl.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matched) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(matched, dm.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_non_inclusion_paths(imt_tree* t, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                              void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && !values) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (sharded(t)) return fail(ctx, IMT_ERR_INVALID_ARG, "low-leaf lookups on a sharded tree go through the per-rank candidate call");
+    IMT_TRY(ensure_index(t));
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned depth = t->depth;
+    DevBuf dv, dl, dm, dlv, dsib, dhel, dlg;
+    IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dm.alloc(q));
+    if (low_leaves) IMT_TRY_CUDA(ctx, dlv.alloc(q * 3 * sizeof(Fr)));
+    if (siblings) IMT_TRY_CUDA(ctx, dsib.alloc(q * (size_t)depth * sizeof(Fr)));
+    if (helpers) IMT_TRY_CUDA(ctx, dhel.alloc(q * (size_t)depth));
+    if (is_largest) IMT_TRY_CUDA(ctx, dlg.alloc(q));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(lookup_dev(t, dv.p, q, dl.as<uint64_t>(), dm.as<uint8_t>()));
+    if (low_leaves || is_largest) {
+        k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, dl.as<uint64_t>(), q,
+                                                                   low_leaves ? dlv.as<uint4>() : nullptr,
+                                                                   is_largest ? dlg.as<uint8_t>() : nullptr);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+    }
+    if (siblings || helpers) {
+        DevBuf scratch;  // the gather kernel always writes siblings
+        void* d_sib = dsib.p;
+        if (!siblings) {
+            IMT_TRY_CUDA(ctx, scratch.alloc(q * (size_t)depth * sizeof(Fr)));
+            d_sib = scratch.p;
+        }
+        IMT_TRY(launch_gather_proofs(t, dl.as<uint64_t>(), q, d_sib, helpers ? dhel.as<uint8_t>() : nullptr, nullptr));
+        IMT_TRY(finish(ctx));
+    } else {
+        IMT_TRY(finish(ctx));
+    }
+    if (low_idx) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_idx, dl.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matched) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(matched, dm.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (low_leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_leaves, dlv.p, q * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (siblings && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(siblings, dsib.p, q * (size_t)depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (helpers && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(helpers, dhel.p, q * (size_t)depth, cudaMemcpyDeviceToHost, ctx->stream));
+    if (is_largest) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dlg.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (b && !new_vals) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (sharded(t)) return fail(ctx, IMT_ERR_INVALID_ARG, "inserts into a sharded tree are not supported");
+    IMT_TRY(ensure_index(t));
+    if (first_idx != t->occupied) return fail(ctx, IMT_ERR_INVALID_ARG, "first_idx must be the next free slot (the number of occupied slots)");
+    if (b > t->n - t->occupied) return fail(ctx, IMT_ERR_TREE_FULL, imt_status_string(IMT_ERR_TREE_FULL));
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned depth = t->depth;
+    const imt_insert_witness none = {};
+    const imt_insert_witness out = w ? *w : none;
+
+    // ---- the whole batch as canonical integers, validated before anything is modified
+    DevBuf staged, vals, sorted_vals, sorted_slots;
+    IMT_TRY_CUDA(ctx, staged.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, vals.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, sorted_vals.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, sorted_slots.alloc(b * sizeof(uint32_t)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, new_vals, b * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_convert(ctx, staged.p, vals.p, b, ctx->fmt, kFmtCanonical));
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(sorted_vals.p, vals.p, b * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_iota_slots<<<grid_for(b, 256), 256, 0, ctx->stream>>>(sorted_slots.as<uint32_t>(), b, first_idx);
+    ++ctx->launches;
+    IMT_TRY(sort_pairs(ctx, sorted_vals.as<Fr>(), sorted_slots.as<uint32_t>(), b));
+    IMT_TRY(clear_err(ctx));
+    k_ins_validate<<<grid_for(b, 256), 256, 0, ctx->stream>>>(sorted_vals.as<uint4>(), b, (const uint4*)t->d_sorted_keys, t->occupied, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+
+    // ---- per-chunk scratch
+    const size_t C = std::min(b, kInsertChunk), W = 2 * C, L = depth + 1;
+    DevBuf x, upd, low_old, largest, prev, last, ver, sib_low, sib_new, r_old, r_new, h_low, h_new, low_idx, chunk_keys, chunk_slots, alt_keys,
+        alt_slots;
+    IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, low_old.alloc(C * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, largest.alloc(C));
+    IMT_TRY_CUDA(ctx, prev.alloc(W * L * sizeof(int)));
+    IMT_TRY_CUDA(ctx, last.alloc(W * L));
+    IMT_TRY_CUDA(ctx, ver.alloc(L * W * sizeof(Fr)));
+    if (out.low_siblings) IMT_TRY_CUDA(ctx, sib_low.alloc(C * depth * sizeof(Fr)));
+    if (out.new_siblings) IMT_TRY_CUDA(ctx, sib_new.alloc(C * depth * sizeof(Fr)));
+    if (out.old_roots) IMT_TRY_CUDA(ctx, r_old.alloc(C * sizeof(Fr)));
+    if (out.new_roots) IMT_TRY_CUDA(ctx, r_new.alloc(C * sizeof(Fr)));
+    if (out.low_helpers) IMT_TRY_CUDA(ctx, h_low.alloc(C * depth));
+    if (out.new_helpers) IMT_TRY_CUDA(ctx, h_new.alloc(C * depth));
+    if (out.low_idx) IMT_TRY_CUDA(ctx, low_idx.alloc(C * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, chunk_keys.alloc(C * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, chunk_slots.alloc(C * sizeof(uint32_t)));
+    IMT_TRY_CUDA(ctx, alt_keys.alloc(t->index_capacity * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, alt_slots.alloc(t->index_capacity * sizeof(uint32_t)));
+
+    for (size_t off = 0; off < b; off += C) {
+        const size_t cb = std::min(C, b - off);
+        const unsigned writes = (unsigned)(2 * cb);
+        const uint64_t first = first_idx + off;
+        const uint4* cvals = vals.as<uint4>() + 2 * off;
+        k_ins_resolve<<<grid_for(cb, 128), 128, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied, cvals, cb, first,
+                                                                 ctx->fmt, x.as<uint64_t>(), upd.as<uint4>(), low_old.as<uint4>(),
+                                                                 largest.as<uint8_t>());
+        k_ins_links<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(x.as<uint64_t>(), writes, depth, prev.as<int>(), last.as<uint8_t>());
+        ctx->launches += 2;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        // version 0 of every write: the hash of its leaf preimage (IMT:662-671)
+        IMT_TRY(launch_hash(ctx, 3, upd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
+        for (unsigned l = 0; l < depth; ++l) {
+            k_ins_level<<<grid_for(writes, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+                ver.as<uint4>(), (const uint4*)t->d_levels, t->n, l, x.as<uint64_t>(), prev.as<int>(), writes, depth, ctx->fmt,
+                out.low_siblings ? sib_low.as<uint4>() : nullptr, out.new_siblings ? sib_new.as<uint4>() : nullptr);
+            ++ctx->launches;
+        }
+        k_ins_outputs<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), (const uint4*)t->d_levels, t->n, x.as<uint64_t>(), (unsigned)cb,
+                                                                  depth, ctx->fmt, out.old_roots ? r_old.as<uint4>() : nullptr,
+                                                                  out.new_roots ? r_new.as<uint4>() : nullptr,
+                                                                  out.low_helpers ? h_low.as<uint8_t>() : nullptr,
+                                                                  out.new_helpers ? h_new.as<uint8_t>() : nullptr,
+                                                                  out.low_idx ? low_idx.as<uint64_t>() : nullptr);
+        k_ins_commit<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), upd.as<uint4>(), x.as<uint64_t>(),
+                                                                                last.as<uint8_t>(), writes, depth, t->n, (uint4*)t->d_levels,
+                                                                                (uint4*)t->d_pre);
+        ctx->launches += 2;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        // ---- witnesses of this chunk back to the caller
+        auto d2h = [&](void* host, size_t stride, const void* dev) -> cudaError_t {
+            if (!host || stride == 0) return cudaSuccess;
+            return cudaMemcpyAsync((char*)host + off * stride, dev, cb * stride, cudaMemcpyDeviceToHost, ctx->stream);
+        };
+        IMT_TRY_CUDA(ctx, d2h(out.old_roots, sizeof(Fr), r_old.p));
+        IMT_TRY_CUDA(ctx, d2h(out.new_roots, sizeof(Fr), r_new.p));
+        IMT_TRY_CUDA(ctx, d2h(out.low_idx, sizeof(uint64_t), low_idx.p));
+        IMT_TRY_CUDA(ctx, d2h(out.low_leaves, 3 * sizeof(Fr), low_old.p));
+        IMT_TRY_CUDA(ctx, d2h(out.low_siblings, depth * sizeof(Fr), sib_low.p));
+        IMT_TRY_CUDA(ctx, d2h(out.new_siblings, depth * sizeof(Fr), sib_new.p));
+        IMT_TRY_CUDA(ctx, d2h(out.low_helpers, depth, h_low.p));
+        IMT_TRY_CUDA(ctx, d2h(out.new_helpers, depth, h_new.p));
+        IMT_TRY_CUDA(ctx, d2h(out.is_largest, 1, largest.p));
+        if (out.new_leaves) {  // upd[2k+1], strided
+            IMT_TRY_CUDA(ctx, cudaMemcpy2DAsync((char*)out.new_leaves + off * 3 * sizeof(Fr), 3 * sizeof(Fr), (const char*)upd.p + 3 * sizeof(Fr),
+                                                6 * sizeof(Fr), 3 * sizeof(Fr), cb, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        // ---- keep the sorted index current: merge this chunk's keys into it
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(chunk_keys.p, cvals, cb * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        k_iota_slots<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(chunk_slots.as<uint32_t>(), cb, first);
+        ++ctx->launches;
+        IMT_TRY(sort_pairs(ctx, chunk_keys.as<Fr>(), chunk_slots.as<uint32_t>(), cb));
+        k_merge_rank<<<grid_for(t->occupied + cb, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
+                                                                              chunk_keys.as<uint4>(), chunk_slots.as<uint32_t>(), cb,
+                                                                              alt_keys.as<uint4>(), alt_slots.as<uint32_t>());
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        void* old_keys = t->d_sorted_keys;  // the merged arrays become the index; the old ones the next merge target
+        void* old_slots = t->d_sorted_slots;
+        t->d_sorted_keys = alt_keys.as<Fr>(), t->d_sorted_slots = alt_slots.as<uint32_t>();
+        alt_keys.p = old_keys, alt_slots.p = old_slots;
+        t->occupied += cb;
+        t->head_next_zero = false;
+    }
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}

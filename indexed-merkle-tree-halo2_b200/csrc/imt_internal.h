@@ -1,0 +1,135 @@
+// Internal declarations shared by the translation units of libimt_b200.so (not part of the C-ABI).
+//   imt_capi.cu     context, batched hashing, tree build, paths, folds, traces, sharding cap, calibration
+//   imt_indexed.cu  sorted-key index, low-leaf lookups, non-inclusion witnesses, batched inserts
+// Each translation unit that hashes owns a private __constant__ copy of the Poseidon parameters (the library is
+// built without relocatable device code); imt_ctx_create uploads both.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "imt_b200.h"
+#include "poseidon.cuh"
+
+struct imt_ctx {
+    int device = 0;
+    int fmt = 0;                         // imt_fe_format
+    cudaStream_t stream = nullptr;       // compute (own_stream unless the caller supplied one)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
+    uint32_t* d_err = nullptr;           // device error bits, see kErr*
+    uint32_t* h_err = nullptr;           // pinned mirror
+    uint64_t launches = 0;
+    std::string last_error;
+    // optional per-launch device timing of the hash kernels
+    bool timing = false;
+    struct Timed {
+        cudaEvent_t a, b;
+        int arity;
+        size_t hashes;
+    };
+    std::vector<Timed> pending;
+    double kernel_ms[4] = {0, 0, 0, 0};
+    uint64_t kernel_launches[4] = {0, 0, 0, 0};
+    uint64_t kernel_hashes[4] = {0, 0, 0, 0};
+};
+
+struct imt_tree {
+    imt_ctx* ctx = nullptr;
+    size_t n = 0;                 // leaves on this rank
+    unsigned depth = 0;           // log2(n)
+    imt::Fr* d_levels = nullptr;  // 2n - 1 FE, Montgomery, level 0 first
+    imt::Fr* d_pre = nullptr;     // 3n FE in the context format (only when built from leaves)
+    bool owns_pre = false;
+    // subtree sharding
+    unsigned rank = 0, world = 1, cap_depth = 0;
+    imt::Fr* d_cap = nullptr;  // 2*world - 1 FE, Montgomery
+    unsigned cap_alloc_world = 0;
+    bool cap_valid = false;  // a rebuild makes the attached cap stale until the roots are exchanged again
+    // sorted index over the occupied leaves (low-leaf lookups); built lazily, kept current by imt_insert_batch
+    bool index_valid = false;
+    size_t occupied = 0;                 // occupied slots form the prefix [0, occupied)
+    size_t index_capacity = 0;           // entries the two arrays below can hold
+    imt::Fr* d_sorted_keys = nullptr;    // canonical integer values, ascending
+    uint32_t* d_sorted_slots = nullptr;  // slot of each key
+    bool head_next_zero = false;         // preimage[0].next_val == 0  (the reference's first-insert branch, IMT:640)
+};
+
+namespace imt {
+
+constexpr int kFmtCanonical = 0;
+constexpr int kFmtMontgomery = 1;
+constexpr int kHashThreads = 128;
+
+// bits of imt_ctx::d_err
+constexpr uint32_t kErrNonCanonical = 1u;   // an input FE >= p
+constexpr uint32_t kErrIndexOob = 2u;       // a leaf index outside the tree
+constexpr uint32_t kErrNotWellFormed = 4u;  // preimages are not a consistent indexed tree
+constexpr uint32_t kErrBadInsert = 8u;      // insert value is 0, already present, or repeated inside the batch
+
+// FE offset of level `lvl` inside the concatenated level buffer of an n-leaf tree (n a power of two)
+__host__ __device__ __forceinline__ size_t level_offset(size_t n, unsigned lvl) { return 2 * n - 2 * (n >> lvl); }
+
+}  // namespace imt
+
+#define IMT_TRY_CUDA(ctx, expr)                                                     \
+    do {                                                                            \
+        cudaError_t e_ = (expr);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            return IMT_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define IMT_TRY(expr)                \
+    do {                             \
+        imt_status s_ = (expr);      \
+        if (s_ != IMT_OK) return s_; \
+    } while (0)
+
+namespace imt_host {
+
+inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+inline imt_status fail(imt_ctx* ctx, imt_status st, const char* what) {
+    ctx->last_error = what;
+    return st;
+}
+
+// RAII device buffer
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    void* release() {
+        void* q = p;
+        p = nullptr;
+        return q;
+    }
+    template <class T>
+    T* as() { return static_cast<T*>(p); }
+};
+
+// ---- implemented in imt_capi.cu
+imt_status clear_err(imt_ctx* ctx);
+// waits for the compute stream and turns the device error bits into a status
+imt_status finish(imt_ctx* ctx);
+// out[i] = H(in[arity*i ..]) on `s`; formats are imt::kFmt*
+imt_status launch_hash(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
+// dense FE array between formats (validates < p)
+imt_status launch_convert(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int from_fmt, int to_fmt);
+// batched get_proof from device indices into device buffers (any of d_helpers / d_helpers_fe may be null)
+imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe);
+
+// ---- implemented in imt_indexed.cu
+cudaError_t upload_params_indexed(const imt::PoseidonParams* host_params);
+void invalidate_index(imt_tree* t);
+
+}  // namespace imt_host

@@ -4,35 +4,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "poseidon.cuh"
+#include "kernels_common.cuh"
 
 namespace imt {
-
-__constant__ PoseidonParams c_params;
-
-constexpr int kFmtCanonical = 0;
-constexpr int kFmtMontgomery = 1;
-constexpr int kHashThreads = 128;
-
-__device__ __forceinline__ void load_fe(uint32_t* x, const uint4* p) {
-    const uint4 a = __ldg(p), b = __ldg(p + 1);
-    x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
-    x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-}
-__device__ __forceinline__ void store_fe(uint4* p, const uint32_t* x) {
-    p[0] = make_uint4(x[0], x[1], x[2], x[3]);
-    p[1] = make_uint4(x[4], x[5], x[6], x[7]);
-}
-// user format -> Montgomery (semi-reduced). Returns false when the input is not < p.
-__device__ __forceinline__ bool ingest(uint32_t* x, int fmt) {
-    const bool ok = is_canonical(x);
-    if (fmt == kFmtCanonical) to_mont(x, x);
-    return ok;
-}
-// Montgomery canonical -> user format
-__device__ __forceinline__ void egress(uint32_t* x, int fmt) {
-    if (fmt == kFmtCanonical) from_mont(x, x);
-}
 
 // out[i] = H(in[ARITY*i .. ARITY*i + ARITY)). in_fmt/out_fmt select canonical <-> Montgomery conversion at the
 // edges; tree levels are Montgomery on both sides.
@@ -48,7 +22,7 @@ __global__ void __launch_bounds__(kHashThreads) k_hash(const uint4* __restrict__
         load_fe(x[j], in + 2 * (ARITY * i + j));
         ok &= ingest(x[j], in_fmt);
     }
-    if (!ok) atomicOr(err, 1u);
+    if (!ok) atomicOr(err, kErrNonCanonical);
     NoTrace nt;
     hash_fixed<ARITY>(d, x, c_params, nt);
     egress(d, out_fmt);
@@ -86,7 +60,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __rest
         load_fe(x[j], in + 2 * (ARITY * i + j));
         ok &= ingest(x[j], fmt);
     }
-    if (!ok) atomicOr(err, 1u);
+    if (!ok) atomicOr(err, kErrNonCanonical);
     if (states) {
         TraceSink sink{states + i * (size_t)(kStatesPerHash * 3 * 2), fmt};
         hash_fixed<ARITY>(d, x, c_params, sink);
@@ -97,9 +71,6 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __rest
     egress(d, fmt);
     if (digests) store_fe(digests + 2 * i, d);
 }
-
-// FE offset of level `lvl` inside the concatenated level buffer of an n-leaf tree (n a power of two)
-__host__ __device__ __forceinline__ size_t level_offset(size_t n, unsigned lvl) { return 2 * n - 2 * (n >> lvl); }
 
 // Batched get_proof: one thread per (query, level). For a sharded tree the top `cap_depth` levels come from the
 // replicated cap (built over the gathered subtree roots) and `rank` locates this subtree inside it.
@@ -115,7 +86,7 @@ __global__ void k_gather_proofs(const uint4* __restrict__ levels, const uint4* _
     const uint64_t g = idx[qi];
     const uint64_t base = (uint64_t)rank * n_local;
     if (g < base || g >= base + n_local) {
-        atomicOr(err, 2u);
+        atomicOr(err, kErrIndexOob);
         return;
     }
     const uint64_t local = g - base;
@@ -180,7 +151,7 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
         }
         index >>= 1;
     }
-    if (!ok) atomicOr(err, 1u);
+    if (!ok) atomicOr(err, kErrNonCanonical);
     canonicalize(h);  // depth 0: the leaf itself, possibly semi-reduced after ingest
     if (ok_out) {
         uint32_t r[8];
@@ -205,7 +176,7 @@ __global__ void k_convert(const uint4* __restrict__ in, uint4* __restrict__ out,
     if (i >= n) return;
     uint32_t x[8];
     load_fe(x, in + 2 * i);
-    if (!is_canonical(x)) atomicOr(err, 1u);
+    if (!is_canonical(x)) atomicOr(err, kErrNonCanonical);
     if (from_fmt != to_fmt) {
         if (to_fmt == kFmtMontgomery) {
             to_mont(x, x);

@@ -261,6 +261,13 @@ class Tree:
             self.engine._check(self._lib.imt_tree_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
         return sib, hel
 
+    @property
+    def occupied(self):
+        """number of occupied slots = the slot the next insert goes to"""
+        m = ctypes.c_size_t()
+        self.engine._check(self._lib.imt_tree_occupied(self._h, ctypes.byref(m)))
+        return int(m.value)
+
     def low_leaf_lookup(self, values):
         v = _fe_array(values, ())
         q = v.shape[0]
@@ -279,8 +286,10 @@ class Tree:
                                                              _ptr(o["is_largest"])))
         return o
 
-    def insert_batch(self, new_vals, first_idx):
+    def insert_batch(self, new_vals, first_idx=None):
         v = _fe_array(new_vals, ())
+        if first_idx is None:
+            first_idx = self.occupied
         b, d = v.shape[0], self.depth
         o = dict(old_roots=np.empty((b, 4), np.uint64), low_idx=np.empty(b, np.uint64), low_leaves=np.empty((b, 3, 4), np.uint64),
                  low_siblings=np.empty((b, d, 4), np.uint64), low_helpers=np.empty((b, d), np.uint8),

@@ -1,0 +1,276 @@
+"""GPU parity tests of the indexed-leaf logic: low-leaf lookups, non-inclusion witnesses and
+batched inserts through the C-ABI, against the oracle's restatement of the reference's test helpers
+(update_idx_leaf IMT:632-660, insert orchestration IMT:710-741) — bit-exact. Run with `-m gpu`."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import imt_b200
+from imt_b200 import synth, _ffi
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+P = imt_b200.P
+WIT = ["old_root", "low_idx", "low_leaf", "low_proof", "low_helper", "new_root", "new_leaf", "new_proof", "new_helper", "is_largest"]
+GPU = ["old_roots", "low_idx", "low_leaves", "low_siblings", "low_helpers", "new_roots", "new_leaves", "new_siblings", "new_helpers", "is_largest"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = imt_b200.Engine(0, "canonical")
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_mont():
+    e = imt_b200.Engine(0, "montgomery")
+    yield e
+    e.close()
+
+
+def to_mont(a):
+    return O.fes([x * (1 << 256) % P for x in O.to_ints(a)]).reshape(np.asarray(a).shape)
+
+
+def from_mont(a):
+    rinv = pow(1 << 256, -1, P)
+    return O.fes([x * rinv % P for x in O.to_ints(a)]).reshape(np.asarray(a).shape)
+
+
+def assert_witness_equal(got, k, want):
+    for g, w in zip(GPU, WIT):
+        a, b = got[g][k], want[w]
+        assert np.array_equal(np.asarray(a), np.asarray(b)), f"insert {k}: {g} differs"
+
+
+def test_reference_scenario_as_one_batch(eng):
+    """test_insert_leaf_multiple_round (IMT:679-741): 6 inserts into the empty depth-3 tree, in ONE device batch.
+    Roots / low-leaf indices are the committed fixtures; every other witness field is compared with the oracle running
+    the reference's own re-hash + rebuild per round."""
+    pre = np.zeros((8, 3, 4), np.uint64)
+    tree = eng.build_from_leaves(pre)
+    assert imt_b200.fe_to_int(tree.root()) == int(GOLD["empty_depth3_root"])
+    assert tree.occupied == 1
+    vals = O.fes(GOLD["scenario_inserts"])
+    got = tree.insert_batch(vals, 1)
+    assert [int(v) for v in got["low_idx"]] == GOLD["scenario_low_idx"]
+    assert [str(v) for v in O.to_ints(got["new_roots"])] == GOLD["scenario_roots"]
+    st = O.InsertState(pre)
+    for k in range(6):
+        assert_witness_equal(got, k, st.insert(vals[k], k + 1, incremental=False))
+    final = tree.preimages(8)
+    assert [[str(v) for v in O.to_ints(leaf)] for leaf in final] == GOLD["scenario_final_preimages"]
+    assert np.array_equal(final, st.pre)
+    assert np.array_equal(tree.root(), st.root()) and tree.occupied == 7
+    for lvl in range(4):
+        assert np.array_equal(tree.level(lvl, 8 >> lvl), O.levels(st.tree, 8)[lvl])
+
+
+def test_reference_scenario_one_insert_at_a_time(eng, eng_mont):
+    for e, enc, dec in ((eng, lambda a: a, lambda a: a), (eng_mont, to_mont, from_mont)):
+        tree = e.build_from_leaves(enc(np.zeros((8, 3, 4), np.uint64)))
+        st = O.InsertState(np.zeros((8, 3, 4), np.uint64))
+        for k, v in enumerate(GOLD["scenario_inserts"]):
+            got = tree.insert_batch(enc(O.fes([v])))
+            want = st.insert(O.fe(v), k + 1, incremental=False)
+            for g, w in zip(GPU, WIT):
+                a = got[g][0]
+                if g in ("old_roots", "low_leaves", "low_siblings", "new_roots", "new_leaves", "new_siblings"):
+                    a = dec(a)
+                assert np.array_equal(np.asarray(a), np.asarray(want[w])), (k, g)
+            assert str(O.to_int(dec(tree.root()))) == GOLD["scenario_roots"][k]
+
+
+def _queries(pre, m, rng, count):
+    vals = [O.to_int(pre[i, 0]) for i in range(1, m)]
+    qs = [0, 1, P - 1, P - 2]
+    if vals:
+        qs += [min(vals) - 1, min(vals) + 1, max(vals) - 1, max(vals) + 1 if max(vals) + 1 < P else 1]
+        qs += rng.sample(vals, min(len(vals), 12))                      # present values: the scan falls through
+    qs += [rng.randrange(P) for _ in range(count)]
+    return O.fes(qs)
+
+
+@pytest.mark.parametrize("n,m", [(256, 200), (256, 256), (64, 1), (64, 2), (2, 1), (2, 2)])
+def test_low_leaf_lookup_matches_the_linear_scan(eng, n, m):
+    rng = random.Random(n * 1000 + m)
+    pre = synth.indexed_preimages(n, m, seed=n + m)
+    tree = eng.build_from_leaves(pre)
+    assert tree.occupied == m
+    qs = _queries(pre, m, rng, 150)
+    low, matched = tree.low_leaf_lookup(qs)
+    for k in range(len(qs)):
+        wl, wm = O.low_leaf(pre, qs[k])
+        assert (int(low[k]), bool(matched[k])) == (wl, wm), (k, O.to_int(qs[k]))
+
+
+def test_low_leaf_lookup_montgomery_context(eng_mont):
+    n, m = 128, 100
+    pre = synth.indexed_preimages(n, m, seed=9)
+    tree = eng_mont.build_from_leaves(to_mont(pre))
+    qs = _queries(pre, m, random.Random(4), 60)
+    low, matched = tree.low_leaf_lookup(to_mont(qs))
+    for k in range(len(qs)):
+        assert (int(low[k]), bool(matched[k])) == O.low_leaf(pre, qs[k])
+
+
+def test_non_inclusion_witnesses(eng):
+    """Everything verify_non_inclusion loads (IMT:127-137): low leaf, its path, is_largest — and the chip's own
+    predicates hold on them (IMT:180-191, 226-228)."""
+    n, m = 1024, 700
+    pre = synth.indexed_preimages(n, m, seed=31)
+    tree = eng.build_from_leaves(pre)
+    top = max(O.to_int(pre[i, 0]) for i in range(m))
+    qs = O.fes([random.Random(8).randrange(1, P) for _ in range(300)] + [top + 1, P - 1])
+    o = tree.non_inclusion_paths(qs)
+    assert o["matched"].all()
+    sib, hel = tree.get_proofs(o["low_idx"])
+    assert np.array_equal(o["siblings"], sib) and np.array_equal(o["helpers"], hel)
+    assert np.array_equal(o["low_leaves"], pre[o["low_idx"].astype(np.int64)])
+    for k in range(len(qs)):
+        wl, wm = O.low_leaf(pre, qs[k])
+        assert int(o["low_idx"][k]) == wl and wm
+        val, nxt, v = O.to_int(o["low_leaves"][k, 0]), O.to_int(o["low_leaves"][k, 1]), O.to_int(qs[k])
+        assert val < v and (v < nxt if not o["is_largest"][k] else nxt == 0)
+    assert o["is_largest"][-1] == 1 and o["is_largest"][-2] == 1
+    ok = eng.verify_proofs(eng.hash3(o["low_leaves"]), o["low_idx"], tree.root(), o["siblings"])
+    assert ok.all()
+
+
+@pytest.mark.parametrize("depth,m,b", [(6, 10, 40), (10, 512, 300), (13, 3000, 4200)])
+def test_insert_batch_matches_sequential_oracle(eng, depth, m, b):
+    """b inserts in one call (b > 4096 crosses the internal chunking) against the oracle advancing one insert at a
+    time; then the device state (preimages, every level, index) against the oracle's final state."""
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, m, seed=depth)
+    tree = eng.build_from_leaves(pre)
+    vals = synth.field_elements(b, seed=1000 + depth)
+    got = tree.insert_batch(vals, m)
+    st = O.InsertState(pre, threads=8)
+    step = 1 if b <= 400 else 7
+    for k in range(b):
+        want = st.insert(vals[k], m + k, incremental=True)
+        if k % step == 0 or k >= b - 3:
+            assert_witness_equal(got, k, want)
+        else:
+            assert np.array_equal(got["new_roots"][k], want["new_root"]) and int(got["low_idx"][k]) == want["low_idx"]
+    assert np.array_equal(tree.preimages(n), st.pre)
+    want_levels = O.levels(st.tree, n)
+    for lvl in range(depth + 1):
+        assert np.array_equal(tree.level(lvl, n >> lvl), want_levels[lvl]), lvl
+    assert tree.occupied == m + b
+    # the merged index answers like a linear scan over the new preimages
+    qs = _queries(st.pre, m + b, random.Random(depth), 80)
+    low, matched = tree.low_leaf_lookup(qs)
+    for k in range(len(qs)):
+        assert (int(low[k]), bool(matched[k])) == O.low_leaf(st.pre, qs[k])
+    # idempotence: a from-scratch build of the updated preimages reproduces the incrementally maintained root
+    assert np.array_equal(eng.build_from_leaves(st.pre).root(), tree.root())
+
+
+def test_insert_batch_matches_full_rebuild_oracle(eng):
+    """small enough for the reference's literal O(n)-per-insert sequence (re-hash all + rebuild all, IMT:724-730)"""
+    n, m, b = 32, 5, 20
+    pre = synth.indexed_preimages(n, m, seed=77)
+    tree = eng.build_from_leaves(pre)
+    vals = synth.field_elements(b, seed=78)
+    got = tree.insert_batch(vals)
+    st = O.InsertState(pre)
+    for k in range(b):
+        assert_witness_equal(got, k, st.insert(vals[k], m + k, incremental=False))
+
+
+def test_insert_errors_leave_the_tree_untouched(eng):
+    n, m = 16, 6
+    pre = synth.indexed_preimages(n, m, seed=5)
+    tree = eng.build_from_leaves(pre)
+    root = tree.root()
+    present = pre[3, 0]
+    fresh = synth.field_elements(3, seed=99)
+    for bad in (np.stack([fresh[0], present]), np.stack([fresh[0], fresh[1], fresh[0]]), np.stack([fresh[0], O.fe(0)])):
+        with pytest.raises(imt_b200.ImtError) as e:
+            tree.insert_batch(bad, m)
+        assert e.value.status == _ffi.ERR_INVALID_ARG
+    with pytest.raises(imt_b200.ImtError) as e:
+        tree.insert_batch(fresh, m + 1)                                  # not the next free slot
+    assert e.value.status == _ffi.ERR_INVALID_ARG
+    with pytest.raises(imt_b200.ImtError) as e:
+        tree.insert_batch(synth.field_elements(n - m + 1, seed=3), m)
+    assert e.value.status == _ffi.ERR_TREE_FULL
+    assert np.array_equal(tree.root(), root) and np.array_equal(tree.preimages(n), pre) and tree.occupied == m
+    # a tree built from hashes has no preimages to index
+    with pytest.raises(imt_b200.ImtError) as e:
+        eng.build_from_hashes(O.hash3(pre, 4)).low_leaf_lookup(fresh)
+    assert e.value.status == _ffi.ERR_INVALID_ARG
+    # preimages that are not a sorted linked list
+    broken = pre.copy()
+    broken[2, 1] = fresh[2]
+    with pytest.raises(imt_b200.ImtError) as e:
+        eng.build_from_leaves(broken).low_leaf_lookup(fresh)
+    assert e.value.status == _ffi.ERR_NOT_WELL_FORMED
+    hole = pre.copy()
+    hole[m + 2] = pre[2]
+    with pytest.raises(imt_b200.ImtError) as e:
+        eng.build_from_leaves(hole).low_leaf_lookup(fresh)
+    assert e.value.status == _ffi.ERR_NOT_WELL_FORMED
+
+
+def test_config5_one_million_lookups_then_4096_inserts(eng):
+    """BASELINE config[4] at depth 20: 1M low-leaf lookups + non-inclusion paths, then a batched insert of 4096
+    leaves with per-insert roots — checked through size-independent properties and spot checks against the oracle."""
+    depth, b = 20, 4096
+    n = 1 << depth
+    m = n - b
+    pre = synth.indexed_preimages(n, m)
+    tree = eng.build_from_leaves(pre)
+    q = 1 << 20
+    qs = synth.field_elements(q, seed=555)
+    low, matched = tree.low_leaf_lookup(qs)
+    assert matched.all()
+    lo = low.astype(np.int64)
+
+    def lt(a, b):  # a < b on (k, 4) little-endian words
+        res = np.zeros(a.shape[0], bool)
+        dec = np.zeros(a.shape[0], bool)
+        for w in (3, 2, 1, 0):
+            res |= ~dec & (a[:, w] < b[:, w])
+            dec |= a[:, w] != b[:, w]
+        return res
+
+    nxt = pre[lo, 1]
+    assert lt(pre[lo, 0], qs).all() and (lt(qs, nxt) | ~nxt.any(axis=1)).all()      # val < v < next_val (or next_val == 0)
+    for k in random.Random(1).sample(range(q), 3):
+        assert (int(low[k]), True) == O.low_leaf(pre, qs[k])
+    part = tree.non_inclusion_paths(qs[:4096])
+    assert np.array_equal(part["low_idx"], low[:4096])
+    assert eng.verify_proofs(eng.hash3(part["low_leaves"]), part["low_idx"], tree.root(), part["siblings"]).all()
+
+    vals = synth.field_elements(b, seed=556)
+    old_root = tree.root()
+    got = tree.insert_batch(vals, m)
+    assert np.array_equal(got["old_roots"][0], old_root)
+    assert np.array_equal(got["old_roots"][1:], got["new_roots"][:-1])              # the roots chain
+    assert np.array_equal(got["new_roots"][-1], tree.root())
+    # every witness verifies the way the chip checks it: low leaf under old_root (IMT:253-263), new leaf under new_root (IMT:305-313)
+    idx_new = np.arange(m, m + b, dtype=np.uint64)
+    assert eng.verify_proofs(eng.hash3(got["low_leaves"]), got["low_idx"], got["old_roots"], got["low_siblings"]).all()
+    assert eng.verify_proofs(eng.hash3(got["new_leaves"]), idx_new, got["new_roots"], got["new_siblings"]).all()
+    # ... and the empty leaf sits under the interim root the chip derives itself (IMT:277-294)
+    low_after = got["low_leaves"].copy()
+    low_after[:, 1] = vals
+    low_after[:, 2] = 0
+    low_after[:, 2, 0] = idx_new
+    roots_i, _ = eng.trace_merkle_proofs(eng.hash3(low_after), got["low_idx"], got["low_siblings"], want_states=False)
+    zero_leaf = np.broadcast_to(eng.hash3(np.zeros((1, 3, 4), np.uint64)), (b, 4))
+    assert eng.verify_proofs(zero_leaf, idx_new, roots_i, got["new_siblings"]).all()
+    # the first inserts against the sequential oracle, the final root against a from-scratch oracle build
+    st = O.InsertState(pre, threads=O.max_threads())
+    for k in range(3):
+        assert_witness_equal(got, k, st.insert(vals[k], m + k, incremental=True))
+    final = tree.preimages(n)
+    assert np.array_equal(O.build_from_preimages(final, O.max_threads()), tree.root())
