@@ -175,6 +175,26 @@ imt_status imt_tree_subtree_root_dev(imt_tree* tree, const void** d_subtree_root
 imt_status imt_tree_attach_cap(imt_tree* tree, unsigned rank, unsigned world, const void* subtree_roots);
 imt_status imt_tree_attach_cap_dev(imt_tree* tree, unsigned rank, unsigned world, const void* d_subtree_roots);
 
+/* Indexed-leaf lookups on a sharded tree. The preimages of a shard carry GLOBAL slot numbers in next_idx, and the
+ * occupied slots are a global prefix, so each shard's occupied slots are a local prefix. imt_tree_set_shard declares
+ * the shard (attach_cap does the same) so that the sorted index of this rank reports global slots; the linked-list
+ * consistency check of imt_low_leaf_lookup needs the whole list and is skipped on shards (distinctness is kept).
+ *   1. every rank: imt_low_leaf_candidates -> for each query value the largest LOCAL key below it (cand_keys: canonical
+ *      integers, NOT the context format), its global slot, flags (bit 0: candidate exists, bit 1: value present locally)
+ *   2. the caller all-gathers the three arrays ([world][q], rank-major) and the per-rank imt_tree_occupied counts
+ *   3. any rank: imt_low_leaf_merge -> low_idx / matched, identical to imt_low_leaf_lookup on the unsharded tree
+ *      (head_next_zero = imt_tree_head_next_zero of rank 0: the reference's first-insert branch, IMT:640)
+ *   4. the owner of each low_idx serves its preimage (imt_tree_leaves) and path (imt_tree_get_proofs), global indices. */
+imt_status imt_tree_set_shard(imt_tree* tree, unsigned rank, unsigned world);
+imt_status imt_tree_head_next_zero(imt_tree* tree, int* flag);
+imt_status imt_low_leaf_candidates(imt_tree* tree, const void* values, size_t q, void* cand_keys, uint64_t* cand_slots, uint8_t* flags);
+imt_status imt_low_leaf_merge(imt_ctx* ctx, const void* values, const void* cand_keys, const uint64_t* cand_slots, const uint8_t* flags,
+                              unsigned world, size_t q, uint64_t occupied_total, uint64_t n_total, int head_next_zero,
+                              uint64_t* low_idx, uint8_t* matched);
+/* Preimages (3 FE each, context format) of the given slots and is_largest = (next_val == 0). Global indices inside this
+ * rank's range for a shard. Either output may be NULL. */
+imt_status imt_tree_leaves(imt_tree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest);
+
 /* ---------------------------------------------------------------- calibration -------------------------------- */
 /* Integer-multiply roofline calibration: saturates every SM with IMAD.WIDE.U32.X carry chains (the instruction the
  * field arithmetic issues) for about `ms` milliseconds per launch and returns the sustained 32x32->64

@@ -63,6 +63,11 @@ SIGNATURES = {
     "imt_tree_subtree_root_dev": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "imt_tree_attach_cap": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),
     "imt_tree_attach_cap_dev": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),
+    "imt_tree_set_shard": (c_int, [c_void_p, c_uint, c_uint]),
+    "imt_tree_head_next_zero": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "imt_low_leaf_candidates": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "imt_low_leaf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint, c_size_t, c_u64, c_u64, c_int, c_void_p, c_void_p]),
+    "imt_tree_leaves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_calibrate_imad": (c_int, [c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 

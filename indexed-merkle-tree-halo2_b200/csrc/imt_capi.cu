@@ -586,6 +586,7 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
         IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_cap, (2 * (size_t)world - 1) * sizeof(Fr)));
         t->cap_alloc_world = world;
     }
+    if (t->rank != rank || t->world != world) invalidate_index(t);  // slot numbers of the index are global
     t->rank = rank;
     t->world = world;
     t->cap_depth = 0;

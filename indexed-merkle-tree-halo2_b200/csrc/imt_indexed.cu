@@ -75,8 +75,9 @@ __device__ __forceinline__ size_t lower_bound(const uint4* __restrict__ keys, si
 
 // ------------------------------------------------------------------------------------------------- index build
 // keys[i] = canonical val of slot i, slots[i] = i; stats[0] = first empty slot (min), stats[1] = last occupied slot
-// (max). Slot 0 is the head and always counts as occupied; any other slot is occupied iff val != 0.
-__global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__ pre, size_t n, int fmt, uint4* __restrict__ keys,
+// (max). Global slot 0 is the head and always counts as occupied; any other slot is occupied iff val != 0.
+// `base` = global slot of local slot 0 (rank * n for a subtree shard).
+__global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__ pre, size_t n, uint64_t base, int fmt, uint4* __restrict__ keys,
                                                        uint32_t* __restrict__ slots, unsigned long long* __restrict__ stats,
                                                        uint32_t* __restrict__ head_next_zero, uint32_t* __restrict__ err) {
     __shared__ unsigned long long s_min, s_max;
@@ -91,13 +92,13 @@ __global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__
         if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
         store_fe(keys + 2 * i, v);
         slots[i] = (uint32_t)i;
-        const bool occ = i == 0 || !zero256(v);
+        const bool occ = (base + i) == 0 || !zero256(v);
         if (occ) atomicMax(&s_max, (unsigned long long)i);
         else {
             atomicMin(&s_min, (unsigned long long)i);
             if (!zero256(a) || !zero256(b)) atomicOr(err, kErrNotWellFormed);  // an empty slot is {0, 0, 0}
         }
-        if (i == 0) *head_next_zero = zero256(a) ? 1u : 0u;
+        if (base + i == 0) *head_next_zero = zero256(a) ? 1u : 0u;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -108,10 +109,20 @@ __global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__
 
 // the sorted order must be the linked list: next_val / next_idx of the j-th smallest point at the (j+1)-th smallest,
 // the largest points at (0, 0), values are distinct
+// (a shard of a larger tree only sees part of the list: there only distinctness is checked)
 __global__ void __launch_bounds__(256) k_index_check(const uint4* __restrict__ pre, int fmt, const uint4* __restrict__ keys,
-                                                     const uint32_t* __restrict__ slots, size_t m, uint32_t* __restrict__ err) {
+                                                     const uint32_t* __restrict__ slots, size_t m, bool links, uint32_t* __restrict__ err) {
     const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (j >= m) return;
+    if (!links) {
+        if (j + 1 < m) {
+            uint32_t k0[8], k1[8];
+            load_fe(k0, keys + 2 * j);
+            load_fe(k1, keys + 2 * (j + 1));
+            if (cmp256(k0, k1) >= 0) atomicOr(err, kErrNotWellFormed);
+        }
+        return;
+    }
     const size_t s = slots[j];
     uint32_t nv[8], ni[8];
     load_fe(nv, pre + 2 * (3 * s + 1));
@@ -170,11 +181,82 @@ __global__ void __launch_bounds__(256) k_low_leaf_lookup(const uint4* __restrict
     if (matched) matched[i] = hit;
 }
 
-__global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__ pre, const uint64_t* __restrict__ idx, size_t q,
-                                                       uint4* __restrict__ leaves, uint8_t* __restrict__ is_largest) {
+// Sharded lookup, per-rank half: the largest LOCAL key below v (as a canonical integer) with its GLOBAL slot.
+// flags bit 0: a candidate exists, bit 1: v itself is a local key.
+__global__ void __launch_bounds__(256) k_low_leaf_candidates(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
+                                                             uint64_t base, const uint4* __restrict__ values, size_t q, int fmt,
+                                                             uint4* __restrict__ cand_keys, uint64_t* __restrict__ cand_slots,
+                                                             uint8_t* __restrict__ flags, uint32_t* __restrict__ err) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= q) return;
-    const size_t s = idx[i];
+    uint32_t v[8], k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load_fe(v, values + 2 * i);
+    if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
+    const size_t j = lower_bound(keys, m, v);
+    uint8_t f = 0;
+    uint64_t slot = 0;
+    if (j < m) {
+        uint32_t w[8];
+        load_fe(w, keys + 2 * j);
+        if (cmp256(w, v) == 0) f |= 2;
+    }
+    if (j >= 1) {
+        load_fe(k, keys + 2 * (j - 1));
+        slot = base + slots[j - 1];
+        f |= 1;
+    }
+    store_fe(cand_keys + 2 * i, k);
+    cand_slots[i] = slot;
+    flags[i] = f;
+}
+
+// Sharded lookup, replicated half: the winner among the `world` gathered candidates of each query, then the same
+// decision as k_low_leaf_lookup. occupied / n are the GLOBAL counts. v_zero[i] != 0 marks a zero query value.
+__global__ void __launch_bounds__(256) k_low_leaf_merge(const uint4* __restrict__ cand_keys, const uint64_t* __restrict__ cand_slots,
+                                                        const uint8_t* __restrict__ flags, unsigned world, size_t q, uint64_t occupied,
+                                                        uint64_t n, uint32_t head_next_zero, const uint8_t* __restrict__ v_zero,
+                                                        uint64_t* __restrict__ low_idx, uint8_t* __restrict__ matched) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    uint32_t best[8];
+    bool have = false, present = false;
+    uint64_t slot = 0;
+    for (unsigned r = 0; r < world; ++r) {
+        const uint8_t f = flags[(size_t)r * q + i];
+        present |= (f & 2) != 0;
+        if (f & 1) {
+            uint32_t k[8];
+            load_fe(k, cand_keys + 2 * ((size_t)r * q + i));
+            if (!have || cmp256(k, best) > 0) copy256(best, k), slot = cand_slots[(size_t)r * q + i], have = true;
+        }
+    }
+    uint64_t low = 0;
+    uint8_t hit = 0;
+    if (head_next_zero) hit = 1;
+    else if (have && !present) low = slot, hit = 1;
+    else if (!v_zero[i] && occupied < n) low = occupied, hit = 1;
+    low_idx[i] = low;
+    if (matched) matched[i] = hit;
+}
+
+__global__ void __launch_bounds__(256) k_is_zero(const uint4* __restrict__ values, size_t q, uint8_t* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    uint32_t v[8];
+    load_fe(v, values + 2 * i);
+    out[i] = zero256(v) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__ pre, size_t n, uint64_t base,
+                                                       const uint64_t* __restrict__ idx, size_t q, uint4* __restrict__ leaves,
+                                                       uint8_t* __restrict__ is_largest, uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    if (idx[i] < base || idx[i] - base >= n) {
+        atomicOr(err, kErrIndexOob);
+        return;
+    }
+    const size_t s = idx[i] - base;
     uint4 w[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) w[k] = __ldg(pre + 6 * s + k);
@@ -438,7 +520,7 @@ imt_status ensure_index(imt_tree* t) {
     const unsigned long long init[3] = {(unsigned long long)t->n, 0ull, 0ull};
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(stats.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY(clear_err(ctx));
-    k_index_extract<<<grid_for(t->n, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, ctx->fmt, (uint4*)t->d_sorted_keys,
+    k_index_extract<<<grid_for(t->n, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, (uint64_t)t->rank * t->n, ctx->fmt, (uint4*)t->d_sorted_keys,
                                                                  t->d_sorted_slots, stats.as<unsigned long long>(),
                                                                  (uint32_t*)(stats.as<unsigned long long>() + 2), ctx->d_err);
     ++ctx->launches;
@@ -448,11 +530,10 @@ imt_status ensure_index(imt_tree* t) {
     IMT_TRY(finish(ctx));
     const size_t m = (size_t)got[0];
     if (got[1] >= m) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, "occupied slots do not form a prefix");
-    if (m == 0) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, imt_status_string(IMT_ERR_NOT_WELL_FORMED));
     IMT_TRY(sort_pairs(ctx, t->d_sorted_keys, t->d_sorted_slots, m));
     IMT_TRY(clear_err(ctx));
-    k_index_check<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, ctx->fmt, (const uint4*)t->d_sorted_keys,
-                                                             t->d_sorted_slots, m, ctx->d_err);
+    if (m) k_index_check<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, ctx->fmt, (const uint4*)t->d_sorted_keys,
+                                                             t->d_sorted_slots, m, t->world == 1, ctx->d_err);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     IMT_TRY(finish(ctx));
@@ -472,7 +553,7 @@ imt_status lookup_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_l
     return IMT_OK;
 }
 
-bool sharded(const imt_tree* t) { return t->cap_valid || t->world > 1; }
+bool sharded(const imt_tree* t) { return t->world > 1; }
 
 }  // namespace
 
@@ -535,9 +616,9 @@ extern "C" imt_status imt_non_inclusion_paths(imt_tree* t, const void* values, s
     IMT_TRY(clear_err(ctx));
     IMT_TRY(lookup_dev(t, dv.p, q, dl.as<uint64_t>(), dm.as<uint8_t>()));
     if (low_leaves || is_largest) {
-        k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, dl.as<uint64_t>(), q,
+        k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, 0, dl.as<uint64_t>(), q,
                                                                    low_leaves ? dlv.as<uint4>() : nullptr,
-                                                                   is_largest ? dlg.as<uint8_t>() : nullptr);
+                                                                   is_largest ? dlg.as<uint8_t>() : nullptr, ctx->d_err);
         ++ctx->launches;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
     }
@@ -688,5 +769,108 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     }
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- sharded lookups
+extern "C" imt_status imt_tree_set_shard(imt_tree* t, unsigned rank, unsigned world) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    if (world == 0 || (world & (world - 1)) || rank >= world) return fail(t->ctx, IMT_ERR_INVALID_ARG, "bad rank/world");
+    if (t->rank != rank || t->world != world) {
+        t->cap_valid = false;
+        invalidate_index(t);
+    }
+    t->rank = rank;
+    t->world = world;
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_tree_head_next_zero(imt_tree* t, int* flag) {
+    if (!t || !flag) return IMT_ERR_INVALID_ARG;
+    IMT_TRY(ensure_index(t));
+    *flag = t->head_next_zero ? 1 : 0;
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_low_leaf_candidates(imt_tree* t, const void* values, size_t q, void* cand_keys, uint64_t* cand_slots, uint8_t* flags) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!values || !cand_keys || !cand_slots || !flags)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    IMT_TRY(ensure_index(t));
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dv, dk, ds, df;
+    IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dk.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, ds.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, df.alloc(q));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_low_leaf_candidates<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
+                                                                     (uint64_t)t->rank * t->n, (const uint4*)dv.p, q, ctx->fmt, dk.as<uint4>(),
+                                                                     ds.as<uint64_t>(), df.as<uint8_t>(), ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(cand_keys, dk.p, q * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(cand_slots, ds.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(flags, df.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_low_leaf_merge(imt_ctx* ctx, const void* values, const void* cand_keys, const uint64_t* cand_slots, const uint8_t* flags,
+                                         unsigned world, size_t q, uint64_t occupied_total, uint64_t n_total, int head_next_zero,
+                                         uint64_t* low_idx, uint8_t* matched) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (q && (!values || !cand_keys || !cand_slots || !flags || !low_idx)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0 || world == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dv, dz, dk, ds, df, dl, dm;
+    IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dz.alloc(q));
+    IMT_TRY_CUDA(ctx, dk.alloc(world * q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, ds.alloc(world * q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, df.alloc(world * q));
+    IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dm.alloc(q));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dk.p, cand_keys, world * q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ds.p, cand_slots, world * q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(df.p, flags, world * q, cudaMemcpyHostToDevice, ctx->stream));
+    k_is_zero<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)dv.p, q, dz.as<uint8_t>());
+    k_low_leaf_merge<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)dk.p, ds.as<uint64_t>(), df.as<uint8_t>(), world, q, occupied_total,
+                                                                n_total, head_next_zero ? 1u : 0u, dz.as<uint8_t>(), dl.as<uint64_t>(),
+                                                                dm.as<uint8_t>());
+    ctx->launches += 2;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_idx, dl.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matched) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(matched, dm.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_tree_leaves(imt_tree* t, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && !indices) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf di, dl, dg;
+    IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
+    if (leaves) IMT_TRY_CUDA(ctx, dl.alloc(q * 3 * sizeof(Fr)));
+    if (is_largest) IMT_TRY_CUDA(ctx, dg.alloc(q));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, (uint64_t)t->rank * t->n * (t->world > 1 ? 1 : 0),
+                                                               di.as<uint64_t>(), q, leaves ? dl.as<uint4>() : nullptr,
+                                                               is_largest ? dg.as<uint8_t>() : nullptr, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    if (leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(leaves, dl.p, q * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (is_largest) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dg.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }

@@ -184,6 +184,19 @@ class Engine:
         self._check(self._lib.imt_trace_merkle_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(sib), q, depth, _ptr(states), _ptr(roots)))
         return roots, states
 
+    def low_leaf_merge(self, values, cand_keys, cand_slots, flags, occupied_total, n_total, head_next_zero):
+        """replicated half of a sharded lookup: [world][q] gathered candidates -> (low_idx, matched)"""
+        v = _fe_array(values, ())
+        q = v.shape[0]
+        ck = np.ascontiguousarray(cand_keys, dtype=np.uint64).reshape(-1, q, 4)
+        world = ck.shape[0]
+        cs = np.ascontiguousarray(cand_slots, dtype=np.uint64).reshape(world, q)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8).reshape(world, q)
+        low, matched = np.empty(q, np.uint64), np.empty(q, np.uint8)
+        self._check(self._lib.imt_low_leaf_merge(self._h, _ptr(v), _ptr(ck), _ptr(cs), _ptr(fl), world, q, int(occupied_total),
+                                                 int(n_total), 1 if head_next_zero else 0, _ptr(low), _ptr(matched)))
+        return low, matched.astype(bool)
+
     def calibrate_imad(self, ms=200.0):
         rate, mhz = ctypes.c_double(), ctypes.c_double()
         self._check(self._lib.imt_calibrate_imad(self._h, float(ms), ctypes.byref(rate), ctypes.byref(mhz)))
@@ -300,6 +313,29 @@ class Tree:
         return o
 
     # ---- subtree sharding
+    def set_shard(self, rank, world):
+        self.engine._check(self._lib.imt_tree_set_shard(self._h, rank, world))
+
+    @property
+    def head_next_zero(self):
+        f = ctypes.c_int()
+        self.engine._check(self._lib.imt_tree_head_next_zero(self._h, ctypes.byref(f)))
+        return bool(f.value)
+
+    def low_leaf_candidates(self, values):
+        v = _fe_array(values, ())
+        q = v.shape[0]
+        keys, slots, flags = np.empty((q, 4), np.uint64), np.empty(q, np.uint64), np.empty(q, np.uint8)
+        self.engine._check(self._lib.imt_low_leaf_candidates(self._h, _ptr(v), q, _ptr(keys), _ptr(slots), _ptr(flags)))
+        return keys, slots, flags
+
+    def leaves(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        out, lg = np.empty((q, 3, 4), np.uint64), np.empty(q, np.uint8)
+        self.engine._check(self._lib.imt_tree_leaves(self._h, _ptr(idx), q, _ptr(out), _ptr(lg)))
+        return out, lg
+
     def attach_cap(self, rank, world, subtree_roots):
         """after (re)building: exchange the N subtree roots (root() of each rank) and attach them here"""
         r = _fe_array(subtree_roots, ())

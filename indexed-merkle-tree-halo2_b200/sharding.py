@@ -1,0 +1,155 @@
+"""Subtree sharding, one process per GPU over torch.distributed.
+
+A depth-d tree over N = 2^k ranks is N independent depth-(d-k) subtrees (rank g owns leaves [g n/N, (g+1) n/N), a
+consequence of level[l+1][i] = H(level[l][2i], level[l][2i+1]), /root/reference/src/utils.rs:43-47) plus a k-level cap.
+The only exchange of the build is ONE all-gather of the N subtree roots (N x 32 bytes); every rank then builds the cap
+redundantly. Queries shard by leaf owner (paths, preimages) or arbitrarily (folds / witness traces); low-leaf lookups
+take one more all-gather of per-rank predecessor candidates.
+
+With the `nccl` backend the root exchange stays on the device (subtree root -> send buffer -> ncclAllGather over
+NVLink -> cap build, no host round trip); with `gloo` the same steps are staged through host memory, which is what the
+CPU tests drive. The engine argument only needs the Engine/Tree methods used here, so the tests can substitute an
+oracle-backed double for the host-side logic.
+"""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class ShardedTree:
+    def __init__(self, engine, local_preimages=None, group=None, d_preimages=None, n_local=None):
+        """local_preimages: this rank's (n_local, 3, 4) uint64 host array — or d_preimages: a CUDA tensor / device
+        pointer with n_local leaves already resident. next_idx fields hold GLOBAL slot numbers."""
+        import torch
+        dist = _dist()
+        self.engine, self.group = engine, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world & (self.world - 1):
+            raise ValueError("the number of ranks must be a power of two")
+        self.on_device = dist.get_backend(group) == "nccl"
+        self._torch = torch
+        self._cdev = torch.device("cuda", engine.device) if self.on_device else torch.device("cpu")
+        if d_preimages is not None:
+            self.tree = engine.build_from_leaves_dev(d_preimages, n_local)
+            self.n_local = int(n_local)
+        else:
+            self.tree = engine.build_from_leaves(local_preimages)
+            self.n_local = int(np.asarray(local_preimages).reshape(-1, 3, 4).shape[0])
+        self.tree.set_shard(self.rank, self.world)
+        if self.on_device:
+            self._send = torch.zeros(4, dtype=torch.int64, device=self._cdev)
+            self._recv = torch.zeros((self.world, 4), dtype=torch.int64, device=self._cdev)
+        self.exchange_roots()
+
+    # ---- build
+    def exchange_roots(self):
+        """all-gather of the N subtree roots + the replicated cap levels; call again after every rebuild"""
+        dist = _dist()
+        if self.on_device:
+            self.tree.root_dev(self._send)
+            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            self.tree.attach_cap_dev(self.rank, self.world, self._recv)
+        else:
+            roots = self._all_gather(self.tree.root())
+            self.tree.attach_cap(self.rank, self.world, roots)
+
+    def rebuild(self, local_preimages=None, d_preimages=None):
+        if d_preimages is not None:
+            self.tree.rebuild_from_leaves_dev(d_preimages)
+        else:
+            self.tree.rebuild_from_leaves(local_preimages)
+        self.exchange_roots()
+
+    @property
+    def depth(self):
+        return self.tree.depth
+
+    @property
+    def num_leaves(self):
+        return self.n_local * self.world
+
+    def root(self):
+        return self.tree.root()
+
+    # ---- collectives on numpy arrays (uint64 / uint8), staged through the backend's device
+    def _all_gather(self, a):
+        torch, dist = self._torch, _dist()
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(self._cdev)
+        t = t.contiguous().unsqueeze(0)  # gloo splits the output along dim 0 and wants each piece shaped like the input
+        out = torch.empty((self.world,) + tuple(t.shape[1:]), dtype=t.dtype, device=self._cdev)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        r = out.cpu().numpy()
+        return r.view(np.uint64) if a.dtype == np.uint64 else r
+
+    def owner(self, indices):
+        return (np.asarray(indices, dtype=np.uint64) // np.uint64(self.n_local)).astype(np.int64)
+
+    def _served_by_owner(self, indices, serve, shapes):
+        """Every rank holds the same `indices`; rank r computes serve(indices it owns) -> tuple of arrays, the pieces are
+        all-gathered (padded to the largest piece) and reassembled in query order on every rank."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        if idx.size and int(idx.max()) >= self.num_leaves:
+            raise IndexError("index out of bounds")
+        own = self.owner(idx)
+        counts = np.bincount(own, minlength=self.world)
+        pad = int(counts.max()) if idx.size else 0
+        mine = np.nonzero(own == self.rank)[0]
+        pieces = serve(idx[mine]) if mine.size else None
+        outs = []
+        for k, (inner, dtype) in enumerate(shapes):
+            buf = np.zeros((pad,) + inner, dtype)
+            if mine.size:
+                buf[: mine.size] = pieces[k]
+            allp = self._all_gather(buf) if pad else np.zeros((self.world, 0) + inner, dtype)
+            full = np.empty((idx.size,) + inner, dtype)
+            for r in range(self.world):
+                full[own == r] = allp[r, : counts[r]]
+            outs.append(full)
+        return outs
+
+    # ---- queries
+    def get_proofs(self, indices):
+        """get_proof (utils.rs:63-85) for GLOBAL leaf indices: the bottom d-k siblings come from the owner's subtree,
+        the top k from the replicated cap. Returns (siblings [q, d, 4], helpers [q, d]) on every rank."""
+        d = self.depth
+        return tuple(self._served_by_owner(indices, lambda ix: self.tree.get_proofs(ix), [((d, 4), np.uint64), ((d,), np.uint8)]))
+
+    def leaves(self, indices):
+        return tuple(self._served_by_owner(indices, lambda ix: self.tree.leaves(ix), [((3, 4), np.uint64), ((), np.uint8)]))
+
+    def low_leaf_lookup(self, values):
+        """update_idx_leaf's scan (IMT:632-660) over the sharded tree: per-rank predecessor candidates from each rank's
+        sorted index, one all-gather, then the same decision as the single-GPU lookup. Replicated result."""
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        keys, slots, flags = self.tree.low_leaf_candidates(v)
+        occ = self._all_gather(np.array([self.tree.occupied, 1 if (self.rank == 0 and self.tree.head_next_zero) else 0], np.uint64))
+        gk, gs, gf = self._all_gather(keys), self._all_gather(slots), self._all_gather(flags)
+        return self.engine.low_leaf_merge(v, gk, gs, gf, int(occ[:, 0].sum()), self.num_leaves, bool(occ[0, 1]))
+
+    def non_inclusion_paths(self, values):
+        """witnesses of verify_non_inclusion (IMT:127-137) for every value, replicated on every rank"""
+        low, matched = self.low_leaf_lookup(values)
+        leaves, largest = self.leaves(low)
+        sib, hel = self.get_proofs(low)
+        return dict(low_idx=low, matched=matched, low_leaves=leaves, siblings=sib, helpers=hel, is_largest=largest)
+
+    def query_slice(self, q):
+        """by-query sharding of pure-compute batches (path folds, witness traces): this rank's slice of q queries"""
+        per = -(-q // self.world)
+        return slice(min(q, self.rank * per), min(q, (self.rank + 1) * per))
+
+    def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True):
+        """compute_merkle_root traces (IMT:78-96) of this rank's query slice: (slice, roots, states). The traces stay
+        on the rank that produced them (19.9 GB for 2^16 depth-24 paths is not gathered)."""
+        lv = np.asarray(leaves, dtype=np.uint64).reshape(-1, 4)
+        sl = self.query_slice(lv.shape[0])
+        if sl.start >= sl.stop:
+            return sl, np.zeros((0, 4), np.uint64), None
+        idx = np.asarray(indices, dtype=np.uint64).reshape(-1)[sl]
+        sib = np.asarray(siblings, dtype=np.uint64).reshape(lv.shape[0], -1, 4)[sl]
+        roots, states = self.engine.trace_merkle_proofs(lv[sl], idx, sib, want_states=want_states)
+        return sl, roots, states

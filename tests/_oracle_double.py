@@ -1,0 +1,121 @@
+"""TEST DOUBLE (test infrastructure, never shipped): the subset of Engine / Tree that sharding.ShardedTree drives,
+computed by the CPU oracle. It lets the world_size-2 gloo tests exercise the host-side sharding logic — root exchange,
+owner routing, candidate merge — in a container without a GPU. The product path never imports this file."""
+import bisect
+
+import numpy as np
+
+import oracle as O
+
+
+class OracleTree:
+    def __init__(self, pre):
+        self.pre = np.ascontiguousarray(pre, dtype=np.uint64).reshape(-1, 3, 4)
+        self.n = self.pre.shape[0]
+        self.local_depth = self.n.bit_length() - 1
+        self.rank, self.world, self.cap = 0, 1, None
+        self._build()
+
+    def _build(self):
+        self.tree = O.tree_build(O.hash3(self.pre, 4), 4)
+
+    def rebuild_from_leaves(self, pre):
+        self.pre = np.ascontiguousarray(pre, dtype=np.uint64).reshape(-1, 3, 4)
+        self.cap = None
+        self._build()
+
+    def set_shard(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def root(self):
+        return (self.cap if self.cap is not None else self.tree)[-1].copy()
+
+    def attach_cap(self, rank, world, roots):
+        self.rank, self.world = rank, world
+        self.cap = O.tree_build(np.ascontiguousarray(roots, dtype=np.uint64).reshape(world, 4), 1) if world > 1 else None
+
+    @property
+    def depth(self):
+        return self.local_depth + (self.world.bit_length() - 1 if self.cap is not None else 0)
+
+    def get_proofs(self, indices):
+        idx = np.asarray(indices, dtype=np.uint64).reshape(-1)
+        sib, hel = np.zeros((idx.size, self.depth, 4), np.uint64), np.zeros((idx.size, self.depth), np.uint8)
+        base = self.rank * self.n if self.cap is not None else 0
+        for k, g in enumerate(idx):
+            local = int(g) - base
+            if not 0 <= local < self.n:
+                raise IndexError("index out of bounds")
+            s, h = O.get_proof(self.tree, self.n, local)
+            sib[k, : self.local_depth], hel[k, : self.local_depth] = s, h
+            if self.cap is not None:
+                s, h = O.get_proof(self.cap, self.world, self.rank)
+                sib[k, self.local_depth:], hel[k, self.local_depth:] = s, h
+        return sib, hel
+
+    def leaves(self, indices):
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1) - (self.rank * self.n if self.world > 1 else 0)
+        out = self.pre[idx]
+        return out, (~out[:, 1].any(axis=1)).astype(np.uint8)
+
+    def _sorted(self):
+        base = self.rank * self.n
+        occ = [i for i in range(self.n) if base + i == 0 or self.pre[i, 0].any()]
+        keys = sorted((O.to_int(self.pre[i, 0]), base + i) for i in occ)
+        return keys
+
+    @property
+    def occupied(self):
+        return len(self._sorted())
+
+    @property
+    def head_next_zero(self):
+        return self.rank == 0 and not self.pre[0, 1].any()
+
+    def low_leaf_candidates(self, values):
+        v = O.to_ints(values)
+        ks = self._sorted()
+        only = [k for k, _ in ks]
+        keys, slots, flags = np.zeros((len(v), 4), np.uint64), np.zeros(len(v), np.uint64), np.zeros(len(v), np.uint8)
+        for i, x in enumerate(v):
+            j = bisect.bisect_left(only, x)
+            if j < len(only) and only[j] == x:
+                flags[i] |= 2
+            if j >= 1:
+                keys[i], slots[i] = O.fe(ks[j - 1][0]), ks[j - 1][1]
+                flags[i] |= 1
+        return keys, slots, flags
+
+
+class OracleEngine:
+    device = 0
+
+    def build_from_leaves(self, pre):
+        return OracleTree(pre)
+
+    def low_leaf_merge(self, values, cand_keys, cand_slots, flags, occupied_total, n_total, head_next_zero):
+        v = O.to_ints(values)
+        q = len(v)
+        ck = np.asarray(cand_keys, dtype=np.uint64).reshape(-1, q, 4)
+        cs, fl = np.asarray(cand_slots).reshape(-1, q), np.asarray(flags).reshape(-1, q)
+        low, matched = np.zeros(q, np.uint64), np.zeros(q, bool)
+        for i in range(q):
+            cands = [(O.to_int(ck[r, i]), int(cs[r, i])) for r in range(ck.shape[0]) if fl[r, i] & 1]
+            present = any(fl[r, i] & 2 for r in range(ck.shape[0]))
+            if head_next_zero:
+                matched[i] = True
+            elif cands and not present:
+                low[i], matched[i] = max(cands)[1], True
+            elif v[i] != 0 and occupied_total < n_total:
+                low[i], matched[i] = occupied_total, True
+        return low, matched
+
+    def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True):
+        roots = []
+        for lf, ix, sb in zip(leaves, indices, siblings):
+            h, ix = lf, int(ix)
+            for s in sb:
+                h = O.hash2(np.stack([h, s]) if ix % 2 == 0 else np.stack([s, h]))[0]
+                ix //= 2
+            roots.append(h)
+        return np.stack(roots), None
