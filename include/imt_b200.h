@@ -62,9 +62,11 @@ const char* imt_last_error(const imt_ctx* ctx);
 const char* imt_status_string(imt_status st);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t imt_ctx_launch_count(const imt_ctx* ctx);
-/* Launch on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of the context's own;
- * NULL restores the internal stream. Lets callers bracket calls with their own events / order them with NCCL. */
+/* Launch on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of the context's own
+ * non-blocking stream, so that callers can bracket calls with their own events and order them against NCCL. NULL is
+ * the CUDA legacy default stream. imt_ctx_reset_stream returns to the internal stream. */
 imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream);
+imt_status imt_ctx_reset_stream(imt_ctx* ctx);
 /* Per-kernel device timing: when enabled every hash launch is bracketed by CUDA events on its stream.
  * imt_ctx_kernel_time returns, for hash kernels of the given arity (2 = node levels, 3 = leaf hashing), the summed
  * device time in ms, the launch count and the number of hashes since the last reset. */

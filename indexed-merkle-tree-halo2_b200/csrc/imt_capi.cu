@@ -275,7 +275,14 @@ extern "C" imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL is a stream too: the legacy default stream
+    return IMT_OK;
+}
+extern "C" imt_status imt_ctx_reset_stream(imt_ctx* ctx) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = ctx->own_stream;
     return IMT_OK;
 }
 extern "C" imt_status imt_ctx_enable_timing(imt_ctx* ctx, int enabled) {

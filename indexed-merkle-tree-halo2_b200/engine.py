@@ -92,8 +92,12 @@ class Engine:
         return int(self._lib.imt_ctx_launch_count(self._h))
 
     def set_stream(self, cuda_stream_ptr):
-        """launch on a caller-owned cudaStream_t (int; 0/None = the engine's own stream)"""
-        self._check(self._lib.imt_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+        """launch on a caller-owned cudaStream_t (int handle; 0 = the legacy default stream, torch's default)"""
+        self._check(self._lib.imt_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_ptr or 0))))
+
+    def reset_stream(self):
+        """back to the engine's own non-blocking stream"""
+        self._check(self._lib.imt_ctx_reset_stream(self._h))
 
     def enable_timing(self, on=True):
         self._check(self._lib.imt_ctx_enable_timing(self._h, 1 if on else 0))

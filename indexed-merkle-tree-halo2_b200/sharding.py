@@ -32,6 +32,10 @@ class ShardedTree:
         self.on_device = dist.get_backend(group) == "nccl"
         self._torch = torch
         self._cdev = torch.device("cuda", engine.device) if self.on_device else torch.device("cpu")
+        if self.on_device:
+            # NCCL orders its work against torch's current stream: run the engine's kernels on that stream too, so the
+            # send buffer is written before the all-gather reads it and the cap build starts after it lands
+            engine.set_stream(torch.cuda.current_stream(self._cdev).cuda_stream)
         if d_preimages is not None:
             self.tree = engine.build_from_leaves_dev(d_preimages, n_local)
             self.n_local = int(n_local)
