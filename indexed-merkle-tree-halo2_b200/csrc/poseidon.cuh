@@ -104,7 +104,19 @@ IMT_HD void partial_round(uint32_t (*s)[8], const PartialRound& pr, Sink& sink) 
     sink.emit(s);
 }
 
-// One permutation, in place. `P` may live in __constant__, shared or host memory.
+// (s0, s1, s2) <- (s1, s2, s0)
+IMT_HD void rotate3(uint32_t (*s)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t t = s[0][i];
+        s[0][i] = s[1][i];
+        s[1][i] = s[2][i];
+        s[2][i] = t;
+    }
+}
+
+#ifdef IMT_PERMUTE_UNROLLED
+// One permutation, in place: every S-box / dot product of a round is its own inlined copy (~150 KB of SASS).
 template <class Sink>
 IMT_HD void permute(uint32_t (*s)[8], const PoseidonParams& P, Sink& sink) {
     add_semi(s[0], s[0], P.pre[0].l);
@@ -118,6 +130,59 @@ IMT_HD void permute(uint32_t (*s)[8], const PoseidonParams& P, Sink& sink) {
 #pragma unroll 1
     for (int r = kHalfF; r < kRF; ++r) full_round(s, P.full[r], P.mds, sink);
 }
+#else
+// One permutation, in place. `P` may live in __constant__, shared or host memory.
+// Compact form: ONE copy each of the S-box, the 3-term dot product and the multiply-add serves all 65 rounds (the
+// state is rotated through fixed registers instead of duplicating code per lane), so the whole permutation is
+// ~25 KB of SASS and stays resident in the 32 KB L1.5 instruction cache; the fully inlined form above is ~150 KB and
+// loses ~20 % of the multiply pipe to instruction-fetch stalls (profiles/). All branches are warp-uniform.
+template <class Sink>
+IMT_HD void permute(uint32_t (*s)[8], const PoseidonParams& P, Sink& sink) {
+    add_semi(s[0], s[0], P.pre[0].l);
+    add_semi(s[1], s[1], P.pre[1].l);
+    add_semi(s[2], s[2], P.pre[2].l);
+    sink.emit(s);
+#pragma unroll 1
+    for (int r = 0; r < kRF + kRP; ++r) {
+        const bool full = r < kHalfF || r >= kHalfF + kRP;
+        const int fr = r < kHalfF ? r : r - kRP;  // index into full[] (full rounds)
+        const int pk = full ? 0 : r - kHalfF;     // index into partial[] (partial rounds)
+        // ---- S-box layer (+ the constants folded behind it): all three lanes, or lane 0 only
+        const int lanes = full ? 3 : 1;
+#pragma unroll 1
+        for (int j = 0; j < lanes; ++j) {
+            const uint32_t* c = full ? P.full[fr][j].l : P.partial[pk].c.l;
+            sbox_add(s[0], s[0], c);
+            if (full) rotate3(s);  // three rotations bring the lanes back in order
+        }
+        // ---- linear layer: dense 3x3 (full rounds) or sparse (row . s ; s_i + col_i * s0)
+        const Fr(*m)[3] = (r == kHalfF - 1) ? P.pre_sparse : P.mds;
+        uint32_t n[3][8] = {};
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+            uint32_t t[8];
+            if (full || j == 0) {
+                const Fr* row = full ? m[j] : P.partial[pk].row;
+                dot3(t, s[0], s[1], s[2], row[0].l, row[1].l, row[2].l);
+            } else {
+                uint32_t sj[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sj[i] = (j == 1) ? s[1][i] : s[2][i];
+                mul_add(t, s[0], P.partial[pk].col[j - 1].l, sj);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // n <- (n1, n2, t): after three steps n = (t0, t1, t2)
+                n[0][i] = n[1][i];
+                n[1][i] = n[2][i];
+                n[2][i] = t[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[0][i] = n[0][i], s[1][i] = n[1][i], s[2][i] = n[2][i];
+        sink.emit(s);
+    }
+}
+#endif
 
 // H(in[0..ARITY)) = update(in) + squeeze_and_reset(), ARITY in {2, 3}: two permutations.
 // Inputs: Montgomery form, semi-reduced. Output: Montgomery form, canonical.
