@@ -32,6 +32,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="build", choices=["build", "paths", "lookups"],
+                    help="build = the headline metric (default); paths = 2^16 path extraction + witness traces (BASELINE config 4); "
+                         "lookups = 1M low-leaf lookups + non-inclusion paths + 4096 inserts (config 5). Single GPU.")
+    ap.add_argument("--queries", type=int, default=0, help="query count of the paths / lookups workloads (default 2^16 / 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -141,11 +145,199 @@ def run_reference(a):
     }), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- secondary workloads
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _ev_time(torch, stream, fn, steps, warmup):
+    """CUDA-event time of `steps` calls of fn on `stream`, ms per call"""
+    for _ in range(warmup):
+        fn()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    stream.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_paths(a):
+    """BASELINE config 4: 2^16 Merkle paths out of the depth-D tree + the per-round Poseidon witness trace of
+    verify_merkle_proof for each (D hashes x 132 x 3 FE per query). One JSON line."""
+    import numpy as np
+    import torch
+    import imt_b200
+    from imt_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    depth, q = a.depth, a.queries or (1 << 16)
+    n = 1 << depth
+    eng = imt_b200.Engine(0, "montgomery")
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    d_pre = synth.field_elements_torch(3 * n, synth.DEFAULT_SEED, device=dev).view(n, 3, 4)
+    tree = eng.build_from_leaves_dev(d_pre, n)
+    g = torch.Generator(device=dev)
+    g.manual_seed(synth.DEFAULT_SEED)
+    d_idx = torch.randint(0, n, (q,), generator=g, device=dev, dtype=torch.int64)
+    d_sib = torch.empty((q, depth, 4), dtype=torch.int64, device=dev)
+    d_hel = torch.empty((q, depth), dtype=torch.uint8, device=dev)
+    d_leaf = torch.empty((q, 4), dtype=torch.int64, device=dev)
+    d_roots = torch.empty((q, 4), dtype=torch.int64, device=dev)
+    d_states = torch.empty((q, depth, 132, 3, 4), dtype=torch.int64, device=dev)   # 19.9 GB at depth 24
+    eng.hash3_dev(d_pre[d_idx].contiguous(), q, d_leaf)                           # leaf hashes of the queried slots
+
+    t_gather = _ev_time(torch, stream, lambda: tree.get_proofs_dev(d_idx, q, d_sib, d_hel), a.steps, a.warmup)
+    l0 = eng.launches
+    t_trace = _ev_time(torch, stream, lambda: eng.trace_merkle_proofs_dev(d_leaf, d_idx, d_sib, q, depth, d_states, d_roots), a.steps, a.warmup)
+    launches = eng.launches - l0
+    t_fold = _ev_time(torch, stream, lambda: eng.trace_merkle_proofs_dev(d_leaf, d_idx, d_sib, q, depth, None, d_roots), a.steps, a.warmup)
+    root = torch.empty(4, dtype=torch.int64, device=dev)
+    tree.root_dev(root)
+    stream.synchronize()
+    assert bool((d_roots == root).all()), "a traced path does not fold to the tree root"
+    hashes = q * depth
+    trace_bytes = hashes * 132 * 96
+    gather_bytes = q * depth * (32 + 32 + 1)
+    peaks = _peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    imad_rate, imad_mhz = eng.calibrate_imad(150.0)
+    # e2e through the host API on a bounded slice (the full trace is 19.9 GB of pageable host memory)
+    qe = min(q, 1 << 11)
+    h_idx = d_idx[:qe].cpu().numpy().astype(np.uint64)
+    h_leaf = d_leaf[:qe].cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    sib, _ = tree.get_proofs(h_idx)
+    _, st = eng.trace_merkle_proofs(h_leaf, h_idx, sib)
+    dt = time.perf_counter() - t0
+    # CPU leg: the oracle tracing the same folds, one thread (the reference's hasher is a &mut borrow)
+    rinv = pow(1 << 256, -1, imt_b200.P)
+    cs = min(qe, 48)
+    lv = O.fes([x * rinv % imt_b200.P for x in O.to_ints(h_leaf[:cs])])
+    sb = O.fes([x * rinv % imt_b200.P for x in O.to_ints(sib[:cs].reshape(-1, 4))]).reshape(cs, depth, 4)
+    t0 = time.perf_counter()
+    for k in range(cs):
+        h, ix = lv[k], int(h_idx[k])
+        for lvl in range(depth):
+            h, _ = O.hash_trace(np.stack([h, sb[k, lvl]]) if ix % 2 == 0 else np.stack([sb[k, lvl], h]))
+            ix //= 2
+    cpu = cs * depth / (time.perf_counter() - t0)
+    out = {
+        "metric": "merkle_path_witness_trace_hashes_per_s", "value": hashes / (t_trace * 1e-3), "unit": "hashes/s", "n_gpus": 1, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": t_trace, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8-montgomery",
+        "data": "synthetic",
+        "config": {"workload": f"2^{q.bit_length() - 1} uniform random paths of the depth-{depth} tree: batched get_proof + verify_merkle_proof witness trace "
+                               f"(132 x 3 FE per hash)", "depth": depth, "queries": q, "hashes_per_step": hashes, "trace_bytes_per_step": trace_bytes,
+                   "l2_policy": f"trace output {trace_bytes / 2**30:.1f} GiB per step, far larger than L2", "seed": synth.DEFAULT_SEED, "fe_format": "montgomery"},
+        "e2e": {"value": qe * depth / dt, "unit": "hashes/s", "sample": f"{qe} queries through the host API (paths + traces copied back to pageable host memory)",
+                "h2d_bytes_per_step": qe * (8 + 32 + depth * 32), "d2h_bytes_per_step": qe * depth * (32 + 1 + 132 * 96)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "imad", "kernel": "k_fold_paths (trace sink)", "achieved": hashes * MACS_PER_HASH / (t_trace * 1e-3) / 1e9, "peak": imad_rate / 1e9,
+                     "unit": "GMAC/s", "frac": hashes * MACS_PER_HASH / (t_trace * 1e-3) / imad_rate, "traffic": None,
+                     "peak_source": f"imt_calibrate_imad in this run ({imad_mhz:.0f} MHz implied)",
+                     "hbm": {"achieved_gbs": trace_bytes / (t_trace * 1e-3) / 1e9, "peak_gbs": hbm, "frac": trace_bytes / (t_trace * 1e-3) / 1e9 / hbm}},
+        "parts": {"get_proofs_ms": t_gather, "get_proofs_gbs": gather_bytes / (t_gather * 1e-3) / 1e9, "get_proofs_paths_per_s": q / (t_gather * 1e-3),
+                  "fold_without_trace_ms": t_fold, "fold_hashes_per_s": hashes / (t_fold * 1e-3)},
+        "cpu_baseline": {"value": cpu, "unit": "hashes/s", "cores": 1, "kind": "port", "sample": f"{cs} paths x {depth} traced hashes, oracle, 1 thread"},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_lookups(a):
+    """BASELINE config 5: 1M low-leaf (predecessor) lookups + non-inclusion paths on the depth-D indexed tree, then a
+    batched insert of 4096 leaves with per-insert roots. One JSON line (metric: lookups/s)."""
+    import numpy as np
+    import torch
+    import imt_b200
+    from imt_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    depth, q, b = a.depth, a.queries or (1 << 20), 4096
+    n = 1 << depth
+    m = n - b * (a.steps + a.warmup + 1)
+    eng = imt_b200.Engine(0, "canonical")
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    d_pre = synth.indexed_preimages_torch(n, m, device=dev)
+    tree = eng.build_from_leaves_dev(d_pre, n)
+    t0 = time.perf_counter()
+    assert tree.occupied == m                                                      # builds the sorted index (one merge sort of m keys)
+    t_index = time.perf_counter() - t0
+    d_vals = synth.field_elements_torch(q, seed=555, device=dev)
+    d_low = torch.empty(q, dtype=torch.int64, device=dev)
+    d_match = torch.empty(q, dtype=torch.uint8, device=dev)
+    d_sib = torch.empty((q, depth, 4), dtype=torch.int64, device=dev)
+    d_hel = torch.empty((q, depth), dtype=torch.uint8, device=dev)
+    l0 = eng.launches
+    t_lookup = _ev_time(torch, stream, lambda: tree.low_leaf_lookup_dev(d_vals, q, d_low, d_match), a.steps, a.warmup)
+    launches = eng.launches - l0
+    t_paths = _ev_time(torch, stream, lambda: tree.get_proofs_dev(d_low, q, d_sib, d_hel), a.steps, a.warmup)
+    assert bool(d_match.all())
+    # spot check against the oracle's linear scan
+    h_pre = d_pre.cpu().numpy().view(np.uint64)
+    h_vals = d_vals[:4].cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    for k in range(4):
+        assert (int(d_low[k]), True) == O.low_leaf(h_pre, h_vals[k])
+    cpu_lookup = 4 / (time.perf_counter() - t0)
+    # e2e: host values in, low_idx + witnesses out
+    h_q = d_vals.cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    o = tree.non_inclusion_paths(h_q)
+    t_e2e = time.perf_counter() - t0
+    assert np.array_equal(o["low_idx"], d_low.cpu().numpy().astype(np.uint64))
+    # inserts: each step one batch of 4096 (host API: values in, full witness bundle out)
+    ins = []
+    for s in range(a.warmup + a.steps):
+        vals = synth.field_elements(b, seed=9000 + s)
+        t0 = time.perf_counter()
+        w = tree.insert_batch(vals)
+        ins.append(time.perf_counter() - t0)
+    t_ins = sum(ins[a.warmup:]) / a.steps
+    assert np.array_equal(w["new_roots"][-1], tree.root())
+    peaks = _peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    probes = max(1, m.bit_length())
+    out = {
+        "metric": "low_leaf_lookups_per_s", "value": q / (t_lookup * 1e-3), "unit": "lookups/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": t_lookup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 compare", "data": "synthetic",
+        "config": {"workload": f"{q} uniform random low-leaf lookups on the depth-{depth} indexed tree ({m} occupied slots), non-inclusion paths, "
+                               f"then {b} inserts per batch with per-insert roots", "depth": depth, "queries": q, "occupied": m,
+                   "l2_policy": f"sorted index {m * 36 / 2**20:.0f} MiB, random probes", "seed": synth.DEFAULT_SEED, "fe_format": "canonical"},
+        "e2e": {"value": q / t_e2e, "unit": "lookups/s", "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": q * 32,
+                "d2h_bytes_per_step": q * (8 + 1 + 96 + depth * 33 + 1), "note": "imt_non_inclusion_paths: lookup + low leaf + path + is_largest per value"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_low_leaf_lookup", "achieved": q * probes * 32 / (t_lookup * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": q * probes * 32 / (t_lookup * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "note": f"algorithmic bytes = {probes} dependent 32-byte probes per lookup; the top of the search tree stays in L2, so this is a latency-bound gather"},
+        "parts": {"index_build_s": t_index, "non_inclusion_path_gather_ms": t_paths,
+                  "path_gather_gbs": q * depth * 65 / (t_paths * 1e-3) / 1e9, "insert_batch_ms": t_ins * 1e3, "inserts_per_s": b / t_ins,
+                  "insert_hashes_per_s": 2 * b * (depth + 1) / t_ins},
+        "cpu_baseline": {"value": cpu_lookup, "unit": "lookups/s", "cores": 1, "kind": "port",
+                         "sample": "4 lookups by the reference's linear scan (update_idx_leaf, IMT:632-660) over the same preimages, oracle"},
+    }
+    print(json.dumps(out), flush=True)
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.workload == "paths":
+        return run_paths(a)
+    if a.workload == "lookups":
+        return run_lookups(a)
 
     import torch
     import torch.distributed as dist

@@ -116,6 +116,8 @@ imt_status imt_tree_preimages(imt_tree* tree, void* out);
 
 /* get_proof(index) batched  (src/utils.rs:63-85): siblings[q][depth] FE, helpers[q][depth] bytes (1 = left). */
 imt_status imt_tree_get_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers);
+/* Device-pointer variant (indices, siblings, helper bytes all in HBM): for provers that consume witnesses on the GPU. */
+imt_status imt_tree_get_proofs_dev(imt_tree* tree, const uint64_t* d_indices, size_t q, void* d_siblings, uint8_t* d_helpers);
 /* The same helpers as field elements, as the reference returns them (F::from(1) / F::from(0), src/utils.rs:79). */
 imt_status imt_tree_get_proofs_fe(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, void* helpers_fe);
 
@@ -124,10 +126,16 @@ imt_status imt_tree_get_proofs_fe(imt_tree* tree, const uint64_t* indices, size_
 imt_status imt_verify_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots,
                              const void* siblings, size_t q, unsigned depth, uint8_t* ok);
 
+imt_status imt_verify_proofs_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots,
+                                 const void* d_siblings, size_t q, unsigned depth, uint8_t* d_ok);
+
 /* Witness trace of compute_merkle_root (src/indexed_merkle_tree.rs:78-96): for each query the `depth` hashes of
  * the fold, in order, each as 132 x 3 FE; plus the computed roots. states[q][depth][132][3] FE. */
 imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* siblings,
                                    size_t q, unsigned depth, void* states, void* roots);
+
+imt_status imt_trace_merkle_proofs_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_siblings,
+                                       size_t q, unsigned depth, void* d_states, void* d_roots);
 
 /* ---------------------------------------------------------------- indexed-leaf logic ------------------------- */
 /* Low-leaf (predecessor) lookup, the read-only half of update_idx_leaf (src/indexed_merkle_tree.rs:632-660):
@@ -136,6 +144,7 @@ imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint6
  * returns index 0 and leaves the leaves unchanged. Requires a tree built from leaves whose occupied slots form a
  * prefix and a consistent sorted linked list (IMT_ERR_NOT_WELL_FORMED otherwise). */
 imt_status imt_low_leaf_lookup(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched);
+imt_status imt_low_leaf_lookup_dev(imt_tree* tree, const void* d_values, size_t q, uint64_t* d_low_idx, uint8_t* d_matched);
 /* Number of occupied slots (they form the prefix [0, occupied)): the slot the next insert goes to (IMT:733). */
 imt_status imt_tree_occupied(imt_tree* tree, size_t* occupied);
 /* Non-inclusion witnesses for verify_non_inclusion (src/indexed_merkle_tree.rs:127-137): lookup + the low leaf's

@@ -54,6 +54,10 @@ SIGNATURES = {
     "imt_tree_level": (c_int, [c_void_p, c_uint, c_void_p]),
     "imt_tree_preimages": (c_int, [c_void_p, c_void_p]),
     "imt_tree_get_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_tree_get_proofs_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_verify_proofs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
+    "imt_trace_merkle_proofs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
+    "imt_low_leaf_lookup_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_tree_get_proofs_fe": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_verify_proofs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "imt_trace_merkle_proofs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),

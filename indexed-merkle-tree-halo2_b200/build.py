@@ -39,6 +39,7 @@ def build(force=False, verbose=False):
              "-diag-suppress", "550", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         flags.append("-Xptxas=-v")
+    flags += os.environ.get("IMT_NVCC_FLAGS", "").split()  # experiments only, e.g. -DIMT_ILP
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")

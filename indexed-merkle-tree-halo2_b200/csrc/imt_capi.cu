@@ -167,7 +167,7 @@ imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
 imt_status copy_out_fe(imt_ctx* ctx, const Fr* d_src, size_t count, void* h_dst, bool convert_from_mont) {
     if (count == 0) return IMT_OK;
     if (convert_from_mont && ctx->fmt == kFmtCanonical) {
-        DevBuf tmp;
+        DevBuf tmp(ctx);
         IMT_TRY_CUDA(ctx, tmp.alloc(count * sizeof(Fr)));
         k_convert<<<grid_for(count, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, tmp.as<uint4>(), count, kFmtMontgomery,
                                                               kFmtCanonical, ctx->d_err);
@@ -241,6 +241,12 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
         have_params = true;
     }
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {  // scratch buffers come from the default pool: keep freed memory cached instead of returning it to the OS
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, device);
+        unsigned long long keep = ~0ull;
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -325,7 +331,7 @@ static imt_status hash_host(imt_ctx* ctx, const void* in, size_t n, void* out) {
     if (n && (!in || !out)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf din, dout;
+    DevBuf din(ctx), dout(ctx);
     IMT_TRY_CUDA(ctx, din.alloc(n * ARITY * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dout.alloc(n * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * ARITY * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
@@ -363,7 +369,7 @@ extern "C" imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, 
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
-    DevBuf din, dst, ddg;
+    DevBuf din(ctx), dst(ctx), ddg(ctx);
     IMT_TRY_CUDA(ctx, din.alloc(n * arity * sizeof(Fr)));
     if (states) IMT_TRY_CUDA(ctx, dst.alloc(n * state_fe * sizeof(Fr)));
     if (digests) IMT_TRY_CUDA(ctx, ddg.alloc(n * sizeof(Fr)));
@@ -385,7 +391,7 @@ static imt_status build_from_hashes(imt_ctx* ctx, const void* leaf_hashes, size_
     imt_tree* t = nullptr;
     IMT_TRY(tree_alloc(ctx, n, false, &t));
     imt_status st = clear_err(ctx);
-    DevBuf staged;
+    DevBuf staged(ctx);
     const void* d_src = leaf_hashes;
     if (st == IMT_OK && !device_src) {
         if (staged.alloc(n * sizeof(Fr)) != cudaSuccess ||
@@ -454,6 +460,8 @@ extern "C" void imt_tree_destroy(imt_tree* t) {
     if (t->d_cap) cudaFree(t->d_cap);
     if (t->d_sorted_keys) cudaFree(t->d_sorted_keys);
     if (t->d_sorted_slots) cudaFree(t->d_sorted_slots);
+    if (t->d_alt_keys) cudaFree(t->d_alt_keys);
+    if (t->d_alt_slots) cudaFree(t->d_alt_slots);
     delete t;
 }
 
@@ -507,7 +515,7 @@ static imt_status get_proofs(imt_tree* t, const uint64_t* indices, size_t q, voi
     const unsigned depth = t->depth + cap_depth;
     if (q == 0 || depth == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf didx, dsib, dhel, dhfe;
+    DevBuf didx(ctx), dsib(ctx), dhel(ctx), dhfe(ctx);
     IMT_TRY_CUDA(ctx, didx.alloc(q * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, dsib.alloc(q * depth * sizeof(Fr)));
     if (helpers) IMT_TRY_CUDA(ctx, dhel.alloc(q * depth));
@@ -522,6 +530,16 @@ static imt_status get_proofs(imt_tree* t, const uint64_t* indices, size_t q, voi
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }
+extern "C" imt_status imt_tree_get_proofs_dev(imt_tree* t, const uint64_t* d_indices, size_t q, void* d_siblings, uint8_t* d_helpers) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!d_indices || !d_siblings)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_gather_proofs(t, d_indices, q, d_siblings, d_helpers, nullptr));
+    return finish(ctx);
+}
 extern "C" imt_status imt_tree_get_proofs(imt_tree* t, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers) {
     return get_proofs(t, indices, q, siblings, helpers, nullptr);
 }
@@ -529,6 +547,21 @@ extern "C" imt_status imt_tree_get_proofs_fe(imt_tree* t, const uint64_t* indice
     return get_proofs(t, indices, q, siblings, nullptr, helpers_fe);
 }
 
+static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings,
+                                 size_t q, unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (q && (!d_leaves || !d_indices || (depth && !d_siblings) || (d_ok && !d_roots))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    const unsigned fold_threads = q >= (size_t)1 << 20 ? kHashThreads : 32;  // small batches: one warp per block spreads evenly over the SMs
+    k_fold_paths<<<grid_for(q, fold_threads), fold_threads, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
+                                                                           (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
+                                                                           (uint4*)d_states, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return finish(ctx);
+}
 static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots, const void* siblings,
                              size_t q, unsigned depth, uint8_t* ok, void* roots_out, void* states) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
@@ -536,7 +569,7 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
-    DevBuf dl, di, dr, ds, dok, dro, dst;
+    DevBuf dl(ctx), di(ctx), dr(ctx), ds(ctx), dok(ctx), dro(ctx), dst(ctx);
     IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, ds.alloc(q * depth * sizeof(Fr)));
@@ -550,19 +583,23 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dl.p, leaves, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ds.p, siblings, q * depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    IMT_TRY(clear_err(ctx));
-    k_fold_paths<<<grid_for(q, kHashThreads), kHashThreads, 0, ctx->stream>>>(
-        dl.as<uint4>(), di.as<uint64_t>(), ds.as<uint4>(), ok ? dr.as<uint4>() : nullptr, q, depth, ctx->fmt,
-        ok ? dok.as<uint8_t>() : nullptr, roots_out ? dro.as<uint4>() : nullptr, states ? dst.as<uint4>() : nullptr, ctx->d_err);
-    ++ctx->launches;
-    IMT_TRY_CUDA(ctx, cudaGetLastError());
-    IMT_TRY(finish(ctx));
+    IMT_TRY(fold_paths_dev(ctx, dl.p, di.as<uint64_t>(), ok ? dr.p : nullptr, ds.p, q, depth, ok ? dok.as<uint8_t>() : nullptr,
+                           roots_out ? dro.p : nullptr, states ? dst.p : nullptr));
     if (ok) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ok, dok.p, q, cudaMemcpyDeviceToHost, ctx->stream));
     if (roots_out) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(roots_out, dro.p, q * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (states)
         IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, q * depth * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
+}
+extern "C" imt_status imt_verify_proofs_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots,
+                                            const void* d_siblings, size_t q, unsigned depth, uint8_t* d_ok) {
+    if (q && !d_ok) return ctx ? fail(ctx, IMT_ERR_INVALID_ARG, "null buffer") : IMT_ERR_INVALID_ARG;
+    return fold_paths_dev(ctx, d_leaves, d_indices, d_roots, d_siblings, q, depth, d_ok, nullptr, nullptr);
+}
+extern "C" imt_status imt_trace_merkle_proofs_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_siblings,
+                                                  size_t q, unsigned depth, void* d_states, void* d_roots) {
+    return fold_paths_dev(ctx, d_leaves, d_indices, nullptr, d_siblings, q, depth, nullptr, d_roots, d_states);
 }
 extern "C" imt_status imt_verify_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots,
                                         const void* siblings, size_t q, unsigned depth, uint8_t* ok) {
@@ -598,7 +635,7 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
     t->world = world;
     t->cap_depth = 0;
     while ((1u << t->cap_depth) < world) ++t->cap_depth;
-    DevBuf staged;
+    DevBuf staged(ctx);
     const void* d_src = roots;
     if (!device_src) {
         IMT_TRY_CUDA(ctx, staged.alloc(world * sizeof(Fr)));
@@ -630,7 +667,7 @@ extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_m
     cudaDeviceProp prop;
     IMT_TRY_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256;  // 64 resident warps per SM
-    DevBuf out;
+    DevBuf out(ctx);
     IMT_TRY_CUDA(ctx, out.alloc((size_t)blocks * threads * sizeof(uint64_t)));
     cudaEvent_t e0, e1;
     IMT_TRY_CUDA(ctx, cudaEventCreate(&e0));

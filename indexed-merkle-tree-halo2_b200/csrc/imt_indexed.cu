@@ -13,6 +13,9 @@
 #include <cub/device/device_merge_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 
 #include "imt_internal.h"
@@ -493,7 +496,7 @@ imt_status sort_pairs(imt_ctx* ctx, Fr* d_keys, uint32_t* d_slots, size_t count)
     if (count < 2) return IMT_OK;
     size_t temp_bytes = 0;
     IMT_TRY_CUDA(ctx, cub::DeviceMergeSort::SortPairs(nullptr, temp_bytes, d_keys, d_slots, (long long)count, KeyLess(), ctx->stream));
-    DevBuf temp;
+    DevBuf temp(ctx);
     IMT_TRY_CUDA(ctx, temp.alloc(temp_bytes));
     IMT_TRY_CUDA(ctx, cub::DeviceMergeSort::SortPairs(temp.p, temp_bytes, d_keys, d_slots, (long long)count, KeyLess(), ctx->stream));
     ctx->launches += 2;  // block sort + merge passes (at least)
@@ -510,12 +513,14 @@ imt_status ensure_index(imt_tree* t) {
     if (!t->d_sorted_keys || t->index_capacity < t->n) {
         if (t->d_sorted_keys) cudaFree(t->d_sorted_keys), t->d_sorted_keys = nullptr;
         if (t->d_sorted_slots) cudaFree(t->d_sorted_slots), t->d_sorted_slots = nullptr;
+        if (t->d_alt_keys) cudaFree(t->d_alt_keys), t->d_alt_keys = nullptr;
+        if (t->d_alt_slots) cudaFree(t->d_alt_slots), t->d_alt_slots = nullptr;
         t->index_capacity = 0;
         IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_keys, t->n * sizeof(Fr)));
         IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_slots, t->n * sizeof(uint32_t)));
         t->index_capacity = t->n;
     }
-    DevBuf stats;  // [0] first empty, [1] last occupied, then the head flag
+    DevBuf stats(ctx);  // [0] first empty, [1] last occupied, then the head flag
     IMT_TRY_CUDA(ctx, stats.alloc(3 * sizeof(unsigned long long)));
     const unsigned long long init[3] = {(unsigned long long)t->n, 0ull, 0ull};
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(stats.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
@@ -580,7 +585,7 @@ extern "C" imt_status imt_low_leaf_lookup(imt_tree* t, const void* values, size_
     IMT_TRY(ensure_index(t));
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dv, dl, dm;
+    DevBuf dv(ctx), dl(ctx), dm(ctx);
     IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, dm.alloc(q));
@@ -594,6 +599,19 @@ extern "C" imt_status imt_low_leaf_lookup(imt_tree* t, const void* values, size_
     return IMT_OK;
 }
 
+extern "C" imt_status imt_low_leaf_lookup_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low_idx, uint8_t* d_matched) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!d_values || !d_low_idx)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (sharded(t)) return fail(ctx, IMT_ERR_INVALID_ARG, "low-leaf lookups on a sharded tree go through the per-rank candidate call");
+    IMT_TRY(ensure_index(t));
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(lookup_dev(t, d_values, q, d_low_idx, d_matched));
+    return finish(ctx);
+}
+
 extern "C" imt_status imt_non_inclusion_paths(imt_tree* t, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
                                               void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest) {
     if (!t) return IMT_ERR_INVALID_ARG;
@@ -604,7 +622,7 @@ extern "C" imt_status imt_non_inclusion_paths(imt_tree* t, const void* values, s
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const unsigned depth = t->depth;
-    DevBuf dv, dl, dm, dlv, dsib, dhel, dlg;
+    DevBuf dv(ctx), dl(ctx), dm(ctx), dlv(ctx), dsib(ctx), dhel(ctx), dlg(ctx);
     IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, dm.alloc(q));
@@ -623,7 +641,7 @@ extern "C" imt_status imt_non_inclusion_paths(imt_tree* t, const void* values, s
         IMT_TRY_CUDA(ctx, cudaGetLastError());
     }
     if (siblings || helpers) {
-        DevBuf scratch;  // the gather kernel always writes siblings
+        DevBuf scratch(ctx);  // the gather kernel always writes siblings
         void* d_sib = dsib.p;
         if (!siblings) {
             IMT_TRY_CUDA(ctx, scratch.alloc(q * (size_t)depth * sizeof(Fr)));
@@ -655,11 +673,20 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     if (b == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const unsigned depth = t->depth;
+    static const bool dbg = std::getenv("IMT_DEBUG_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[imt_insert_batch] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+        tp0 = now;
+    };
     const imt_insert_witness none = {};
     const imt_insert_witness out = w ? *w : none;
 
     // ---- the whole batch as canonical integers, validated before anything is modified
-    DevBuf staged, vals, sorted_vals, sorted_slots;
+    DevBuf staged(ctx), vals(ctx), sorted_vals(ctx), sorted_slots(ctx);
     IMT_TRY_CUDA(ctx, staged.alloc(b * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, vals.alloc(b * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, sorted_vals.alloc(b * sizeof(Fr)));
@@ -678,10 +705,10 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     IMT_TRY(finish(ctx));
 
+    lap("validate");
     // ---- per-chunk scratch
     const size_t C = std::min(b, kInsertChunk), W = 2 * C, L = depth + 1;
-    DevBuf x, upd, low_old, largest, prev, last, ver, sib_low, sib_new, r_old, r_new, h_low, h_new, low_idx, chunk_keys, chunk_slots, alt_keys,
-        alt_slots;
+    DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx);
     IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, low_old.alloc(C * 3 * sizeof(Fr)));
@@ -698,9 +725,10 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     if (out.low_idx) IMT_TRY_CUDA(ctx, low_idx.alloc(C * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, chunk_keys.alloc(C * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, chunk_slots.alloc(C * sizeof(uint32_t)));
-    IMT_TRY_CUDA(ctx, alt_keys.alloc(t->index_capacity * sizeof(Fr)));
-    IMT_TRY_CUDA(ctx, alt_slots.alloc(t->index_capacity * sizeof(uint32_t)));
+    if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
+    if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
 
+    lap("alloc");
     for (size_t off = 0; off < b; off += C) {
         const size_t cb = std::min(C, b - off);
         const unsigned writes = (unsigned)(2 * cb);
@@ -712,6 +740,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         k_ins_links<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(x.as<uint64_t>(), writes, depth, prev.as<int>(), last.as<uint8_t>());
         ctx->launches += 2;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
+        lap("resolve+links");
         // version 0 of every write: the hash of its leaf preimage (IMT:662-671)
         IMT_TRY(launch_hash(ctx, 3, upd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
         for (unsigned l = 0; l < depth; ++l) {
@@ -731,6 +760,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
                                                                                 (uint4*)t->d_pre);
         ctx->launches += 2;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
+        lap("levels+commit");
         // ---- witnesses of this chunk back to the caller
         auto d2h = [&](void* host, size_t stride, const void* dev) -> cudaError_t {
             if (!host || stride == 0) return cudaSuccess;
@@ -749,6 +779,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
             IMT_TRY_CUDA(ctx, cudaMemcpy2DAsync((char*)out.new_leaves + off * 3 * sizeof(Fr), 3 * sizeof(Fr), (const char*)upd.p + 3 * sizeof(Fr),
                                                 6 * sizeof(Fr), 3 * sizeof(Fr), cb, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        lap("d2h");
         // ---- keep the sorted index current: merge this chunk's keys into it
         IMT_TRY_CUDA(ctx, cudaMemcpyAsync(chunk_keys.p, cvals, cb * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
         k_iota_slots<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(chunk_slots.as<uint32_t>(), cb, first);
@@ -756,16 +787,15 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         IMT_TRY(sort_pairs(ctx, chunk_keys.as<Fr>(), chunk_slots.as<uint32_t>(), cb));
         k_merge_rank<<<grid_for(t->occupied + cb, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
                                                                               chunk_keys.as<uint4>(), chunk_slots.as<uint32_t>(), cb,
-                                                                              alt_keys.as<uint4>(), alt_slots.as<uint32_t>());
+                                                                              (uint4*)t->d_alt_keys, t->d_alt_slots);
         ++ctx->launches;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
         IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        void* old_keys = t->d_sorted_keys;  // the merged arrays become the index; the old ones the next merge target
-        void* old_slots = t->d_sorted_slots;
-        t->d_sorted_keys = alt_keys.as<Fr>(), t->d_sorted_slots = alt_slots.as<uint32_t>();
-        alt_keys.p = old_keys, alt_slots.p = old_slots;
+        std::swap(t->d_sorted_keys, t->d_alt_keys);  // the merged arrays become the index; the old ones the next merge target
+        std::swap(t->d_sorted_slots, t->d_alt_slots);
         t->occupied += cb;
         t->head_next_zero = false;
+        lap("merge");
     }
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     IMT_TRY_CUDA(ctx, cudaGetLastError());
@@ -799,7 +829,7 @@ extern "C" imt_status imt_low_leaf_candidates(imt_tree* t, const void* values, s
     IMT_TRY(ensure_index(t));
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dv, dk, ds, df;
+    DevBuf dv(ctx), dk(ctx), ds(ctx), df(ctx);
     IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dk.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, ds.alloc(q * sizeof(uint64_t)));
@@ -826,7 +856,7 @@ extern "C" imt_status imt_low_leaf_merge(imt_ctx* ctx, const void* values, const
     if (q && (!values || !cand_keys || !cand_slots || !flags || !low_idx)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (q == 0 || world == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dv, dz, dk, ds, df, dl, dm;
+    DevBuf dv(ctx), dz(ctx), dk(ctx), ds(ctx), df(ctx), dl(ctx), dm(ctx);
     IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dz.alloc(q));
     IMT_TRY_CUDA(ctx, dk.alloc(world * q * sizeof(Fr)));
@@ -857,7 +887,7 @@ extern "C" imt_status imt_tree_leaves(imt_tree* t, const uint64_t* indices, size
     if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf di, dl, dg;
+    DevBuf di(ctx), dl(ctx), dg(ctx);
     IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
     if (leaves) IMT_TRY_CUDA(ctx, dl.alloc(q * 3 * sizeof(Fr)));
     if (is_largest) IMT_TRY_CUDA(ctx, dg.alloc(q));

@@ -54,6 +54,8 @@ struct imt_tree {
     size_t index_capacity = 0;           // entries the two arrays below can hold
     imt::Fr* d_sorted_keys = nullptr;    // canonical integer values, ascending
     uint32_t* d_sorted_slots = nullptr;  // slot of each key
+    imt::Fr* d_alt_keys = nullptr;       // merge target of the next insert batch (allocated by the first one; the two
+    uint32_t* d_alt_slots = nullptr;     // buffer pairs swap roles after every merge)
     bool head_next_zero = false;         // preimage[0].next_val == 0  (the reference's first-insert branch, IMT:640)
 };
 
@@ -98,21 +100,19 @@ inline imt_status fail(imt_ctx* ctx, imt_status st, const char* what) {
     return st;
 }
 
-// RAII device buffer
+// RAII device scratch buffer, stream-ordered: cudaMallocAsync / cudaFreeAsync on the context's compute stream from
+// the device's default memory pool (imt_ctx_create raises its release threshold, so steady-state calls recycle memory
+// instead of paying a synchronous cudaMalloc / cudaFree per buffer — those cost ~100 ms per insert batch at depth 24).
 struct DevBuf {
     void* p = nullptr;
-    DevBuf() = default;
+    cudaStream_t s = nullptr;
+    explicit DevBuf(imt_ctx* ctx) : s(ctx->stream) {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s);
     }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    void* release() {
-        void* q = p;
-        p = nullptr;
-        return q;
-    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
     template <class T>
     T* as() { return static_cast<T*>(p); }
 };

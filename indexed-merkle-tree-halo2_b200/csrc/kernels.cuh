@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
                                                              size_t q, unsigned depth, int fmt, uint8_t* __restrict__ ok_out,
                                                              uint4* __restrict__ roots_out, uint4* __restrict__ states,
                                                              uint32_t* __restrict__ err) {
-    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= q) return;
     uint32_t x[2][8], h[8];
     load_fe(h, leaves + 2 * i);

@@ -188,6 +188,15 @@ class Engine:
         self._check(self._lib.imt_trace_merkle_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(sib), q, depth, _ptr(states), _ptr(roots)))
         return roots, states
 
+    def verify_proofs_dev(self, d_leaves, d_indices, d_roots, d_siblings, q, depth, d_ok):
+        self._check(self._lib.imt_verify_proofs_dev(self._h, _dev_ptr(d_leaves), _dev_ptr(d_indices), _dev_ptr(d_roots), _dev_ptr(d_siblings),
+                                                    q, depth, _dev_ptr(d_ok)))
+
+    def trace_merkle_proofs_dev(self, d_leaves, d_indices, d_siblings, q, depth, d_states, d_roots):
+        self._check(self._lib.imt_trace_merkle_proofs_dev(self._h, _dev_ptr(d_leaves), _dev_ptr(d_indices), _dev_ptr(d_siblings), q, depth,
+                                                          _dev_ptr(d_states) if d_states is not None else None,
+                                                          _dev_ptr(d_roots) if d_roots is not None else None))
+
     def low_leaf_merge(self, values, cand_keys, cand_slots, flags, occupied_total, n_total, head_next_zero):
         """replicated half of a sharded lookup: [world][q] gathered candidates -> (low_idx, matched)"""
         v = _fe_array(values, ())
@@ -277,6 +286,14 @@ class Tree:
             hel = np.empty((q, d), np.uint8)
             self.engine._check(self._lib.imt_tree_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
         return sib, hel
+
+    def get_proofs_dev(self, d_indices, q, d_siblings, d_helpers=None):
+        self.engine._check(self._lib.imt_tree_get_proofs_dev(self._h, _dev_ptr(d_indices), q, _dev_ptr(d_siblings),
+                                                             _dev_ptr(d_helpers) if d_helpers is not None else None))
+
+    def low_leaf_lookup_dev(self, d_values, q, d_low_idx, d_matched=None):
+        self.engine._check(self._lib.imt_low_leaf_lookup_dev(self._h, _dev_ptr(d_values), q, _dev_ptr(d_low_idx),
+                                                             _dev_ptr(d_matched) if d_matched is not None else None))
 
     @property
     def occupied(self):

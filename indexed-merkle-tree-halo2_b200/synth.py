@@ -127,3 +127,30 @@ def field_elements_torch(n, seed=DEFAULT_SEED, first=0, device="cuda"):
             borrow = b1 | b2
         chunks.append(torch.stack(out, dim=1))
     return torch.cat(chunks, dim=0).contiguous() if chunks else torch.zeros((0, 4), dtype=torch.int64, device=device)
+
+
+def indexed_preimages_torch(n, occupied=None, seed=DEFAULT_SEED, device="cuda"):
+    """indexed_preimages() built on `device` with torch (same values, same layout): (n, 3, 4) int64 (bit pattern = uint64,
+    canonical). Setup helper for the depth-24 query benchmarks — the host version needs a 16M-row numpy lexsort."""
+    import torch
+    m = n if occupied is None else occupied
+    assert 1 <= m <= n
+    pre = torch.zeros((n, 3, 4), dtype=torch.int64, device=device)
+    if m == 1:
+        return pre
+    vals = field_elements_torch(m - 1, seed, device=device)
+    MIN = -(1 << 63)
+    order = torch.arange(m - 1, device=device)
+    for k in range(4):  # LSD: four stable sorts, least significant word first, unsigned order via the sign flip
+        key = vals[order, k] ^ MIN
+        order = order[torch.sort(key, stable=True).indices]
+    sv = vals[order]
+    if m > 2 and bool((sv[1:] == sv[:-1]).all(dim=1).any()):
+        raise ValueError("synthetic values collided; pick another seed")
+    pre[1:m, 0] = vals
+    slots = order + 1
+    pre[0, 1] = sv[0]
+    pre[0, 2, 0] = slots[0]
+    pre[slots[:-1], 1] = sv[1:]
+    pre[slots[:-1], 2, 0] = slots[1:]
+    return pre

@@ -89,6 +89,40 @@ __global__ void __launch_bounds__(256) k_wide_plus_alu(uint64_t* out, uint32_t s
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
+// 8 independent double-precision FMA chains (is the FP64 pipe a usable second multiplier on this part?)
+__global__ void __launch_bounds__(256) k_dfma_indep(uint64_t* out, uint32_t seed) {
+    double acc[8]; double a = 1.0 + 1e-9 * (seed + threadIdx.x), b = 1e-12 * blockIdx.x;
+    for (int j = 0; j < 8; ++j) acc[j] = 1.0 + j * 1e-3;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[j]) : "d"(a), "d"(b));
+    double x = 0; for (int j = 0; j < 8; ++j) x += acc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)__double_as_longlong(x);
+}
+// the serial wide+carry chain of the field arithmetic with one independent DFMA per wide MAC: do the two pipes overlap?
+__global__ void __launch_bounds__(256) k_wide_carry_plus_dfma(uint64_t* out, uint32_t seed) {
+    uint32_t lo[8], hi[8]; uint32_t b = seed + threadIdx.x;
+    double acc[8]; double a = 1.0 + 1e-9 * (seed + threadIdx.x), c = 1e-12 * blockIdx.x;
+    for (int j = 0; j < 8; ++j) { lo[j] = seed + j; hi[j] = j; acc[j] = 1.0 + j * 1e-3; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(lo[(j + 3) & 7]), "r"(b));
+                asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[j]) : "d"(a), "d"(c));
+            }
+        }
+    }
+    double y = 0; for (int j = 0; j < 8; ++j) y += acc[j];
+    uint64_t x = (uint64_t)__double_as_longlong(y); for (int j = 0; j < 8; ++j) x ^= ((uint64_t)hi[j] << 32) | lo[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
 template <class K>
 static void run(const char* name, K kernel, int blocks_per_sm, int sms, double clock_hz, double ops_per_thread_iter) {
     int blocks = blocks_per_sm * sms, threads = 256;
@@ -118,6 +152,8 @@ int main() {
         run("wide+carry, one serial chain", k_wide_carry_serial, bps, p.multiProcessorCount, hz, 32);
         run("wide+carry, chains of 4", k_wide_carry_chains4, bps, p.multiProcessorCount, hz, 32);
         run("mad.wide + add 1:1", k_wide_plus_alu, bps, p.multiProcessorCount, hz, 32);
+        run("fma.rz.f64 x8 independent", k_dfma_indep, bps, p.multiProcessorCount, hz, 32);
+        run("wide+carry chain + dfma 1:1", k_wide_carry_plus_dfma, bps, p.multiProcessorCount, hz, 32);
     }
     return 0;
 }
