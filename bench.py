@@ -43,17 +43,20 @@ def parse():
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line). The sampler runs
+    from before the warm-up; every row is stamped on arrival and mark_begin()/mark_end() bracket the timed region. When
+    the region is shorter than the sampling period (8-GPU steps last ~80 ms) the rows taken under the identical load of
+    the warm-up steps just before it are used, and `window` says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -61,19 +64,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.05]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: the warm-up steps right before it ran the same load
+            inside = [r for ts, r in self.rows if t0 - 1.0 <= ts <= t1 + 0.25]
+            window = "timed region shorter than the sampling period: samples from the warm-up steps within 1 s before it"
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
@@ -82,7 +98,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -418,11 +434,13 @@ def main():
     # ---- value: inputs resident in HBM. Per-kernel device times come from the library's own event pairs.
     eng.enable_timing(True)
     sampler = ClockSampler(local_rank)
-    for _ in range(a.warmup):
+    sampler.start()
+    for _ in range(max(a.warmup, 3)):
         step_resident()
     eng.reset_timing()
-    sampler.start()
+    sampler.mark_begin()
     ms_total, launches = timed(step_resident, a.steps, 0)
+    sampler.mark_end()
     clocks = sampler.stop()
     k3_ms, k3_launches, k3_hashes = eng.kernel_time(3)
     k2_ms, k2_launches, k2_hashes = eng.kernel_time(2)

@@ -77,8 +77,8 @@ __device__ __forceinline__ size_t lower_bound(const uint4* __restrict__ keys, si
 }
 
 // ------------------------------------------------------------------------------------------------- index build
-// keys[i] = canonical val of slot i, slots[i] = i; stats[0] = first empty slot (min), stats[1] = last occupied slot
-// (max). Global slot 0 is the head and always counts as occupied; any other slot is occupied iff val != 0.
+// keys[i] = canonical val of slot i, slots[i] = i; stats[0] = first empty slot (min), stats[1] = last occupied slot + 1
+// (max; 0 = none: an all-empty shard). Global slot 0 is the head and always counts as occupied; any other slot is occupied iff val != 0.
 // `base` = global slot of local slot 0 (rank * n for a subtree shard).
 __global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__ pre, size_t n, uint64_t base, int fmt, uint4* __restrict__ keys,
                                                        uint32_t* __restrict__ slots, unsigned long long* __restrict__ stats,
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) k_index_extract(const uint4* __restrict__
         store_fe(keys + 2 * i, v);
         slots[i] = (uint32_t)i;
         const bool occ = (base + i) == 0 || !zero256(v);
-        if (occ) atomicMax(&s_max, (unsigned long long)i);
+        if (occ) atomicMax(&s_max, (unsigned long long)i + 1);
         else {
             atomicMin(&s_min, (unsigned long long)i);
             if (!zero256(a) || !zero256(b)) atomicOr(err, kErrNotWellFormed);  // an empty slot is {0, 0, 0}
@@ -534,7 +534,7 @@ imt_status ensure_index(imt_tree* t) {
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(got, stats.p, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY(finish(ctx));
     const size_t m = (size_t)got[0];
-    if (got[1] >= m) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, "occupied slots do not form a prefix");
+    if (got[1] > m) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, "occupied slots do not form a prefix");
     IMT_TRY(sort_pairs(ctx, t->d_sorted_keys, t->d_sorted_slots, m));
     IMT_TRY(clear_err(ctx));
     if (m) k_index_check<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, ctx->fmt, (const uint4*)t->d_sorted_keys,
