@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
 SOURCES = ["imt_capi.cu", "imt_indexed.cu", "poseidon_params.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "imt_internal.h", "poseidon.cuh", "fr.cuh", "poseidon_params.h"]
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "fr.cuh", "poseidon_params.h"]
 OBJ_DIR = os.path.join(HERE, "build")
 
 

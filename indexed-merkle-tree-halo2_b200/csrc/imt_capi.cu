@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -11,6 +12,7 @@
 #include "imt_b200.h"
 #include "imt_internal.h"
 #include "kernels.cuh"
+#include "poseidon_coop.cuh"
 #include "poseidon_params.h"
 
 using namespace imt;
@@ -60,6 +62,10 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
     return IMT_OK;
 }
 
+// threshold of the cooperative kernel; IMT_COOP_MAX_NODES overrides it (tuning / A-B measurements only)
+constexpr size_t kCoopMaxNodesDefault = 8192;
+size_t coop_max_nodes();
+
 template <int ARITY>
 imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
     if (n == 0) return IMT_OK;
@@ -80,14 +86,41 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
     return IMT_OK;
 }
 
+size_t coop_max_nodes() {
+    static const size_t v = [] {
+        const char* e = std::getenv("IMT_COOP_MAX_NODES");
+        return e ? (size_t)std::strtoull(e, nullptr, 10) : kCoopMaxNodesDefault;
+    }();
+    return v;
+}
+
+// Levels with at most this many nodes cannot fill the GPU with one thread per hash and cost one full hash latency each:
+// they go to the 3-lanes-per-hash kernel (poseidon_coop.cuh), which trades lanes for latency.
+
+// one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
+imt_status launch_level(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
+    if (nodes > coop_max_nodes()) return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    imt_ctx::Timed tm{nullptr, nullptr, 2, nodes};
+    if (ctx->timing) {
+        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.a));
+        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
+        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, ctx->stream));
+    }
+    k_hash2_coop<<<grid_for(4 * nodes, 128), 128, 0, ctx->stream>>>((const uint4*)src, (uint4*)dst, nodes, ctx->d_params);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    if (ctx->timing) {
+        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.b, ctx->stream));
+        ctx->pending.push_back(tm);
+    }
+    return IMT_OK;
+}
+
 // all levels above level 0 (which must already hold the Montgomery leaf hashes)
 imt_status build_upper_levels(imt_tree* t) {
     imt_ctx* ctx = t->ctx;
-    for (unsigned l = 0; l < t->depth; ++l) {
-        const Fr* src = t->d_levels + level_offset(t->n, l);
-        Fr* dst = t->d_levels + level_offset(t->n, l + 1);
-        IMT_TRY(launch_hash_t<2>(ctx, src, dst, t->n >> (l + 1), kFmtMontgomery, kFmtMontgomery, ctx->stream));
-    }
+    for (unsigned l = 0; l < t->depth; ++l)
+        IMT_TRY(launch_level(ctx, t->d_levels + level_offset(t->n, l), t->d_levels + level_offset(t->n, l + 1), t->n >> (l + 1)));
     return IMT_OK;
 }
 
@@ -252,6 +285,8 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_err, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_params, sizeof(PoseidonParams));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_params, &host_params, sizeof(PoseidonParams), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
     if (e == cudaSuccess) e = upload_params_indexed(&host_params);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -271,6 +306,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     delete ctx;
 }
@@ -647,8 +683,7 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
                                                           ctx->d_err);
     ++ctx->launches;
     for (unsigned l = 0; l < t->cap_depth; ++l)
-        IMT_TRY(launch_hash_t<2>(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1),
-                               kFmtMontgomery, kFmtMontgomery, ctx->stream));
+        IMT_TRY(launch_level(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1)));
     IMT_TRY(finish(ctx));
     t->cap_valid = true;
     return IMT_OK;

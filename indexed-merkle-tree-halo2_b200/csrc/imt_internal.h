@@ -21,6 +21,7 @@ struct imt_ctx {
     cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
     uint32_t* d_err = nullptr;           // device error bits, see kErr*
     uint32_t* h_err = nullptr;           // pinned mirror
+    imt::PoseidonParams* d_params = nullptr;  // global-memory copy of the parameters (lane-dependent reads of the cooperative kernel)
     uint64_t launches = 0;
     std::string last_error;
     // optional per-launch device timing of the hash kernels

@@ -1,0 +1,104 @@
+// Latency-oriented Poseidon for the top of the tree: THREE lanes cooperate on one hash.
+//
+// A level with fewer nodes than the GPU has warp slots cannot be sped up by more threads: with one thread per hash
+// (poseidon.cuh) such a level costs one full hash latency, ~0.57 ms of dependent IMADs, however few nodes it has, and
+// a depth-24 build ends with ~15 of them. Here each of the three state lanes of a hash lives in its own SIMT lane
+// (a quad per hash, the 4th lane idles), every lane runs the SAME instruction stream on its own element, and values
+// cross lanes with warp shuffles:
+//   full round     lane i: u_i = s_i^5 + c_i            | exchange u | lane i: s_i' = M[i] . u
+//   partial round  lane 0: x^2, x^4                     (lanes 1, 2 idle through two multiplications)
+//                  lane 0: u = x^4 x + c   lane 1: P1 = s1 row1   lane 2: P2 = s2 row2      (one multiply-reduce slot)
+//                  exchange u, P1, P2
+//                  lane 0: s0' = u row0 + (P1 + P2)   lane i: s_i' = u col_i + s_i          (one multiply-add slot)
+// i.e. 4 dependent multiply-reduce slots per partial round instead of 8, 4 instead of 18 per full round: ~1.7x lower
+// latency per hash. Results are the same field elements as poseidon.cuh (canonical on output), bit for bit.
+// Round constants come from a copy of the parameters in global memory (the address depends on the lane).
+#pragma once
+#include "kernels_common.cuh"
+
+namespace imt {
+
+__device__ __forceinline__ void ld_fe(uint32_t* x, const Fr* p) { load_fe(x, reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void shfl_fe(uint32_t* d, const uint32_t* s, int src_lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
+}
+
+// x: this lane's state element (role r = 0, 1, 2; r = 3 mirrors lane 2 and is ignored). base = first lane of the quad.
+__device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* __restrict__ G, int r, int base) {
+    const int rr = r < 3 ? r : 2;
+    const bool lead = r == 0;
+    {
+        uint32_t c[8];
+        ld_fe(c, &G->pre[rr]);
+        add_semi(x, x, c);
+    }
+#pragma unroll 1
+    for (int round = 0; round < kRF + kRP; ++round) {
+        const bool full = round < kHalfF || round >= kHalfF + kRP;
+        if (full) {
+            const int fr = round < kHalfF ? round : round - kRP;
+            uint32_t c[8], u0[8], u1[8], u2[8], m0[8], m1[8], m2[8];
+            ld_fe(c, &G->full[fr][rr]);
+            sbox_add(x, x, c);
+            shfl_fe(u0, x, base);
+            shfl_fe(u1, x, base + 1);
+            shfl_fe(u2, x, base + 2);
+            const Fr(*m)[3] = (round == kHalfF - 1) ? G->pre_sparse : G->mds;
+            ld_fe(m0, &m[rr][0]);
+            ld_fe(m1, &m[rr][1]);
+            ld_fe(m2, &m[rr][2]);
+            dot3(x, u0, u1, u2, m0, m1, m2);
+        } else {
+            const PartialRound* pr = &G->partial[round - kHalfF];
+            uint32_t x2[8], x4[8], a[8], b[8], c[8], t[8];
+            mont_sqr(x2, x);
+            mont_sqr(x4, x2);
+            ld_fe(b, lead ? &pr->c : &pr->row[rr]);  // lead: the round constant (added), others: their row entry (multiplied)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = lead ? x4[i] : x[i];
+                c[i] = lead ? b[i] : 0u;
+                b[i] = lead ? x[i] : b[i];
+            }
+            mul_add(t, a, b, c);  // lead: u = x^4 x + c ; lane i: P_i = s_i row_i
+            uint32_t u[8], p1[8], p2[8], y[8], k[8];
+            shfl_fe(u, t, base);
+            shfl_fe(p1, t, base + 1);
+            shfl_fe(p2, t, base + 2);
+            add_semi(y, p1, p2);
+            ld_fe(k, lead ? &pr->row[0] : &pr->col[rr - 1]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = lead ? y[i] : x[i];
+            mul_add(x, u, k, y);  // lead: s0' = u row0 + P1 + P2 ; lane i: s_i' = u col_i + s_i
+        }
+    }
+}
+
+// H(in[2h], in[2h+1]) for the nodes of one (small) tree level, Montgomery in, Montgomery out: 4 threads per hash.
+__global__ void __launch_bounds__(128) k_hash2_coop(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
+                                                    const PoseidonParams* __restrict__ G) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t h = tid >> 2;
+    const int r = (int)(tid & 3);
+    const int base = (int)(threadIdx.x & 31) & ~3;
+    const size_t hc = h < n ? h : n - 1;  // lanes past the end recompute the last hash: every lane must reach the shuffles
+    uint32_t x[8];
+    if (r == 0) ld_fe(x, &G->cap);
+    else load_fe(x, in + 2 * (2 * hc + (r == 1 ? 0 : 1)));
+    permute_coop(x, G, r, base);
+    {  // second absorb of a 2-input hash: nothing left but the padding 1 on lane 1
+        uint32_t one[8];
+        ld_fe(one, &G->one);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) one[i] = (r == 1) ? one[i] : 0u;
+        add_semi(x, x, one);
+    }
+    permute_coop(x, G, r, base);
+    if (r == 1 && h < n) {
+        canonicalize(x);
+        store_fe(out + 2 * h, x);
+    }
+}
+
+}  // namespace imt
