@@ -98,7 +98,7 @@ size_t coop_max_nodes() {
 // they go to the 3-lanes-per-hash kernel (poseidon_coop.cuh), which trades lanes for latency.
 
 // one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
-imt_status launch_level(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
+imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
     if (nodes > coop_max_nodes()) return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, ctx->stream);
     imt_ctx::Timed tm{nullptr, nullptr, 2, nodes};
     if (ctx->timing) {
@@ -120,7 +120,7 @@ imt_status launch_level(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
 imt_status build_upper_levels(imt_tree* t) {
     imt_ctx* ctx = t->ctx;
     for (unsigned l = 0; l < t->depth; ++l)
-        IMT_TRY(launch_level(ctx, t->d_levels + level_offset(t->n, l), t->d_levels + level_offset(t->n, l + 1), t->n >> (l + 1)));
+        IMT_TRY(launch_level_impl(ctx, t->d_levels + level_offset(t->n, l), t->d_levels + level_offset(t->n, l + 1), t->n >> (l + 1)));
     return IMT_OK;
 }
 
@@ -217,6 +217,7 @@ imt_status copy_out_fe(imt_ctx* ctx, const Fr* d_src, size_t count, void* h_dst,
 }  // namespace
 
 namespace imt_host {
+imt_status launch_level(imt_ctx* ctx, const Fr* d_src, Fr* d_dst, size_t nodes) { return launch_level_impl(ctx, d_src, d_dst, nodes); }
 imt_status launch_hash(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
     return arity == 3 ? launch_hash_t<3>(ctx, d_in, d_out, n, in_fmt, out_fmt, s) : launch_hash_t<2>(ctx, d_in, d_out, n, in_fmt, out_fmt, s);
 }
@@ -288,7 +289,6 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_params, sizeof(PoseidonParams));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_params, &host_params, sizeof(PoseidonParams), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
-    if (e == cudaSuccess) e = upload_params_indexed(&host_params);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "imt_ctx_create: %s\n", cudaGetErrorString(e));
@@ -683,7 +683,7 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
                                                           ctx->d_err);
     ++ctx->launches;
     for (unsigned l = 0; l < t->cap_depth; ++l)
-        IMT_TRY(launch_level(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1)));
+        IMT_TRY(launch_level_impl(ctx, t->d_cap + level_offset(world, l), t->d_cap + level_offset(world, l + 1), world >> (l + 1)));
     IMT_TRY(finish(ctx));
     t->cap_valid = true;
     return IMT_OK;

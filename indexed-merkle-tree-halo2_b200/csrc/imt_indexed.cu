@@ -371,46 +371,37 @@ __global__ void __launch_bounds__(256) k_ins_links(const uint64_t* __restrict__ 
     last[id] = fin ? 1 : 0;
 }
 
-// One level of all writes: ver[(l+1) * writes + t] = H(own child version, sibling) ; the sibling operand is also
-// the witness path element of that write (low path of insert t/2 in the OLD tree for even t, new-leaf path in the
-// NEW tree for odd t — see the header of this file).
-__global__ void __launch_bounds__(kHashThreads) k_ins_level(uint4* __restrict__ ver, const uint4* __restrict__ tree_levels, size_t n,
-                                                            unsigned l, const uint64_t* __restrict__ x, const int* __restrict__ prev,
-                                                            unsigned writes, unsigned depth, int fmt, uint4* __restrict__ sib_low,
-                                                            uint4* __restrict__ sib_new) {
-    const unsigned t = blockIdx.x * kHashThreads + threadIdx.x;
+// One level of all writes, operand half: pairs[t] = (left, right) children of write t's level-(l+1) node — its own
+// child version and the sibling (latest earlier write to the sibling node, else the stored tree). The sibling is also
+// the witness path element of that write (low path of insert t/2 in the OLD tree for even t, new-leaf path in the NEW
+// tree for odd t — see the header of this file). The hashing half is the ordinary level kernel over `pairs`
+// (imt_host::launch_level: with <= 8192 writes that is the 3-lanes-per-hash latency kernel).
+__global__ void __launch_bounds__(256) k_ins_pairs(const uint4* __restrict__ ver_level, const uint4* __restrict__ tree_levels, size_t n,
+                                                   unsigned l, const uint64_t* __restrict__ x, const int* __restrict__ prev, unsigned writes,
+                                                   unsigned depth, int fmt, uint4* __restrict__ pairs, uint4* __restrict__ sib_low,
+                                                   uint4* __restrict__ sib_new) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= writes) return;
     const uint64_t node = x[t] >> l;
     const int p = prev[(size_t)t * (depth + 1) + l];
-    uint32_t in[2][8], own[8], sib[8], h[8];
-    const uint4* cur = ver + 2 * ((size_t)l * writes);
-    // versions are written by earlier launches of this kernel: plain loads (not the read-only path)
-    {
-        const uint4 a = cur[2 * t], c = cur[2 * t + 1];
-        own[0] = a.x, own[1] = a.y, own[2] = a.z, own[3] = a.w, own[4] = c.x, own[5] = c.y, own[6] = c.z, own[7] = c.w;
-    }
-    if (p >= 0) {
-        const uint4 a = cur[2 * p], c = cur[2 * p + 1];
-        sib[0] = a.x, sib[1] = a.y, sib[2] = a.z, sib[3] = a.w, sib[4] = c.x, sib[5] = c.y, sib[6] = c.z, sib[7] = c.w;
-    } else {
-        load_fe(sib, tree_levels + 2 * (level_offset(n, l) + (node ^ 1)));
-    }
-    uint4* wit = (t & 1) ? sib_new : sib_low;
-    if (wit) {
-        uint32_t s2[8];
-        copy256(s2, sib);
-        egress(s2, fmt);
-        store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), s2);
-    }
+    uint32_t own[8], sib[8];
+    load_fe(own, ver_level + 2 * (size_t)t);
+    if (p >= 0) load_fe(sib, ver_level + 2 * (size_t)p);
+    else load_fe(sib, tree_levels + 2 * (level_offset(n, l) + (node ^ 1)));
     const bool left = (node & 1) == 0;
+    uint32_t lo[8], hi[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        in[0][i] = left ? own[i] : sib[i];
-        in[1][i] = left ? sib[i] : own[i];
+        lo[i] = left ? own[i] : sib[i];
+        hi[i] = left ? sib[i] : own[i];
     }
-    NoTrace nt;
-    hash_fixed<2>(h, in, c_params, nt);
-    store_fe(ver + 2 * ((size_t)(l + 1) * writes + t), h);
+    store_fe(pairs + 4 * (size_t)t, lo);
+    store_fe(pairs + 4 * (size_t)t + 2, hi);
+    uint4* wit = (t & 1) ? sib_new : sib_low;
+    if (wit) {
+        egress(sib, fmt);
+        store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), sib);
+    }
 }
 
 // per insert: roots before / after, helper bits of both paths
@@ -563,7 +554,6 @@ bool sharded(const imt_tree* t) { return t->world > 1; }
 }  // namespace
 
 namespace imt_host {
-cudaError_t upload_params_indexed(const PoseidonParams* host_params) { return cudaMemcpyToSymbol(c_params, host_params, sizeof(PoseidonParams)); }
 void invalidate_index(imt_tree* t) {  // the buffers are kept for the next build of the index
     t->index_valid = false;
     t->occupied = 0;
@@ -708,7 +698,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     lap("validate");
     // ---- per-chunk scratch
     const size_t C = std::min(b, kInsertChunk), W = 2 * C, L = depth + 1;
-    DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx);
+    DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx), pairs(ctx);
     IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, low_old.alloc(C * 3 * sizeof(Fr)));
@@ -716,6 +706,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     IMT_TRY_CUDA(ctx, prev.alloc(W * L * sizeof(int)));
     IMT_TRY_CUDA(ctx, last.alloc(W * L));
     IMT_TRY_CUDA(ctx, ver.alloc(L * W * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, pairs.alloc(2 * W * sizeof(Fr)));
     if (out.low_siblings) IMT_TRY_CUDA(ctx, sib_low.alloc(C * depth * sizeof(Fr)));
     if (out.new_siblings) IMT_TRY_CUDA(ctx, sib_new.alloc(C * depth * sizeof(Fr)));
     if (out.old_roots) IMT_TRY_CUDA(ctx, r_old.alloc(C * sizeof(Fr)));
@@ -744,10 +735,11 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         // version 0 of every write: the hash of its leaf preimage (IMT:662-671)
         IMT_TRY(launch_hash(ctx, 3, upd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
         for (unsigned l = 0; l < depth; ++l) {
-            k_ins_level<<<grid_for(writes, kHashThreads), kHashThreads, 0, ctx->stream>>>(
-                ver.as<uint4>(), (const uint4*)t->d_levels, t->n, l, x.as<uint64_t>(), prev.as<int>(), writes, depth, ctx->fmt,
-                out.low_siblings ? sib_low.as<uint4>() : nullptr, out.new_siblings ? sib_new.as<uint4>() : nullptr);
+            k_ins_pairs<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(
+                ver.as<uint4>() + 2 * ((size_t)l * writes), (const uint4*)t->d_levels, t->n, l, x.as<uint64_t>(), prev.as<int>(), writes, depth,
+                ctx->fmt, pairs.as<uint4>(), out.low_siblings ? sib_low.as<uint4>() : nullptr, out.new_siblings ? sib_new.as<uint4>() : nullptr);
             ++ctx->launches;
+            IMT_TRY(launch_level(ctx, pairs.as<Fr>(), ver.as<Fr>() + (size_t)(l + 1) * writes, writes));
         }
         k_ins_outputs<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), (const uint4*)t->d_levels, t->n, x.as<uint64_t>(), (unsigned)cb,
                                                                   depth, ctx->fmt, out.old_roots ? r_old.as<uint4>() : nullptr,

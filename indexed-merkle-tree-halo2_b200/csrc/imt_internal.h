@@ -1,8 +1,8 @@
 // Internal declarations shared by the translation units of libimt_b200.so (not part of the C-ABI).
 //   imt_capi.cu     context, batched hashing, tree build, paths, folds, traces, sharding cap, calibration
 //   imt_indexed.cu  sorted-key index, low-leaf lookups, non-inclusion witnesses, batched inserts
-// Each translation unit that hashes owns a private __constant__ copy of the Poseidon parameters (the library is
-// built without relocatable device code); imt_ctx_create uploads both.
+// All hashing kernels live in imt_capi.cu (one __constant__ copy of the Poseidon parameters); imt_indexed.cu prepares
+// operands and calls them through imt_host::launch_hash / launch_level.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -129,8 +129,10 @@ imt_status launch_convert(imt_ctx* ctx, const void* d_in, void* d_out, size_t n,
 // batched get_proof from device indices into device buffers (any of d_helpers / d_helpers_fe may be null)
 imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe);
 
+// one tree level, Montgomery in / out: d_dst[i] = H(d_src[2i], d_src[2i+1]); small levels take the cooperative kernel
+imt_status launch_level(imt_ctx* ctx, const imt::Fr* d_src, imt::Fr* d_dst, size_t nodes);
+
 // ---- implemented in imt_indexed.cu
-cudaError_t upload_params_indexed(const imt::PoseidonParams* host_params);
 void invalidate_index(imt_tree* t);
 
 }  // namespace imt_host
