@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MACS_PER_HASH = 163_200          # 2 perms x 600 Montgomery muls x 136 32x32->64 MACs
+EXECUTED_MACS_PER_HASH = 123_792  # what the kernels issue: squarings are 36 products, 3-term dot products reduce once (ncu: profiles/)
+LEAF_DRAM_BYTES_PER_HASH = 112.6  # dram__bytes_read+write of k_hash<3> per leaf, ncu --set full (profiles/r01b_summary.md)
 METRIC = "poseidon_hashes_per_s_depth24_tree_build"
 
 
@@ -465,7 +467,13 @@ def main():
     leaf_bytes = 128.0  # 96 B preimage read + 32 B hash written per leaf hash
     roofline = {
         "bound": "imad", "kernel": "k_hash<3> (leaf hashing)", "achieved": achieved / 1e9, "peak": imad_rate / 1e9, "unit": "GMAC/s",
-        "frac": achieved / imad_rate if imad_rate else None, "traffic": None,
+        "frac": achieved / imad_rate if imad_rate else None,
+        "executed_frac": achieved / imad_rate * EXECUTED_MACS_PER_HASH / MACS_PER_HASH if imad_rate else None,
+        "traffic": LEAF_DRAM_BYTES_PER_HASH * (k3_hashes / max(k3_launches, 1)),
+        "traffic_note": "bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel per leaf (112.6 B, one --set full "
+                        "capture, profiles/) x leaves per launch; algorithmic 128 B per leaf",
+        "frac_note": "frac uses ALGORITHMIC MACs (163200 per hash) and exceeds 1 because squarings and one-reduction dot products execute "
+                     "123792; executed_frac is the multiply-pipe utilisation (ncu sm__pipe_fmaheavy_cycles_active agrees)",
         "peak_source": f"calibrated in this run: IMAD.WIDE.U32.X carry chains saturating all SMs (imt_calibrate_imad); = 32 wide MACs/clk/SM at "
                        f"{imad_mhz:.0f} MHz. MEASURED_PEAKS.json has no integer peak",
         "algorithmic_macs_per_hash": MACS_PER_HASH, "kernel_ms_per_launch": k3_per_launch_ms,

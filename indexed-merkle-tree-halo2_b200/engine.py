@@ -197,6 +197,34 @@ class Engine:
                                                           _dev_ptr(d_states) if d_states is not None else None,
                                                           _dev_ptr(d_roots) if d_roots is not None else None))
 
+    def trace_insert_witness(self, w, first_idx):
+        """Poseidon witness traces of everything the chip's insert_leaf hashes, per insert and in its call order
+        (indexed_merkle_tree.rs:253-313): 3 leaf hashes + 4 x depth node hashes = (6 + 8 depth) permutations.
+        `w` is the dict Tree.insert_batch returned, first_idx the slot of its first insert. Returns traces
+        (b, 132, 3, 4) for the leaf hashes / (b, depth, 132, 3, 4) for the folds, plus the roots each fold ends in."""
+        b, d = w["low_idx"].shape[0], w["low_siblings"].shape[1]
+        new_idx = np.arange(first_idx, first_idx + b, dtype=np.uint64)
+        idx_fe = np.zeros((b, 4), np.uint64)
+        if self.fmt == _ffi.FE_CANONICAL:
+            idx_fe[:, 0] = new_idx
+        else:
+            idx_fe = fes_from_ints([(int(i) << 256) % P for i in new_idx])
+        new_low = w["low_leaves"].copy()                                    # {low.val, new.val, new_idx}   IMT:265-270
+        new_low[:, 1] = w["new_leaves"][:, 0]
+        new_low[:, 2] = idx_fe
+        zero = np.zeros((b, 3, 4), np.uint64)                               # the empty slot the new leaf replaces, IMT:247-251
+        h_low, t_low = self.trace_hashes(w["low_leaves"], 3)                # verify_non_inclusion: low leaf hash      IMT:193-194
+        r_old, t_low_path = self.trace_merkle_proofs(h_low, w["low_idx"], w["low_siblings"])            # ... under old_root IMT:196-204
+        h_nl, t_nl = self.trace_hashes(new_low, 3)                          # updated low leaf                         IMT:271-275
+        r_int, t_int_path = self.trace_merkle_proofs(h_nl, w["low_idx"], w["low_siblings"])             # interim root       IMT:277-284
+        h_zero, _ = self.trace_hashes(zero[:1], 3, want_states=False)
+        r_zero, t_zero_path = self.trace_merkle_proofs(np.broadcast_to(h_zero, (b, 4)), new_idx, w["new_siblings"])  # IMT:286-294
+        h_new, t_new = self.trace_hashes(w["new_leaves"], 3)                # new leaf hash                            IMT:299-303
+        r_new, t_new_path = self.trace_merkle_proofs(h_new, new_idx, w["new_siblings"])                 # new root           IMT:305-313
+        return dict(low_leaf=t_low, low_path=t_low_path, new_low_leaf=t_nl, interim_path=t_int_path, zero_path=t_zero_path,
+                    new_leaf=t_new, new_path=t_new_path, old_root=r_old, interim_root=r_int, zero_leaf_root=r_zero, new_root=r_new,
+                    new_low_leaf_preimage=new_low)
+
     def low_leaf_merge(self, values, cand_keys, cand_slots, flags, occupied_total, n_total, head_next_zero):
         """replicated half of a sharded lookup: [world][q] gathered candidates -> (low_idx, matched)"""
         v = _fe_array(values, ())

@@ -185,6 +185,37 @@ def test_insert_batch_matches_full_rebuild_oracle(eng):
         assert_witness_equal(got, k, st.insert(vals[k], m + k, incremental=False))
 
 
+def test_insert_leaf_witness_traces(eng, eng_mont):
+    """the per-round Poseidon states of all (3 + 4 depth) hashes insert_leaf constrains (IMT:253-313), in its
+    call order, against the oracle's trace of the same hashes; the four folds end in old / interim / interim / new root."""
+    depth, m, b = 5, 7, 6
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, m, seed=21)
+    vals = synth.field_elements(b, seed=22)
+    for e, enc, dec in ((eng, lambda a: a, lambda a: a), (eng_mont, to_mont, from_mont)):
+        tree = e.build_from_leaves(enc(pre))
+        w = tree.insert_batch(enc(vals), m)
+        tr = e.trace_insert_witness(w, m)
+        assert np.array_equal(tr["old_root"], w["old_roots"]) and np.array_equal(tr["new_root"], w["new_roots"])
+        assert np.array_equal(tr["zero_leaf_root"], tr["interim_root"])          # IMT:286-294 holds on GPU-made witnesses
+        for k in (0, 3, b - 1):
+            low, new = dec(w["low_leaves"][k]), dec(w["new_leaves"][k])
+            new_low = np.stack([low[0], new[0], O.fe(m + k)])
+            assert np.array_equal(dec(tr["new_low_leaf_preimage"][k]), new_low)
+            for name, leaf, path_name, idx, sib in (("low_leaf", low, "low_path", int(w["low_idx"][k]), dec(w["low_siblings"][k])),
+                                                    ("new_low_leaf", new_low, "interim_path", int(w["low_idx"][k]), dec(w["low_siblings"][k])),
+                                                    (None, np.zeros((3, 4), np.uint64), "zero_path", m + k, dec(w["new_siblings"][k])),
+                                                    ("new_leaf", new, "new_path", m + k, dec(w["new_siblings"][k]))):
+                h, ws = O.hash_trace(leaf)
+                if name:
+                    assert np.array_equal(dec(tr[name][k]), ws), (k, name)
+                for lvl in range(depth):
+                    pair = np.stack([h, sib[lvl]]) if idx % 2 == 0 else np.stack([sib[lvl], h])
+                    h, ws = O.hash_trace(pair)
+                    assert np.array_equal(dec(tr[path_name][k, lvl]), ws), (k, path_name, lvl)
+                    idx //= 2
+
+
 def test_insert_errors_leave_the_tree_untouched(eng):
     n, m = 16, 6
     pre = synth.indexed_preimages(n, m, seed=5)
