@@ -74,17 +74,17 @@ def launches(tag, md):
     md.append("")
 
 
-def full(tag, md):
-    rep = os.path.join(ROOT, "gpurun_out", f"{tag}_k_hash.ncu-rep")
+def full(tag, md, suffix="k_hash", title="Top kernels"):
+    rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{suffix}.ncu-rep")
     if not os.path.exists(rep):
         return
     rows = ncu_csv(rep, "raw")
     hdr, units = rows[0], rows[1]
-    md.append("## Top kernel, `ncu --set full --clock-control none --import-source on`\n")
+    md.append(f"## {title}, `ncu --set full --clock-control none --import-source on` ({tag}_{suffix}.ncu-rep)\n")
     for r in rows[2:]:
         md.append(f"### `{r[hdr.index('Kernel Name')][:60]}`\n\n| metric | value |\n|---|---:|")
         for key, label in KEYS:
-            if key in hdr:
+            if key in hdr and "nan" not in r[hdr.index(key)]:
                 i = hdr.index(key)
                 md.append(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
         md.append("")
@@ -99,7 +99,11 @@ def full(tag, md):
             cur["hdr"] = r
         elif cur is not None:
             cur["rows"].append(r)
-    for k in kern[:2]:
+    seen = set()
+    for k in kern:
+        if k["name"] in seen:
+            continue
+        seen.add(k["name"])
         h = k["hdr"]
         i_s, i_e, i_n = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
         ops, samp = collections.Counter(), collections.Counter()
@@ -123,6 +127,7 @@ def main():
     md = [f"# ncu summary `{tag}` (B200, sm_100a) — generated by tools/ncu_summary.py from gpurun_out/{tag}_*\n"]
     launches(tag, md)
     full(tag, md)
+    full(tag, md, "k_coop", "Cooperative kernel (3 lanes per hash): levels of 8192, 4096, ... nodes")
     os.makedirs(OUT, exist_ok=True)
     out = os.path.join(OUT, f"{tag}_summary.md")
     open(out, "w").write("\n".join(md) + "\n")
