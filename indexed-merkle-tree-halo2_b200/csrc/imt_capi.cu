@@ -75,8 +75,11 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
         IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
         IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
     }
-    k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
-                                                                  ctx->d_err);
+    if (n <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh)
+        k_hash_coop<ARITY><<<grid_for(4 * n, 128), 128, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, ctx->d_err);
+    else
+        k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
+                                                                      ctx->d_err);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     if (ctx->timing) {
@@ -99,21 +102,7 @@ size_t coop_max_nodes() {
 
 // one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
 imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
-    if (nodes > coop_max_nodes()) return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    imt_ctx::Timed tm{nullptr, nullptr, 2, nodes};
-    if (ctx->timing) {
-        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.a));
-        IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
-        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, ctx->stream));
-    }
-    k_hash2_coop<<<grid_for(4 * nodes, 128), 128, 0, ctx->stream>>>((const uint4*)src, (uint4*)dst, nodes, ctx->d_params);
-    ++ctx->launches;
-    IMT_TRY_CUDA(ctx, cudaGetLastError());
-    if (ctx->timing) {
-        IMT_TRY_CUDA(ctx, cudaEventRecord(tm.b, ctx->stream));
-        ctx->pending.push_back(tm);
-    }
-    return IMT_OK;
+    return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, ctx->stream);
 }
 
 // all levels above level 0 (which must already hold the Montgomery leaf hashes)

@@ -75,28 +75,41 @@ __device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* 
     }
 }
 
-// H(in[2h], in[2h+1]) for the nodes of one (small) tree level, Montgomery in, Montgomery out: 4 threads per hash.
-__global__ void __launch_bounds__(128) k_hash2_coop(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
-                                                    const PoseidonParams* __restrict__ G) {
+// out[h] = H(in[ARITY*h .. ARITY*h + ARITY)) for a SMALL batch (one tree level near the root, the leaves of an insert
+// batch, a handful of hashes from the reference-style API): 4 threads per hash. Formats as in k_hash.
+template <int ARITY>
+__global__ void __launch_bounds__(128) k_hash_coop(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int in_fmt, int out_fmt,
+                                                   const PoseidonParams* __restrict__ G, uint32_t* __restrict__ err) {
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t h = tid >> 2;
     const int r = (int)(tid & 3);
     const int base = (int)(threadIdx.x & 31) & ~3;
     const size_t hc = h < n ? h : n - 1;  // lanes past the end recompute the last hash: every lane must reach the shuffles
-    uint32_t x[8];
-    if (r == 0) ld_fe(x, &G->cap);
-    else load_fe(x, in + 2 * (2 * hc + (r == 1 ? 0 : 1)));
-    permute_coop(x, G, r, base);
-    {  // second absorb of a 2-input hash: nothing left but the padding 1 on lane 1
-        uint32_t one[8];
-        ld_fe(one, &G->one);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) one[i] = (r == 1) ? one[i] : 0u;
-        add_semi(x, x, one);
+    uint32_t x[8], second[8];             // this lane's state element; what it absorbs before the second permutation
+    bool ok = true;
+    if (r == 0) {
+        ld_fe(x, &G->cap);
+    } else {
+        load_fe(x, in + 2 * (ARITY * hc + (r == 1 ? 0 : 1)));
+        ok &= ingest(x, in_fmt);
     }
+    // second absorb: the remaining input (ARITY 3) followed by the padding 1
+    if (ARITY == 3 && r == 1) {
+        load_fe(second, in + 2 * (ARITY * hc + 2));
+        ok &= ingest(second, in_fmt);
+    } else {
+        ld_fe(second, &G->one);
+        const bool pad_here = ARITY == 3 ? r == 2 : r == 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) second[i] = pad_here ? second[i] : 0u;
+    }
+    if (!ok) atomicOr(err, kErrNonCanonical);
+    permute_coop(x, G, r, base);
+    add_semi(x, x, second);
     permute_coop(x, G, r, base);
     if (r == 1 && h < n) {
         canonicalize(x);
+        egress(x, out_fmt);
         store_fe(out + 2 * h, x);
     }
 }

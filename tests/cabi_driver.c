@@ -1,0 +1,86 @@
+/* TEST: a plain C99 client of include/imt_b200.h — what a cgo / Rust `extern "C"` binding sees: no CUDA headers, no
+ * C++, only pointers and sizes. Built by tests/test_cabi_driver.py with gcc and linked against libimt_b200.so.
+ *   exit 0  everything checked (GPU present)
+ *   exit 3  imt_ctx_create failed cleanly (no GPU): the library has no CPU fallback
+ * The scenario is the native half of the reference's test_insert_leaf_multiple_round
+ * (/root/reference/src/indexed_merkle_tree.rs:679-741): empty depth-3 tree, inserts 30,10,20,5,50,35. */
+#include <inttypes.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "imt_b200.h"
+
+#define CHECK(call)                                                                              \
+    do {                                                                                         \
+        imt_status st_ = (call);                                                                 \
+        if (st_ != IMT_OK) {                                                                     \
+            fprintf(stderr, "%s -> %d (%s) %s\n", #call, (int)st_, imt_status_string(st_), imt_last_error(ctx)); \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+static void print_fe(const char* tag, const uint64_t* fe) {
+    printf("%s %016" PRIx64 "%016" PRIx64 "%016" PRIx64 "%016" PRIx64 "\n", tag, fe[3], fe[2], fe[1], fe[0]);
+}
+
+int main(void) {
+    imt_ctx* ctx = NULL;
+    imt_status st = imt_ctx_create(0, IMT_FE_CANONICAL, &ctx);
+    if (st != IMT_OK) {
+        printf("no-gpu status=%d\n", (int)st);
+        return ctx == NULL && st == IMT_ERR_CUDA ? 3 : 1;
+    }
+    /* test_hash_zero (IMT:805-810): Poseidon(0,0,0), the literal at IMT:247-251 */
+    uint64_t zeros[12] = {0}, kat[4];
+    CHECK(imt_poseidon_hash3(ctx, zeros, 1, kat));
+    print_fe("kat", kat);
+
+    /* error strings of IndexedMerkleTree::new (utils.rs:25, 35) */
+    imt_tree* tree = NULL;
+    uint64_t three[12] = {1, 0, 0, 0, 2, 0, 0, 0, 3, 0, 0, 0};
+    st = imt_tree_build_from_hashes(ctx, three, 0, &tree);
+    printf("empty: %d %s\n", (int)st, imt_status_string(st));
+    st = imt_tree_build_from_hashes(ctx, three, 3, &tree);
+    printf("odd: %d %s\n", (int)st, imt_status_string(st));
+
+    /* 8 empty leaves, then six inserts in one batch with every witness the chip loads */
+    uint64_t pre[8 * 12];
+    memset(pre, 0, sizeof pre);
+    CHECK(imt_tree_build_from_leaves(ctx, pre, 8, &tree));
+    uint64_t root[4];
+    CHECK(imt_tree_root(tree, root));
+    print_fe("empty_root", root);
+    size_t occupied = 0;
+    CHECK(imt_tree_occupied(tree, &occupied));
+    const uint64_t ins[6] = {30, 10, 20, 5, 50, 35};
+    uint64_t vals[6 * 4] = {0};
+    for (int i = 0; i < 6; ++i) vals[4 * i] = ins[i];
+    uint64_t old_roots[6 * 4], new_roots[6 * 4], low_idx[6], low_leaves[6 * 12], new_leaves[6 * 12], low_sib[6 * 3 * 4], new_sib[6 * 3 * 4];
+    uint8_t low_hel[6 * 3], new_hel[6 * 3], largest[6];
+    imt_insert_witness w = {old_roots, low_idx, low_leaves, low_sib, low_hel, new_roots, new_leaves, new_sib, new_hel, largest};
+    CHECK(imt_insert_batch(tree, vals, 6, occupied, &w));
+    for (int i = 0; i < 6; ++i) {
+        printf("low_idx %" PRIu64 " largest %d\n", low_idx[i], (int)largest[i]);
+        print_fe("root", new_roots + 4 * i);
+    }
+    /* verify_proof (utils.rs:87-107) of every new leaf under its new root, through the batched call */
+    uint64_t leaf_hashes[6 * 4], idx[6];
+    uint8_t ok[6];
+    CHECK(imt_poseidon_hash3(ctx, new_leaves, 6, leaf_hashes));
+    for (int i = 0; i < 6; ++i) idx[i] = occupied + (uint64_t)i;
+    CHECK(imt_verify_proofs(ctx, leaf_hashes, idx, new_roots, new_sib, 6, 3, ok));
+    for (int i = 0; i < 6; ++i) {
+        if (!ok[i]) {
+            fprintf(stderr, "new leaf %d does not verify\n", i);
+            return 1;
+        }
+    }
+    /* non-inclusion of 25: low leaf 20 -> 30 */
+    uint64_t q[4] = {25, 0, 0, 0}, li, ll[12], sib[3 * 4];
+    uint8_t matched, hel[3], lg;
+    CHECK(imt_non_inclusion_paths(tree, q, 1, &li, &matched, ll, sib, hel, &lg));
+    printf("non_inclusion low_idx %" PRIu64 " val %" PRIu64 " next %" PRIu64 " matched %d largest %d\n", li, ll[0], ll[4], (int)matched, (int)lg);
+    imt_tree_destroy(tree);
+    imt_ctx_destroy(ctx);
+    return 0;
+}

@@ -90,6 +90,23 @@ def test_non_canonical_input_is_rejected(eng, eng_mont):
         eng.hash2(all_ones)
 
 
+def test_large_and_small_batches_take_different_kernels_and_agree(eng):
+    """<= 8192 hashes run on the 3-lanes-per-hash latency kernel, larger batches on the thread-per-hash kernel: same
+    digests from both, and both reject a non-canonical element."""
+    n = 9000
+    x = synth.field_elements(3 * n, seed=4242).reshape(n, 3, 4)
+    big = eng.hash3(x)
+    assert np.array_equal(big, O.hash3(x, 8))
+    assert np.array_equal(eng.hash3(x[:8192]), big[:8192]) and np.array_equal(eng.hash3(x[8192:]), big[8192:])
+    y = x.reshape(-1, 2, 4)[:8500]
+    assert np.array_equal(eng.hash2(y), O.hash2(y, 8))
+    bad = x.copy()
+    bad[8999, 2] = np.array([(P >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    with pytest.raises(imt_b200.ImtError) as e:
+        eng.hash3(bad)
+    assert e.value.status == _ffi.ERR_NON_CANONICAL
+
+
 @pytest.mark.parametrize("depth", [1, 3, 7, 12])
 def test_tree_build_every_level(eng, depth):
     n = 1 << depth
