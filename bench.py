@@ -156,7 +156,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "hashes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery(cpu: u64x4)",
         "data": "synthetic", "config": {"workload": f"depth-{a.depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57",
-                                        "depth": a.depth, "sample_depth": S},
+                                        "depth": a.depth, "leaves": 1 << a.depth, "hashes_per_step": 2 * (1 << a.depth) - 1,
+                                        "sharding": "host threads", "seed": synth.DEFAULT_SEED, "fe_format": "canonical",
+                                        "sample_depth": S, "sample_hashes_per_step": hashes},
         "cpu_baseline": {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C port of the reference's Rust CPU path (oracle/imt_oracle.c): the crate itself is unbuildable here",
