@@ -278,3 +278,15 @@ def test_depth20_root_matches_golden_and_round_trips(eng):
     assert np.array_equal(hel, ((idx[:, None] >> np.arange(20, dtype=np.uint64)[None, :]) & np.uint64(1)) == 0)
     t.rebuild_from_leaves(pre)
     assert np.array_equal(t.root(), root)
+
+
+def test_depth24_roots_match_golden(eng):
+    """The headline size (BASELINE metric: depth-24 build, 33 554 431 hashes): roots of the random and the indexed
+    synthetic trees against the oracle's (tests/golden/make_golden.py --depth24, ~6 min per tree on 8 host cores)."""
+    n = 1 << 24
+    t = eng.build_from_leaves(synth.random_preimages(n))
+    assert imt_b200.fe_to_int(t.root()) == int(GOLD["build_roots"]["24"]["random"])
+    pre = synth.indexed_preimages(n)
+    t.rebuild_from_leaves(pre)
+    assert imt_b200.fe_to_int(t.root()) == int(GOLD["build_roots"]["24"]["indexed"])
+    assert t.occupied == n
