@@ -282,11 +282,15 @@ def test_depth20_root_matches_golden_and_round_trips(eng):
 
 def test_depth24_roots_match_golden(eng):
     """The headline size (BASELINE metric: depth-24 build, 33 554 431 hashes): roots of the random and the indexed
-    synthetic trees against the oracle's (tests/golden/make_golden.py --depth24, ~6 min per tree on 8 host cores)."""
+    synthetic trees against the oracle's (tests/golden/make_golden.py --depth24, ~6 min per tree on 8 host cores).
+    The leaves are synthesised on the device (the torch generators are checked against the numpy ones on the CPU)."""
+    import torch
     n = 1 << 24
-    t = eng.build_from_leaves(synth.random_preimages(n))
+    d_pre = synth.field_elements_torch(3 * n, device="cuda").view(n, 3, 4)
+    t = eng.build_from_leaves_dev(d_pre, n)
     assert imt_b200.fe_to_int(t.root()) == int(GOLD["build_roots"]["24"]["random"])
-    pre = synth.indexed_preimages(n)
-    t.rebuild_from_leaves(pre)
+    d_pre = synth.indexed_preimages_torch(n, device="cuda")
+    torch.cuda.synchronize()
+    t.rebuild_from_leaves_dev(d_pre)
     assert imt_b200.fe_to_int(t.root()) == int(GOLD["build_roots"]["24"]["indexed"])
     assert t.occupied == n

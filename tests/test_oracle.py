@@ -171,3 +171,14 @@ def test_synthetic_generator_matches_oracle_definition():
         assert ints[ni][0] == nv
         cur = ni
     assert count == 100 and all(x == [0, 0, 0] for x in ints[100:])
+
+
+def test_torch_synthetic_generators_match_numpy():
+    """bench.py and the depth-24 GPU test synthesise leaves with torch on the device; same streams as the numpy versions"""
+    import imt_b200
+    from imt_b200 import synth
+    a = synth.field_elements(1000, seed=77, first=5)
+    b = synth.field_elements_torch(1000, seed=77, first=5, device="cpu").numpy().view(np.uint64)
+    assert np.array_equal(a, b)
+    for n, m in [(64, 40), (256, 256), (16, 1), (16, 2)]:
+        assert np.array_equal(synth.indexed_preimages(n, m, seed=5), synth.indexed_preimages_torch(n, m, seed=5, device="cpu").numpy().view(np.uint64))
