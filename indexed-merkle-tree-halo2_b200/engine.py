@@ -163,6 +163,18 @@ class Engine:
     def build_from_hashes_dev(self, d_hashes, n):
         return self._tree(self._lib.imt_tree_build_from_hashes_dev, _dev_ptr(d_hashes), n)
 
+    def load_tree(self, path):
+        """Rebuilds a tree from a checkpoint written by Tree.save(): re-hashes the stored leaves on the GPU and checks the
+        result against the stored root."""
+        with np.load(path) as z:
+            pre, root, fmt = z["preimages"], z["root"], int(z["format"])
+        if fmt != self.fmt:
+            raise ValueError("checkpoint was written by an engine of the other field-element format")
+        tree = self.build_from_leaves(pre)
+        if not np.array_equal(tree.root(), root):
+            raise ImtError(_ffi.ERR_INVALID_ARG, "checkpoint is corrupt: the rebuilt root differs from the stored one")
+        return tree
+
     # ---- path folding
     def verify_proofs(self, leaves, indices, roots, siblings):
         lv = _fe_array(leaves, ())
@@ -291,6 +303,13 @@ class Tree:
         out = np.empty((n_local, 3, 4), np.uint64)
         self.engine._check(self._lib.imt_tree_preimages(self._h, _ptr(out)))
         return out
+
+    def save(self, path):
+        """Checkpoint: the leaves as the reference's serde derive would write them — per leaf val, next_val,
+        next_idx (utils.rs:12-17), 32 little-endian bytes each in the engine's format (canonical = halo2curves `to_repr`) —
+        plus the root. The levels are NOT stored: load_tree() re-hashes (0.55 s at depth 24) and verifies the root."""
+        n = self.num_leaves
+        np.savez(path, preimages=self.preimages(n), root=self.root(), format=np.int64(self.engine.fmt))
 
     def rebuild_from_leaves(self, preimages):
         a = _fe_array(preimages, (3,))

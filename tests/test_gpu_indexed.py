@@ -305,3 +305,22 @@ def test_config5_one_million_lookups_then_4096_inserts(eng):
         assert_witness_equal(got, k, st.insert(vals[k], m + k, incremental=True))
     final = tree.preimages(n)
     assert np.array_equal(O.build_from_preimages(final, O.max_threads()), tree.root())
+
+
+def test_checkpoint_round_trip(eng, tmp_path):
+    n, m = 256, 100
+    pre = synth.indexed_preimages(n, m, seed=12)
+    tree = eng.build_from_leaves(pre)
+    tree.insert_batch(synth.field_elements(20, seed=13))
+    path = str(tmp_path / "tree.npz")
+    tree.save(path)
+    back = eng.load_tree(path)
+    assert np.array_equal(back.root(), tree.root()) and np.array_equal(back.preimages(n), tree.preimages(n)) and back.occupied == m + 20
+    raw = np.load(path)
+    assert raw["preimages"].tobytes()[:96] == tree.preimages(n)[0].tobytes()       # 3 x 32-byte little-endian canonical FE per leaf
+    bad = dict(raw)
+    bad["preimages"] = raw["preimages"].copy()
+    bad["preimages"][5, 0, 0] ^= np.uint64(1)
+    np.savez(path, **bad)
+    with pytest.raises(imt_b200.ImtError):
+        eng.load_tree(path)
