@@ -587,6 +587,10 @@ static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint6
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return finish(ctx);
 }
+// Host-buffer front end of the path fold. Without traces it is one launch. With traces the output is 12 672 bytes per
+// hash (19.9 GB for 2^16 depth-24 paths), so the batch is cut into chunks of queries: chunk c is folded into one of two
+// device buffers while the copy stream drains chunk c-1 to the caller's memory — device memory stays bounded and the
+// PCIe transfer, which is the bound of this call, overlaps the hashing.
 static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots, const void* siblings,
                              size_t q, unsigned depth, uint8_t* ok, void* roots_out, void* states) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
@@ -594,7 +598,7 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
-    DevBuf dl(ctx), di(ctx), dr(ctx), ds(ctx), dok(ctx), dro(ctx), dst(ctx);
+    DevBuf dl(ctx), di(ctx), dr(ctx), ds(ctx), dok(ctx), dro(ctx);
     IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, ds.alloc(q * depth * sizeof(Fr)));
@@ -604,16 +608,57 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
         IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dr.p, roots, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (roots_out) IMT_TRY_CUDA(ctx, dro.alloc(q * sizeof(Fr)));
-    if (states) IMT_TRY_CUDA(ctx, dst.alloc(q * depth * state_fe * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dl.p, leaves, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ds.p, siblings, q * depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    IMT_TRY(fold_paths_dev(ctx, dl.p, di.as<uint64_t>(), ok ? dr.p : nullptr, ds.p, q, depth, ok ? dok.as<uint8_t>() : nullptr,
-                           roots_out ? dro.p : nullptr, states ? dst.p : nullptr));
+    if (!states || depth == 0) {
+        IMT_TRY(fold_paths_dev(ctx, dl.p, di.as<uint64_t>(), ok ? dr.p : nullptr, ds.p, q, depth, ok ? dok.as<uint8_t>() : nullptr,
+                               roots_out ? dro.p : nullptr, nullptr));
+    } else {
+        const size_t per_query = (size_t)depth * state_fe * sizeof(Fr);
+        size_t chunk = 8192;  // queries per launch: enough warps to hide most of the hash latency, 2.5 GB of trace at depth 24
+        while (chunk > 64 && chunk * per_query > ((size_t)3 << 30)) chunk >>= 1;
+        if (chunk > q) chunk = q;
+        DevBuf buf0(ctx), buf1(ctx);
+        IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
+        if (q > chunk) IMT_TRY_CUDA(ctx, buf1.alloc(chunk * per_query));
+        void* bufs[2] = {buf0.p, buf1.p};
+        cudaEvent_t folded[2], drained[2];
+        for (int i = 0; i < 2; ++i) {
+            IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&folded[i], cudaEventDisableTiming));
+            IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+        }
+        IMT_TRY(clear_err(ctx));
+        cudaError_t e = cudaSuccess;
+        size_t c = 0;
+        for (size_t off = 0; off < q && e == cudaSuccess; off += chunk, ++c) {
+            const size_t cq = q - off < chunk ? q - off : chunk;
+            const int b = (int)(c & 1);
+            if (c >= 2) e = cudaStreamWaitEvent(ctx->stream, drained[b], 0);  // the buffer is free once its previous chunk left
+            if (e != cudaSuccess) break;
+            const unsigned threads = 32;
+            k_fold_paths<<<grid_for(cq, threads), threads, 0, ctx->stream>>>(
+                dl.as<uint4>() + 2 * off, di.as<uint64_t>() + off, ds.as<uint4>() + 2 * off * depth, ok ? dr.as<uint4>() + 2 * off : nullptr, cq, depth,
+                ctx->fmt, ok ? dok.as<uint8_t>() + off : nullptr, roots_out ? dro.as<uint4>() + 2 * off : nullptr, (uint4*)bufs[b], ctx->d_err);
+            ++ctx->launches;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaEventRecord(folded[b], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, folded[b], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((char*)states + off * per_query, bufs[b], cq * per_query, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(drained[b], ctx->copy_stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(folded[i]), cudaEventDestroy(drained[i]);
+        if (e != cudaSuccess) {
+            ctx->last_error = std::string("trace pipeline: ") + cudaGetErrorString(e);
+            return IMT_ERR_CUDA;
+        }
+        IMT_TRY(finish(ctx));
+    }
     if (ok) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ok, dok.p, q, cudaMemcpyDeviceToHost, ctx->stream));
     if (roots_out) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(roots_out, dro.p, q * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-    if (states)
-        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, q * depth * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }

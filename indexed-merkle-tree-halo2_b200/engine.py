@@ -189,13 +189,20 @@ class Engine:
         self._check(self._lib.imt_verify_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(rt), _ptr(sib), q, depth, _ptr(ok)))
         return ok.astype(bool)
 
-    def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True):
+    def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True, out_states=None):
+        """out_states: optional preallocated (q, depth, 132, 3, 4) uint64 array to receive the traces — e.g. a view of
+        pinned host memory, which the device can fill at PCIe speed (the traces are 12 672 bytes per hash)."""
         lv = _fe_array(leaves, ())
         q = lv.shape[0]
         idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(q)
         sib = _fe_array(siblings, ()).reshape(q, -1, 4)
         depth = sib.shape[1]
-        states = np.empty((q, depth, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
+        if out_states is not None:
+            if out_states.shape != (q, depth, STATES_PER_HASH, 3, 4) or out_states.dtype != np.uint64 or not out_states.flags.c_contiguous:
+                raise ValueError("out_states must be a C-contiguous uint64 array of shape (q, depth, 132, 3, 4)")
+            states = out_states
+        else:
+            states = np.empty((q, depth, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
         roots = np.empty((q, 4), np.uint64)
         self._check(self._lib.imt_trace_merkle_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(sib), q, depth, _ptr(states), _ptr(roots)))
         return roots, states
