@@ -324,3 +324,48 @@ def test_checkpoint_round_trip(eng, tmp_path):
     np.savez(path, **bad)
     with pytest.raises(imt_b200.ImtError):
         eng.load_tree(path)
+
+
+def test_reference_test_insert_leaf_mirror(eng):
+    """test_insert_leaf (IMT:360-596), native half, written with the reference's names: insert a (seeded) random 254-bit
+    value into the empty depth-3 tree as the largest, then 42 between 0 and it — by hand with re-hash + rebuild as the
+    reference does, and in one insert_batch; both must agree, and every verify_proof must hold."""
+    from imt_b200 import Poseidon, IndexedMerkleTree, IndexedMerkleTreeLeaf as IMTLeaf
+    native_hasher = Poseidon(8, 57, engine=eng)
+    leaves = []
+    for _ in range(8):                                                       # IMT:372-376
+        native_hasher.update([0, 0, 0])
+        leaves.append(native_hasher.squeeze_and_reset())
+    tree = IndexedMerkleTree.new(native_hasher, list(leaves))
+    a = random.Random(2024).getrandbits(254) % P                             # IMT:380-388, seeded
+    old_root = tree.get_root()
+    low_leaf_proof, low_helper = tree.get_proof(0)
+    assert tree.verify_proof(leaves[0], 0, tree.get_root(), low_leaf_proof)  # IMT:397-400
+    new_low_leaf = IMTLeaf(0, a, 1)
+    native_hasher.update(new_low_leaf.as_tuple())
+    leaves[0] = native_hasher.squeeze_and_reset()
+    native_hasher.update([a, 0, 0])
+    leaves[1] = native_hasher.squeeze_and_reset()
+    tree = IndexedMerkleTree.new(native_hasher, list(leaves))                # IMT:417
+    new_leaf_proof, new_helper = tree.get_proof(1)
+    assert tree.verify_proof(leaves[1], 1, tree.get_root(), new_leaf_proof)  # IMT:420-423
+    root1 = tree.get_root()
+    # second insert: 42, low leaf = slot 0 {0, a, 1} (IMT:495-525)
+    native_hasher.update([0, 42, 2])
+    leaves[0] = native_hasher.squeeze_and_reset()
+    native_hasher.update([42, a, 1])
+    leaves[2] = native_hasher.squeeze_and_reset()
+    tree = IndexedMerkleTree.new(native_hasher, list(leaves))
+    proof2, _ = tree.get_proof(2)
+    assert tree.verify_proof(leaves[2], 2, tree.get_root(), proof2)          # IMT:522-525
+    root2 = tree.get_root()
+    # the same two inserts as one device batch
+    dev = eng.build_from_leaves(np.zeros((8, 3, 4), np.uint64))
+    w = dev.insert_batch(O.fes([a, 42]), 1)
+    assert O.to_ints(w["old_roots"]) == [old_root, root1] and O.to_ints(w["new_roots"]) == [root1, root2]
+    assert [int(v) for v in w["low_idx"]] == [0, 0] and [int(v) for v in w["is_largest"]] == [1, 0]
+    assert O.to_ints(w["low_leaves"][0]) == [0, 0, 0] and O.to_ints(w["low_leaves"][1]) == [0, a, 1]
+    assert O.to_ints(w["new_leaves"][0]) == [a, 0, 0] and O.to_ints(w["new_leaves"][1]) == [42, a, 1]
+    assert O.to_ints(w["low_siblings"][0]) == low_leaf_proof and O.to_ints(w["new_siblings"][0]) == new_leaf_proof
+    assert O.to_ints(w["new_siblings"][1]) == proof2
+    assert [int(h) for h in w["low_helpers"][0]] == low_helper and [int(h) for h in w["new_helpers"][0]] == new_helper
