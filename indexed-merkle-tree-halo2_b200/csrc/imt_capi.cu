@@ -572,6 +572,22 @@ extern "C" imt_status imt_tree_get_proofs_fe(imt_tree* t, const uint64_t* indice
     return get_proofs(t, indices, q, siblings, nullptr, helpers_fe);
 }
 
+// one fold launch on the compute stream: few paths -> a quad per path (latency), many -> a thread per path (throughput)
+static void launch_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
+                        unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states) {
+    if (q <= coop_max_nodes()) {
+        k_fold_paths_coop<<<grid_for(4 * q, 128), 128, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
+                                                                         (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
+                                                                         (uint4*)d_states, ctx->d_params, ctx->d_err);
+    } else {
+        const unsigned threads = q >= (size_t)1 << 20 ? kHashThreads : 32;  // mid-size batches: one warp per block spreads evenly over the SMs
+        k_fold_paths<<<grid_for(q, threads), threads, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
+                                                                       (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
+                                                                       (uint4*)d_states, ctx->d_err);
+    }
+    ++ctx->launches;
+}
+
 static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings,
                                  size_t q, unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
@@ -579,11 +595,7 @@ static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint6
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     IMT_TRY(clear_err(ctx));
-    const unsigned fold_threads = q >= (size_t)1 << 20 ? kHashThreads : 32;  // small batches: one warp per block spreads evenly over the SMs
-    k_fold_paths<<<grid_for(q, fold_threads), fold_threads, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
-                                                                           (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
-                                                                           (uint4*)d_states, ctx->d_err);
-    ++ctx->launches;
+    launch_fold(ctx, d_leaves, d_indices, d_roots, d_siblings, q, depth, d_ok, d_roots_out, d_states);
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return finish(ctx);
 }
@@ -636,11 +648,9 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
             const int b = (int)(c & 1);
             if (c >= 2) e = cudaStreamWaitEvent(ctx->stream, drained[b], 0);  // the buffer is free once its previous chunk left
             if (e != cudaSuccess) break;
-            const unsigned threads = 32;
-            k_fold_paths<<<grid_for(cq, threads), threads, 0, ctx->stream>>>(
-                dl.as<uint4>() + 2 * off, di.as<uint64_t>() + off, ds.as<uint4>() + 2 * off * depth, ok ? dr.as<uint4>() + 2 * off : nullptr, cq, depth,
-                ctx->fmt, ok ? dok.as<uint8_t>() + off : nullptr, roots_out ? dro.as<uint4>() + 2 * off : nullptr, (uint4*)bufs[b], ctx->d_err);
-            ++ctx->launches;
+            launch_fold(ctx, dl.as<uint4>() + 2 * off, di.as<uint64_t>() + off, ok ? dr.as<uint4>() + 2 * off : nullptr,
+                        ds.as<uint4>() + 2 * off * depth, cq, depth, ok ? dok.as<uint8_t>() + off : nullptr,
+                        roots_out ? dro.as<uint4>() + 2 * off : nullptr, bufs[b]);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaEventRecord(folded[b], ctx->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, folded[b], 0);

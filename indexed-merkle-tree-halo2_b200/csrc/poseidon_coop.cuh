@@ -24,8 +24,31 @@ __device__ __forceinline__ void shfl_fe(uint32_t* d, const uint32_t* s, int src_
     for (int i = 0; i < 8; ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
 }
 
+struct NoCoopTrace {
+    __device__ __forceinline__ void emit(const uint32_t*, int) {}
+};
+// Witness-trace sink of the cooperative kernels: lane r writes element r of every traced state (3 x 32 contiguous bytes
+// per state from the three lanes of a quad).
+struct CoopTraceSink {
+    uint4* dst;  // next state of this hash (3 FE each)
+    int fmt;
+    bool on;     // false for the padding quads of the last warp: they run the same code (shuffles are collective) but store nothing
+    __device__ __forceinline__ void emit(const uint32_t* x, int r) {
+        if (on && r < 3) {
+            uint32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = x[i];
+            if (fmt == kFmtCanonical) from_mont(t, t);
+            else canonicalize(t);
+            store_fe(dst + 2 * r, t);
+        }
+        dst += 6;
+    }
+};
+
 // x: this lane's state element (role r = 0, 1, 2; r = 3 mirrors lane 2 and is ignored). base = first lane of the quad.
-__device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* __restrict__ G, int r, int base) {
+template <class Sink>
+__device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* __restrict__ G, int r, int base, Sink& sink) {
     const int rr = r < 3 ? r : 2;
     const bool lead = r == 0;
     {
@@ -33,6 +56,7 @@ __device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* 
         ld_fe(c, &G->pre[rr]);
         add_semi(x, x, c);
     }
+    sink.emit(x, r);
 #pragma unroll 1
     for (int round = 0; round < kRF + kRP; ++round) {
         const bool full = round < kHalfF || round >= kHalfF + kRP;
@@ -49,6 +73,7 @@ __device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* 
             ld_fe(m1, &m[rr][1]);
             ld_fe(m2, &m[rr][2]);
             dot3(x, u0, u1, u2, m0, m1, m2);
+            sink.emit(x, r);
         } else {
             const PartialRound* pr = &G->partial[round - kHalfF];
             uint32_t x2[8], x4[8], a[8], b[8], c[8], t[8];
@@ -71,6 +96,7 @@ __device__ __forceinline__ void permute_coop(uint32_t* x, const PoseidonParams* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = lead ? y[i] : x[i];
             mul_add(x, u, k, y);  // lead: s0' = u row0 + P1 + P2 ; lane i: s_i' = u col_i + s_i
+            sink.emit(x, r);
         }
     }
 }
@@ -104,13 +130,80 @@ __global__ void __launch_bounds__(128) k_hash_coop(const uint4* __restrict__ in,
         for (int i = 0; i < 8; ++i) second[i] = pad_here ? second[i] : 0u;
     }
     if (!ok) atomicOr(err, kErrNonCanonical);
-    permute_coop(x, G, r, base);
+    NoCoopTrace nt;
+    permute_coop(x, G, r, base, nt);
     add_semi(x, x, second);
-    permute_coop(x, G, r, base);
+    permute_coop(x, G, r, base, nt);
     if (r == 1 && h < n) {
         canonicalize(x);
         egress(x, out_fmt);
         store_fe(out + 2 * h, x);
+    }
+}
+
+// Batched verify_proof / compute_merkle_root for a SMALL batch of paths: a quad folds one path, level after level.
+// Same contract as k_fold_paths (kernels.cuh), including the optional witness trace.
+__global__ void __launch_bounds__(128) k_fold_paths_coop(const uint4* __restrict__ leaves, const uint64_t* __restrict__ idx,
+                                                         const uint4* __restrict__ siblings, const uint4* __restrict__ roots, size_t q,
+                                                         unsigned depth, int fmt, uint8_t* __restrict__ ok_out, uint4* __restrict__ roots_out,
+                                                         uint4* __restrict__ states, const PoseidonParams* __restrict__ G,
+                                                         uint32_t* __restrict__ err) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t p = tid >> 2;
+    const int r = (int)(tid & 3);
+    const int base = (int)(threadIdx.x & 31) & ~3;
+    const size_t pc = p < q ? p : q - 1;
+    const bool active = p < q;
+    uint32_t h[8], one[8];
+    load_fe(h, leaves + 2 * pc);  // every lane of the quad carries the running digest
+    bool ok = ingest(h, fmt);
+    ld_fe(one, &G->one);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) one[i] = (r == 1) ? one[i] : 0u;
+    uint64_t index = idx[pc];
+#pragma unroll 1
+    for (unsigned l = 0; l < depth; ++l) {
+        uint32_t s[8], x[8];
+        load_fe(s, siblings + 2 * (pc * depth + l));
+        ok &= ingest(s, fmt);
+        const bool left = (index & 1) == 0;
+        const bool take_h = (r == 1) == left;  // lane 1 holds the left input, lanes 2 (and 3) the right one
+        if (r == 0) ld_fe(x, &G->cap);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = take_h ? h[i] : s[i];
+        }
+        if (states) {  // warp-uniform: `states` is a kernel argument
+            CoopTraceSink sink{states + (pc * depth + l) * (size_t)(kStatesPerHash * 3 * 2), fmt, active};
+            permute_coop(x, G, r, base, sink);
+            add_semi(x, x, one);
+            permute_coop(x, G, r, base, sink);
+        } else {
+            NoCoopTrace nt;
+            permute_coop(x, G, r, base, nt);
+            add_semi(x, x, one);
+            permute_coop(x, G, r, base, nt);
+        }
+        canonicalize(x);
+        shfl_fe(h, x, base + 1);  // the digest is lane 1's element
+        index >>= 1;
+    }
+    if (!ok) atomicOr(err, kErrNonCanonical);
+    canonicalize(h);
+    if (r != 1 || !active) return;
+    if (ok_out) {
+        uint32_t rt[8];
+        load_fe(rt, roots + 2 * p);
+        if (!ingest(rt, fmt)) atomicOr(err, kErrNonCanonical);
+        canonicalize(rt);
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) same &= rt[k] == h[k];
+        ok_out[p] = (uint8_t)same;
+    }
+    if (roots_out) {
+        egress(h, fmt);
+        store_fe(roots_out + 2 * p, h);
     }
 }
 
