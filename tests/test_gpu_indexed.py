@@ -369,3 +369,61 @@ def test_reference_test_insert_leaf_mirror(eng):
     assert O.to_ints(w["low_siblings"][0]) == low_leaf_proof and O.to_ints(w["new_siblings"][0]) == new_leaf_proof
     assert O.to_ints(w["new_siblings"][1]) == proof2
     assert [int(h) for h in w["low_helpers"][0]] == low_helper and [int(h) for h in w["new_helpers"][0]] == new_helper
+
+
+@pytest.mark.parametrize("pattern", ["ascending", "descending", "zigzag", "dense_chain"])
+def test_insert_batch_adversarial_orders(eng, pattern):
+    """Orders that stress the sequential semantics inside one batch: every insert's low leaf is the previous insert
+    (ascending), always the head (descending), alternates between the two ends (zigzag), or 300 consecutive integers
+    hanging off one existing leaf (dense_chain) — against the oracle advancing one insert at a time."""
+    depth, m = 10, 3
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, m, seed=3)
+    b = 300
+    base = sorted(O.to_int(pre[i, 0]) for i in range(1, m))
+    if pattern == "ascending":
+        vals = [base[-1] + 1 + 7 * k for k in range(b)]
+    elif pattern == "descending":
+        vals = [base[0] - 1 - 7 * k for k in range(b)]
+    elif pattern == "zigzag":
+        vals = [(base[-1] + 1 + k) if k % 2 == 0 else (base[0] - 1 - k) for k in range(b)]
+    else:
+        mid = (base[0] + base[1]) // 2
+        order = list(range(b))
+        random.Random(5).shuffle(order)
+        vals = [mid + k for k in order]
+    assert all(0 < v < P for v in vals) and len(set(vals)) == b
+    v = O.fes(vals)
+    tree = eng.build_from_leaves(pre)
+    got = tree.insert_batch(v, m)
+    st = O.InsertState(pre, threads=4)
+    for k in range(b):
+        assert_witness_equal(got, k, st.insert(v[k], m + k, incremental=True))
+    assert np.array_equal(tree.preimages(n), st.pre) and np.array_equal(tree.root(), st.root())
+
+
+def test_insert_batch_chunk_boundary_and_single_inserts(eng):
+    """4097 inserts = one full internal chunk + 1; then single-insert calls; then the tree filled to the last slot."""
+    depth = 13
+    n = 1 << depth
+    m = n - 4097 - 3
+    pre = synth.indexed_preimages(n, m, seed=44)
+    tree = eng.build_from_leaves(pre)
+    st = O.InsertState(pre, threads=8)
+    vals = synth.field_elements(4100, seed=45)
+    got = tree.insert_batch(vals[:4097], m)
+    for k in range(4097):
+        want = st.insert(vals[k], m + k, incremental=True)
+        if k in (0, 1, 4095, 4096) or k % 97 == 0:
+            assert_witness_equal(got, k, want)
+    assert np.array_equal(tree.root(), st.root())
+    for k in range(4097, 4100):                                          # B = 1, three times, up to a completely full tree
+        got = tree.insert_batch(vals[k:k + 1])
+        assert_witness_equal(got, 0, st.insert(vals[k], m + k, incremental=True))
+    assert tree.occupied == n and np.array_equal(tree.preimages(n), st.pre)
+    with pytest.raises(imt_b200.ImtError) as e:
+        tree.insert_batch(synth.field_elements(1, seed=46))
+    assert e.value.status == _ffi.ERR_TREE_FULL
+    low, matched = tree.low_leaf_lookup(np.stack([vals[7], synth.field_elements(1, seed=47)[0]]))   # present value, full tree
+    assert (int(low[0]), bool(matched[0])) == O.low_leaf(st.pre, vals[7]) == (0, False)
+    assert (int(low[1]), bool(matched[1])) == O.low_leaf(st.pre, synth.field_elements(1, seed=47)[0])
