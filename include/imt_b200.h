@@ -67,6 +67,10 @@ uint64_t imt_ctx_launch_count(const imt_ctx* ctx);
  * the CUDA legacy default stream. imt_ctx_reset_stream returns to the internal stream. */
 imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream);
 imt_status imt_ctx_reset_stream(imt_ctx* ctx);
+/* Scratch buffers of the calls below are stream-ordered allocations from the device's default memory pool, which this
+ * library keeps cached between calls (a depth-24 trace call can leave ~5 GB there). imt_ctx_trim returns the cached,
+ * unused part to the driver — for processes that share the GPU with another allocator. */
+imt_status imt_ctx_trim(imt_ctx* ctx);
 /* Per-kernel device timing: when enabled every hash launch is bracketed by CUDA events on its stream.
  * imt_ctx_kernel_time returns, for hash kernels of the given arity (2 = node levels, 3 = leaf hashing), the summed
  * device time in ms, the launch count and the number of hashes since the last reset. */

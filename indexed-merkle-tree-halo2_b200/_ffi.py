@@ -31,6 +31,7 @@ SIGNATURES = {
     "imt_ctx_launch_count": (c_u64, [c_void_p]),
     "imt_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
     "imt_ctx_reset_stream": (c_int, [c_void_p]),
+    "imt_ctx_trim": (c_int, [c_void_p]),
     "imt_ctx_enable_timing": (c_int, [c_void_p, c_int]),
     "imt_ctx_kernel_time": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_double), c_u64p, c_u64p]),
     "imt_ctx_reset_timing": (c_int, [c_void_p]),

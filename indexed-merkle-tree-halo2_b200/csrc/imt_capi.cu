@@ -316,6 +316,15 @@ extern "C" imt_status imt_ctx_reset_stream(imt_ctx* ctx) {
     ctx->stream = ctx->own_stream;
     return IMT_OK;
 }
+extern "C" imt_status imt_ctx_trim(imt_ctx* ctx) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    IMT_TRY_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    IMT_TRY_CUDA(ctx, cudaMemPoolTrimTo(pool, 0));
+    return IMT_OK;
+}
 extern "C" imt_status imt_ctx_enable_timing(imt_ctx* ctx, int enabled) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
     ctx->timing = enabled != 0;

@@ -99,6 +99,10 @@ class Engine:
         """back to the engine's own non-blocking stream"""
         self._check(self._lib.imt_ctx_reset_stream(self._h))
 
+    def trim(self):
+        """give the cached scratch memory of earlier calls back to the driver"""
+        self._check(self._lib.imt_ctx_trim(self._h))
+
     def enable_timing(self, on=True):
         self._check(self._lib.imt_ctx_enable_timing(self._h, 1 if on else 0))
 

@@ -64,6 +64,13 @@ def test_edge_values(eng):
     assert np.array_equal(eng.hash2(pairs), O.hash2(pairs, 8))
 
 
+def test_trim_returns_cached_scratch(eng):
+    import torch
+    eng.hash3(synth.field_elements(3 * 200000, seed=1).reshape(-1, 3, 4))      # leaves ~25 MB of scratch in the pool
+    eng.trim()
+    assert np.array_equal(eng.hash2(O.fes([1, 2]).reshape(1, 2, 4)), O.fes([int(GOLD["h2_1_2"])]))   # and the engine still works
+
+
 def test_empty_batch(eng):
     assert eng.hash2(np.zeros((0, 2, 4), np.uint64)).shape == (0, 4)
     assert eng.hash3(np.zeros((0, 3, 4), np.uint64)).shape == (0, 4)
