@@ -206,6 +206,25 @@ imt_status imt_low_leaf_candidates(imt_tree* tree, const void* values, size_t q,
 imt_status imt_low_leaf_merge(imt_ctx* ctx, const void* values, const void* cand_keys, const uint64_t* cand_slots, const uint8_t* flags,
                               unsigned world, size_t q, uint64_t occupied_total, uint64_t n_total, int head_next_zero,
                               uint64_t* low_idx, uint8_t* matched);
+/* Insert batches on a sharded tree (<= 4096 inserts per round of calls; next_idx / slots are GLOBAL). Same result as
+ * imt_insert_batch on the unsharded tree — the reference's sequence of rebuilds (src/indexed_merkle_tree.rs:710-741):
+ *   1. every rank: imt_shard_insert_neighbors -> each value's neighbours in the rank's own sorted index (keys as
+ *      canonical integers; flags bit 0 predecessor exists, bit 1 value present, bit 2 successor exists)
+ *   2. all-gather ([world][b], rank-major); every rank: imt_shard_insert_plan -> the replicated plan: x[2b] = slot of
+ *      write t (t = 2k low leaf of insert k, 2k+1 its new leaf), upd[2b][3] = preimage each write stores,
+ *      low_old[b][3] = low leaves before (IMT:720), is_largest[b]. IMT_ERR_INVALID_ARG for a zero / present / repeated value.
+ *   3. every rank: imt_shard_insert_apply -> hashes and applies ITS writes to its subtree (levels, preimages, index);
+ *      sub_roots[2b] = subtree root after each own write, sib_local[2b][log2 n] = its path inside the subtree (zeros
+ *      for other ranks' writes)
+ *   4. all-gather (each write has one owner); every rank: imt_shard_insert_cap -> applies all writes to the replicated
+ *      cap: roots[2b] = global root after every write, sib_cap[2b][log2 world] = the cap part of every path. */
+imt_status imt_shard_insert_neighbors(imt_tree* tree, const void* values, size_t b, void* pred_keys, uint64_t* pred_slots,
+                                      void* succ_keys, uint64_t* succ_slots, uint8_t* flags);
+imt_status imt_shard_insert_plan(imt_ctx* ctx, const void* values, size_t b, uint64_t first_idx, unsigned world, const void* pred_keys,
+                                 const uint64_t* pred_slots, const void* succ_keys, const uint64_t* succ_slots, const uint8_t* flags,
+                                 uint64_t* x, void* upd, void* low_old, uint8_t* is_largest);
+imt_status imt_shard_insert_apply(imt_tree* tree, const uint64_t* x, const void* upd, size_t b, void* sub_roots, void* sib_local);
+imt_status imt_shard_insert_cap(imt_tree* tree, const uint64_t* x, const void* sub_roots, size_t b, void* roots, void* sib_cap);
 /* Preimages (3 FE each, context format) of the given slots and is_largest = (next_val == 0). Global indices inside this
  * rank's range for a shard. Either output may be NULL. */
 imt_status imt_tree_leaves(imt_tree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest);

@@ -73,6 +73,11 @@ SIGNATURES = {
     "imt_tree_head_next_zero": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "imt_low_leaf_candidates": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "imt_low_leaf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint, c_size_t, c_u64, c_u64, c_int, c_void_p, c_void_p]),
+    "imt_shard_insert_neighbors": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "imt_shard_insert_plan": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, c_uint, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "imt_shard_insert_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_shard_insert_cap": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_tree_leaves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_calibrate_imad": (c_int, [c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }

@@ -16,6 +16,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 #include <new>
 
 #include "imt_internal.h"
@@ -297,26 +299,18 @@ __global__ void __launch_bounds__(256) k_ins_validate(const uint4* __restrict__ 
 // Insert k of the chunk: its predecessor / successor among (indexed leaves) U (chunk values 0..k-1), i.e. the state
 // the reference's scan sees at that point, and from them the four preimages IMT:648-654 reads and writes.
 //   x[2k] = low slot, x[2k+1] = new slot;  upd[2k] = low leaf AFTER, upd[2k+1] = new leaf;  low_old[k] = low leaf BEFORE
-__global__ void __launch_bounds__(128) k_ins_resolve(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
-                                                     const uint4* __restrict__ vals, size_t b, uint64_t first_idx, int fmt,
-                                                     uint64_t* __restrict__ x, uint4* __restrict__ upd, uint4* __restrict__ low_old,
-                                                     uint8_t* __restrict__ is_largest) {
-    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (k >= b) return;
-    uint32_t v[8], pred[8], succ[8];
-    load_fe(v, vals + 2 * k);
-    const size_t j = lower_bound(keys, m, v);  // validated: j >= 1 and keys[j] != v
-    load_fe(pred, keys + 2 * (j - 1));
-    uint64_t pred_slot = slots[j - 1], succ_slot = 0;
-    bool has_succ = j < m;
-    if (has_succ) {
-        load_fe(succ, keys + 2 * j);
-        succ_slot = slots[j];
-    }
+// shared tail: refine (pred, succ) — the neighbours among the leaves indexed before the chunk — with the chunk's own
+// earlier values, then emit the slots and preimages. Returns false on a repeat inside the chunk.
+__device__ __forceinline__ bool ins_finish(size_t k, const uint32_t* v, uint32_t* pred, uint64_t pred_slot, uint32_t* succ, uint64_t succ_slot,
+                                           bool has_succ, const uint4* __restrict__ vals, uint64_t first_idx, int fmt, uint64_t* __restrict__ x,
+                                           uint4* __restrict__ upd, uint4* __restrict__ low_old, uint8_t* __restrict__ is_largest) {
+    bool distinct = true;
     for (size_t i = 0; i < k; ++i) {  // warp-uniform address: one broadcast load per step
         uint32_t w[8];
         load_fe(w, vals + 2 * i);
-        if (cmp256(w, v) < 0) {
+        const int c = cmp256(w, v);
+        distinct &= c != 0;
+        if (c < 0) {
             if (cmp256(w, pred) > 0) copy256(pred, w), pred_slot = first_idx + i;
         } else if (!has_succ || cmp256(w, succ) < 0) {
             copy256(succ, w), succ_slot = first_idx + i, has_succ = true;
@@ -342,6 +336,95 @@ __global__ void __launch_bounds__(128) k_ins_resolve(const uint4* __restrict__ k
     store_fe(u0, fp), store_fe(u0 + 2, fv), store_fe(u0 + 4, fni);
     uint4* u1 = upd + 6 * (2 * k + 1);  // {v, succ, succ_slot}
     store_fe(u1, fv), store_fe(u1 + 2, fs), store_fe(u1 + 4, fsi);
+    return distinct;
+}
+
+__global__ void __launch_bounds__(128) k_ins_resolve(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
+                                                     const uint4* __restrict__ vals, size_t b, uint64_t first_idx, int fmt,
+                                                     uint64_t* __restrict__ x, uint4* __restrict__ upd, uint4* __restrict__ low_old,
+                                                     uint8_t* __restrict__ is_largest) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= b) return;
+    uint32_t v[8], pred[8], succ[8];
+    load_fe(v, vals + 2 * k);
+    const size_t j = lower_bound(keys, m, v);  // validated: j >= 1 and keys[j] != v
+    load_fe(pred, keys + 2 * (j - 1));
+    uint64_t succ_slot = 0;
+    const bool has_succ = j < m;
+    if (has_succ) {
+        load_fe(succ, keys + 2 * j);
+        succ_slot = slots[j];
+    }
+    ins_finish(k, v, pred, slots[j - 1], succ, succ_slot, has_succ, vals, first_idx, fmt, x, upd, low_old, is_largest);
+}
+
+// Sharded inserts, per-rank half: the neighbours of every value in THIS rank's sorted index (keys as canonical
+// integers, slots global). flags bit 0: predecessor exists, bit 1: the value is a local key, bit 2: successor exists.
+__global__ void __launch_bounds__(256) k_ins_neighbors(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m, uint64_t base,
+                                                       const uint4* __restrict__ values, size_t b, int fmt, uint4* __restrict__ pred_keys,
+                                                       uint64_t* __restrict__ pred_slots, uint4* __restrict__ succ_keys,
+                                                       uint64_t* __restrict__ succ_slots, uint8_t* __restrict__ flags, uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    uint32_t v[8], p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load_fe(v, values + 2 * i);
+    if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
+    const size_t j = lower_bound(keys, m, v);
+    uint8_t f = 0;
+    uint64_t ps = 0, ss = 0;
+    size_t js = j;
+    if (j < m) {
+        uint32_t w[8];
+        load_fe(w, keys + 2 * j);
+        if (cmp256(w, v) == 0) f |= 2, js = j + 1;
+    }
+    if (j >= 1) load_fe(p, keys + 2 * (j - 1)), ps = base + slots[j - 1], f |= 1;
+    if (js < m) load_fe(q, keys + 2 * js), ss = base + slots[js], f |= 4;
+    store_fe(pred_keys + 2 * i, p);
+    store_fe(succ_keys + 2 * i, q);
+    pred_slots[i] = ps, succ_slots[i] = ss, flags[i] = f;
+}
+
+// Sharded inserts, replicated half: merge the gathered per-rank neighbours ([world][b], rank-major) into the global
+// ones, then the same resolution as k_ins_resolve. Zero, present or repeated values raise kErrBadInsert.
+__global__ void __launch_bounds__(128) k_ins_plan(const uint4* __restrict__ vals, size_t b, uint64_t first_idx, int fmt, unsigned world,
+                                                  const uint4* __restrict__ pred_keys, const uint64_t* __restrict__ pred_slots,
+                                                  const uint4* __restrict__ succ_keys, const uint64_t* __restrict__ succ_slots,
+                                                  const uint8_t* __restrict__ flags, uint64_t* __restrict__ x, uint4* __restrict__ upd,
+                                                  uint4* __restrict__ low_old, uint8_t* __restrict__ is_largest, uint32_t* __restrict__ err) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= b) return;
+    uint32_t v[8], pred[8] = {0, 0, 0, 0, 0, 0, 0, 0}, succ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load_fe(v, vals + 2 * k);
+    bool has_pred = false, has_succ = false, bad = zero256(v);
+    uint64_t pred_slot = 0, succ_slot = 0;
+    for (unsigned r = 0; r < world; ++r) {
+        const size_t o = (size_t)r * b + k;
+        const uint8_t f = flags[o];
+        bad |= (f & 2) != 0;
+        uint32_t w[8];
+        if (f & 1) {
+            load_fe(w, pred_keys + 2 * o);
+            if (!has_pred || cmp256(w, pred) > 0) copy256(pred, w), pred_slot = pred_slots[o], has_pred = true;
+        }
+        if (f & 4) {
+            load_fe(w, succ_keys + 2 * o);
+            if (!has_succ || cmp256(w, succ) < 0) copy256(succ, w), succ_slot = succ_slots[o], has_succ = true;
+        }
+    }
+    bad |= !has_pred;  // nothing below v anywhere: the tree has no head {0, ..}
+    if (!ins_finish(k, v, pred, pred_slot, succ, succ_slot, has_succ, vals, first_idx, fmt, x, upd, low_old, is_largest)) bad = true;
+    if (bad) atomicOr(err, kErrBadInsert);
+}
+
+// per write: the root after it (top versions) in the context format
+__global__ void __launch_bounds__(256) k_export_versions(const uint4* __restrict__ ver_level, unsigned writes, int fmt, uint4* __restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= writes) return;
+    uint32_t r[8];
+    load_fe(r, ver_level + 2 * (size_t)t);
+    egress(r, fmt);
+    store_fe(out + 2 * (size_t)t, r);
 }
 
 // For write t and level l (l fastest): prev = latest earlier write whose level-l node is the SIBLING of t's node
@@ -379,7 +462,7 @@ __global__ void __launch_bounds__(256) k_ins_links(const uint64_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_ins_pairs(const uint4* __restrict__ ver_level, const uint4* __restrict__ tree_levels, size_t n,
                                                    unsigned l, const uint64_t* __restrict__ x, const int* __restrict__ prev, unsigned writes,
                                                    unsigned depth, int fmt, uint4* __restrict__ pairs, uint4* __restrict__ sib_low,
-                                                   uint4* __restrict__ sib_new) {
+                                                   uint4* __restrict__ sib_new, uint4* __restrict__ sib_all) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= writes) return;
     const uint64_t node = x[t] >> l;
@@ -398,10 +481,9 @@ __global__ void __launch_bounds__(256) k_ins_pairs(const uint4* __restrict__ ver
     store_fe(pairs + 4 * (size_t)t, lo);
     store_fe(pairs + 4 * (size_t)t + 2, hi);
     uint4* wit = (t & 1) ? sib_new : sib_low;
-    if (wit) {
-        egress(sib, fmt);
-        store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), sib);
-    }
+    if (wit || sib_all) egress(sib, fmt);
+    if (wit) store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), sib);
+    if (sib_all) store_fe(sib_all + 2 * ((size_t)t * depth + l), sib);  // one row per write (sharded inserts)
 }
 
 // per insert: roots before / after, helper bits of both paths
@@ -447,7 +529,7 @@ __global__ void __launch_bounds__(256) k_ins_commit(const uint4* __restrict__ ve
     const uint4* v = ver + 2 * ((size_t)l * writes + t);
     uint4* dst = tree_levels + 2 * (level_offset(n, l) + node);
     dst[0] = v[0], dst[1] = v[1];
-    if (l == 0) {
+    if (l == 0 && pre) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) pre[6 * node + k] = upd[6 * (size_t)t + k];
     }
@@ -483,6 +565,24 @@ __global__ void k_iota_slots(uint32_t* s, size_t b, uint64_t first) {
 }
 
 // ------------------------------------------------------------------------------------------------- host side
+// Levels 1..depth of `writes` single-leaf writes to a tree (`tree_levels`, n leaves) from their level-0 versions in
+// ver[0 .. writes): links, then per level the operand gather + one level launch. ver holds (depth+1) x writes FE.
+imt_status versioned_levels(imt_ctx* ctx, const Fr* tree_levels, size_t n, unsigned depth, const uint64_t* d_x, unsigned writes, Fr* d_ver,
+                            int* d_prev, uint8_t* d_last, Fr* d_pairs, uint4* sib_low, uint4* sib_new, uint4* sib_all) {
+    const size_t L = depth + 1;
+    k_ins_links<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(d_x, writes, depth, d_prev, d_last);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    for (unsigned l = 0; l < depth; ++l) {
+        k_ins_pairs<<<grid_for(writes, 256), 256, 0, ctx->stream>>>((const uint4*)d_ver + 2 * ((size_t)l * writes), (const uint4*)tree_levels, n, l,
+                                                                    d_x, d_prev, writes, depth, ctx->fmt, (uint4*)d_pairs, sib_low, sib_new, sib_all);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        IMT_TRY(launch_level(ctx, d_pairs, d_ver + (size_t)(l + 1) * writes, writes));
+    }
+    return IMT_OK;
+}
+
 imt_status sort_pairs(imt_ctx* ctx, Fr* d_keys, uint32_t* d_slots, size_t count) {
     if (count < 2) return IMT_OK;
     size_t temp_bytes = 0;
@@ -728,19 +828,14 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         k_ins_resolve<<<grid_for(cb, 128), 128, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied, cvals, cb, first,
                                                                  ctx->fmt, x.as<uint64_t>(), upd.as<uint4>(), low_old.as<uint4>(),
                                                                  largest.as<uint8_t>());
-        k_ins_links<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(x.as<uint64_t>(), writes, depth, prev.as<int>(), last.as<uint8_t>());
-        ctx->launches += 2;
+        ++ctx->launches;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
-        lap("resolve+links");
-        // version 0 of every write: the hash of its leaf preimage (IMT:662-671)
+        lap("resolve");
+        // version 0 of every write: the hash of its leaf preimage (IMT:662-671); then all levels
         IMT_TRY(launch_hash(ctx, 3, upd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
-        for (unsigned l = 0; l < depth; ++l) {
-            k_ins_pairs<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(
-                ver.as<uint4>() + 2 * ((size_t)l * writes), (const uint4*)t->d_levels, t->n, l, x.as<uint64_t>(), prev.as<int>(), writes, depth,
-                ctx->fmt, pairs.as<uint4>(), out.low_siblings ? sib_low.as<uint4>() : nullptr, out.new_siblings ? sib_new.as<uint4>() : nullptr);
-            ++ctx->launches;
-            IMT_TRY(launch_level(ctx, pairs.as<Fr>(), ver.as<Fr>() + (size_t)(l + 1) * writes, writes));
-        }
+        IMT_TRY(versioned_levels(ctx, t->d_levels, t->n, depth, x.as<uint64_t>(), writes, ver.as<Fr>(), prev.as<int>(), last.as<uint8_t>(),
+                                 pairs.as<Fr>(), out.low_siblings ? sib_low.as<uint4>() : nullptr,
+                                 out.new_siblings ? sib_new.as<uint4>() : nullptr, nullptr));
         k_ins_outputs<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), (const uint4*)t->d_levels, t->n, x.as<uint64_t>(), (unsigned)cb,
                                                                   depth, ctx->fmt, out.old_roots ? r_old.as<uint4>() : nullptr,
                                                                   out.new_roots ? r_new.as<uint4>() : nullptr,
@@ -893,6 +988,220 @@ extern "C" imt_status imt_tree_leaves(imt_tree* t, const uint64_t* indices, size
     IMT_TRY(finish(ctx));
     if (leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(leaves, dl.p, q * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (is_largest) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dg.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- sharded inserts
+// An insert batch over a subtree-sharded tree (one process per GPU), at most kInsertChunk inserts per round of calls:
+//   1. every rank   imt_shard_insert_neighbors   neighbours of each value in the rank's own sorted index
+//   2. all-gather of the five arrays; every rank  imt_shard_insert_plan  -> the replicated plan: write slots x[2b]
+//      (GLOBAL), the preimages every write stores (upd), the low leaves before, is_largest
+//   3. every rank   imt_shard_insert_apply       its own writes: leaf hashes + versioned update of its subtree, commit,
+//                                                index merge; returns the subtree-root version and local path per own write
+//   4. all-gather of those (each write has one owner); every rank  imt_shard_insert_cap  the versioned update of the
+//      replicated cap over ALL writes -> the global root after every write + the cap part of every path
+// The result is the reference's sequence of rebuilds, as for imt_insert_batch (sharding.py assembles the witnesses).
+extern "C" imt_status imt_shard_insert_neighbors(imt_tree* t, const void* values, size_t b, void* pred_keys, uint64_t* pred_slots,
+                                                 void* succ_keys, uint64_t* succ_slots, uint8_t* flags) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (b && (!values || !pred_keys || !pred_slots || !succ_keys || !succ_slots || !flags)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    IMT_TRY(ensure_index(t));
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dv(ctx), dpk(ctx), dps(ctx), dsk(ctx), dss(ctx), df(ctx);
+    IMT_TRY_CUDA(ctx, dv.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dpk.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dsk.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dps.alloc(b * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dss.alloc(b * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, df.alloc(b));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, b * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_ins_neighbors<<<grid_for(b, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
+                                                               (uint64_t)t->rank * t->n, (const uint4*)dv.p, b, ctx->fmt, dpk.as<uint4>(),
+                                                               dps.as<uint64_t>(), dsk.as<uint4>(), dss.as<uint64_t>(), df.as<uint8_t>(), ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(pred_keys, dpk.p, b * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(succ_keys, dsk.p, b * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(pred_slots, dps.p, b * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(succ_slots, dss.p, b * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(flags, df.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_shard_insert_plan(imt_ctx* ctx, const void* values, size_t b, uint64_t first_idx, unsigned world, const void* pred_keys,
+                                            const uint64_t* pred_slots, const void* succ_keys, const uint64_t* succ_slots, const uint8_t* flags,
+                                            uint64_t* x, void* upd, void* low_old, uint8_t* is_largest) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (b && (!values || !pred_keys || !pred_slots || !succ_keys || !succ_slots || !flags || !x || !upd || !low_old || !is_largest))
+        return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (b > kInsertChunk || world == 0) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t g = (size_t)world * b;
+    DevBuf staged(ctx), vals(ctx), dpk(ctx), dps(ctx), dsk(ctx), dss(ctx), df(ctx), dx(ctx), dupd(ctx), dlow(ctx), dlg(ctx);
+    IMT_TRY_CUDA(ctx, staged.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, vals.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dpk.alloc(g * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dsk.alloc(g * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dps.alloc(g * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dss.alloc(g * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, df.alloc(g));
+    IMT_TRY_CUDA(ctx, dx.alloc(2 * b * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dupd.alloc(2 * b * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dlow.alloc(b * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dlg.alloc(b));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, values, b * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dpk.p, pred_keys, g * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dsk.p, succ_keys, g * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dps.p, pred_slots, g * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dss.p, succ_slots, g * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(df.p, flags, g, cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_convert(ctx, staged.p, vals.p, b, ctx->fmt, kFmtCanonical));
+    k_ins_plan<<<grid_for(b, 128), 128, 0, ctx->stream>>>(vals.as<uint4>(), b, first_idx, ctx->fmt, world, dpk.as<uint4>(), dps.as<uint64_t>(),
+                                                         dsk.as<uint4>(), dss.as<uint64_t>(), df.as<uint8_t>(), dx.as<uint64_t>(), dupd.as<uint4>(),
+                                                         dlow.as<uint4>(), dlg.as<uint8_t>(), ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(x, dx.p, 2 * b * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(upd, dupd.p, 2 * b * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_old, dlow.p, b * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dlg.p, b, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_shard_insert_apply(imt_tree* t, const uint64_t* x, const void* upd, size_t b, void* sub_roots, void* sib_local) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (b && (!x || !upd || !sub_roots || !sib_local)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (b > kInsertChunk) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    IMT_TRY(ensure_index(t));
+    const unsigned depth = t->depth;
+    const size_t writes_all = 2 * b;
+    std::memset(sub_roots, 0, writes_all * sizeof(Fr));
+    if (depth) std::memset(sib_local, 0, writes_all * depth * sizeof(Fr));
+    // ---- this rank's writes, in time order
+    const uint64_t base = (uint64_t)t->rank * t->n;
+    std::vector<uint64_t> xl;
+    std::vector<uint32_t> src;
+    for (size_t w = 0; w < writes_all; ++w) {
+        if (x[w] >= base && x[w] - base < t->n) xl.push_back(x[w] - base), src.push_back((uint32_t)w);
+    }
+    const unsigned writes = (unsigned)xl.size();
+    if (writes == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<Fr> own_upd((size_t)writes * 3), new_keys;
+    std::vector<uint32_t> new_slots;
+    const Fr* upd_fe = static_cast<const Fr*>(upd);
+    for (unsigned i = 0; i < writes; ++i) {
+        for (int k = 0; k < 3; ++k) own_upd[3 * (size_t)i + k] = upd_fe[3 * (size_t)src[i] + k];
+        if (src[i] & 1) new_keys.push_back(upd_fe[3 * (size_t)src[i]]), new_slots.push_back((uint32_t)xl[i]);  // odd writes are the new leaves
+    }
+    const size_t L = depth + 1;
+    DevBuf dx(ctx), dupd(ctx), prev(ctx), last(ctx), ver(ctx), pairs(ctx), sib(ctx), top(ctx);
+    IMT_TRY_CUDA(ctx, dx.alloc(writes * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dupd.alloc((size_t)writes * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, prev.alloc(writes * L * sizeof(int)));
+    IMT_TRY_CUDA(ctx, last.alloc(writes * L));
+    IMT_TRY_CUDA(ctx, ver.alloc(L * writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, pairs.alloc(2 * (size_t)writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, sib.alloc((size_t)writes * depth * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, top.alloc(writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dx.p, xl.data(), writes * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dupd.p, own_upd.data(), (size_t)writes * 3 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_hash(ctx, 3, dupd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
+    IMT_TRY(versioned_levels(ctx, t->d_levels, t->n, depth, dx.as<uint64_t>(), writes, ver.as<Fr>(), prev.as<int>(), last.as<uint8_t>(),
+                             pairs.as<Fr>(), nullptr, nullptr, sib.as<uint4>()));
+    k_export_versions<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(ver.as<uint4>() + 2 * ((size_t)depth * writes), writes, ctx->fmt, top.as<uint4>());
+    k_ins_commit<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), dupd.as<uint4>(), dx.as<uint64_t>(), last.as<uint8_t>(),
+                                                                            writes, depth, t->n, (uint4*)t->d_levels, (uint4*)t->d_pre);
+    ctx->launches += 2;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    std::vector<Fr> h_top(writes), h_sib((size_t)writes * depth);
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h_top.data(), top.p, writes * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h_sib.data(), sib.p, (size_t)writes * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY(finish(ctx));
+    Fr* out_roots = static_cast<Fr*>(sub_roots);
+    Fr* out_sib = static_cast<Fr*>(sib_local);
+    for (unsigned i = 0; i < writes; ++i) {
+        out_roots[src[i]] = h_top[i];
+        for (unsigned l = 0; l < depth; ++l) out_sib[(size_t)src[i] * depth + l] = h_sib[(size_t)i * depth + l];
+    }
+    // ---- the new leaves of this rank join its sorted index
+    const size_t nk = new_keys.size();
+    if (nk) {
+        DevBuf staged(ctx), keys(ctx), slots(ctx);
+        IMT_TRY_CUDA(ctx, staged.alloc(nk * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, keys.alloc(nk * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, slots.alloc(nk * sizeof(uint32_t)));
+        if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
+        if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, new_keys.data(), nk * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(slots.p, new_slots.data(), nk * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        IMT_TRY(launch_convert(ctx, staged.p, keys.p, nk, ctx->fmt, kFmtCanonical));
+        IMT_TRY(sort_pairs(ctx, keys.as<Fr>(), slots.as<uint32_t>(), nk));
+        k_merge_rank<<<grid_for(t->occupied + nk, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
+                                                                              keys.as<uint4>(), slots.as<uint32_t>(), nk, (uint4*)t->d_alt_keys,
+                                                                              t->d_alt_slots);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::swap(t->d_sorted_keys, t->d_alt_keys);
+        std::swap(t->d_sorted_slots, t->d_alt_slots);
+        t->occupied += nk;
+    }
+    if (t->rank == 0) t->head_next_zero = false;
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_shard_insert_cap(imt_tree* t, const uint64_t* x, const void* sub_roots, size_t b, void* roots, void* sib_cap) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (b && (!x || !sub_roots || !roots)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (b > kInsertChunk) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (!t->cap_valid) return fail(ctx, IMT_ERR_INVALID_ARG, "no cap attached: exchange the subtree roots first");
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned writes = (unsigned)(2 * b), depth = t->cap_depth;
+    const size_t L = depth + 1;
+    std::vector<uint64_t> owner(writes);
+    for (unsigned w = 0; w < writes; ++w) {
+        owner[w] = x[w] / t->n;
+        if (owner[w] >= t->world) return fail(ctx, IMT_ERR_INDEX_OOB, "index out of bounds");
+    }
+    DevBuf dx(ctx), staged(ctx), prev(ctx), last(ctx), ver(ctx), pairs(ctx), sib(ctx), top(ctx);
+    IMT_TRY_CUDA(ctx, dx.alloc(writes * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, staged.alloc(writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, prev.alloc(writes * L * sizeof(int)));
+    IMT_TRY_CUDA(ctx, last.alloc(writes * L));
+    IMT_TRY_CUDA(ctx, ver.alloc(L * writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, pairs.alloc(2 * (size_t)writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, sib.alloc((size_t)writes * (depth ? depth : 1) * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, top.alloc(writes * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dx.p, owner.data(), writes * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, sub_roots, writes * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_convert(ctx, staged.p, ver.p, writes, ctx->fmt, kFmtMontgomery));  // version 0 of write t: its subtree's root after it
+    IMT_TRY(versioned_levels(ctx, t->d_cap, t->world, depth, dx.as<uint64_t>(), writes, ver.as<Fr>(), prev.as<int>(), last.as<uint8_t>(),
+                             pairs.as<Fr>(), nullptr, nullptr, sib_cap ? sib.as<uint4>() : nullptr));
+    k_export_versions<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(ver.as<uint4>() + 2 * ((size_t)depth * writes), writes, ctx->fmt, top.as<uint4>());
+    k_ins_commit<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), nullptr, dx.as<uint64_t>(), last.as<uint8_t>(), writes,
+                                                                            depth, t->world, (uint4*)t->d_cap, nullptr);
+    ctx->launches += 2;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(roots, top.p, writes * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sib_cap && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(sib_cap, sib.p, (size_t)writes * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }

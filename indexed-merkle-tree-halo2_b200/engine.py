@@ -248,6 +248,22 @@ class Engine:
                     new_leaf=t_new, new_path=t_new_path, old_root=r_old, interim_root=r_int, zero_leaf_root=r_zero, new_root=r_new,
                     new_low_leaf_preimage=new_low)
 
+    def shard_insert_plan(self, values, first_idx, pred_keys, pred_slots, succ_keys, succ_slots, flags):
+        """replicated plan of a sharded insert chunk from the gathered [world][b] neighbour arrays"""
+        v = _fe_array(values, ())
+        b = v.shape[0]
+        pk = np.ascontiguousarray(pred_keys, dtype=np.uint64).reshape(-1, b, 4)
+        world = pk.shape[0]
+        sk = np.ascontiguousarray(succ_keys, dtype=np.uint64).reshape(world, b, 4)
+        ps = np.ascontiguousarray(pred_slots, dtype=np.uint64).reshape(world, b)
+        ss = np.ascontiguousarray(succ_slots, dtype=np.uint64).reshape(world, b)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8).reshape(world, b)
+        x, upd = np.empty(2 * b, np.uint64), np.empty((2 * b, 3, 4), np.uint64)
+        low_old, largest = np.empty((b, 3, 4), np.uint64), np.empty(b, np.uint8)
+        self._check(self._lib.imt_shard_insert_plan(self._h, _ptr(v), b, int(first_idx), world, _ptr(pk), _ptr(ps), _ptr(sk), _ptr(ss), _ptr(fl),
+                                                    _ptr(x), _ptr(upd), _ptr(low_old), _ptr(largest)))
+        return x, upd, low_old, largest
+
     def low_leaf_merge(self, values, cand_keys, cand_slots, flags, occupied_total, n_total, head_next_zero):
         """replicated half of a sharded lookup: [world][q] gathered candidates -> (low_idx, matched)"""
         v = _fe_array(values, ())
@@ -407,6 +423,30 @@ class Tree:
         keys, slots, flags = np.empty((q, 4), np.uint64), np.empty(q, np.uint64), np.empty(q, np.uint8)
         self.engine._check(self._lib.imt_low_leaf_candidates(self._h, _ptr(v), q, _ptr(keys), _ptr(slots), _ptr(flags)))
         return keys, slots, flags
+
+    def shard_insert_neighbors(self, values):
+        v = _fe_array(values, ())
+        b = v.shape[0]
+        pk, sk = np.empty((b, 4), np.uint64), np.empty((b, 4), np.uint64)
+        ps, ss, fl = np.empty(b, np.uint64), np.empty(b, np.uint64), np.empty(b, np.uint8)
+        self.engine._check(self._lib.imt_shard_insert_neighbors(self._h, _ptr(v), b, _ptr(pk), _ptr(ps), _ptr(sk), _ptr(ss), _ptr(fl)))
+        return pk, ps, sk, ss, fl
+
+    def shard_insert_apply(self, x, upd, local_depth):
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        u = _fe_array(upd, (3,))
+        b = x.shape[0] // 2
+        sub_roots, sib = np.empty((2 * b, 4), np.uint64), np.empty((2 * b, local_depth, 4), np.uint64)
+        self.engine._check(self._lib.imt_shard_insert_apply(self._h, _ptr(x), _ptr(u), b, _ptr(sub_roots), _ptr(sib)))
+        return sub_roots, sib
+
+    def shard_insert_cap(self, x, sub_roots, cap_depth):
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        r = _fe_array(sub_roots, ())
+        b = x.shape[0] // 2
+        roots, sib = np.empty((2 * b, 4), np.uint64), np.empty((2 * b, cap_depth, 4), np.uint64)
+        self.engine._check(self._lib.imt_shard_insert_cap(self._h, _ptr(x), _ptr(r), b, _ptr(roots), _ptr(sib)))
+        return roots, sib
 
     def leaves(self, indices):
         idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)

@@ -141,6 +141,48 @@ class ShardedTree:
         sib, hel = self.get_proofs(low)
         return dict(low_idx=low, matched=matched, low_leaves=leaves, siblings=sib, helpers=hel, is_largest=largest)
 
+    def insert_batch(self, new_vals, chunk=4096):
+        """imt_insert_batch over the sharded tree (IMT:710-741 with O(depth) hashes per insert): every rank passes the same
+        values; the witnesses (same dict as Tree.insert_batch) come back replicated. Per chunk: neighbours from every
+        rank's index -> all-gather -> replicated plan -> every rank applies its own writes to its subtree -> all-gather
+        of the subtree-root versions and local paths -> every rank applies all writes to the replicated cap."""
+        v = np.ascontiguousarray(new_vals, dtype=np.uint64).reshape(-1, 4)
+        b_total, d = v.shape[0], self.depth
+        d_local = self.n_local.bit_length() - 1
+        d_cap = d - d_local
+        keys = ("old_roots", "low_idx", "low_leaves", "low_siblings", "low_helpers", "new_roots", "new_leaves", "new_siblings", "new_helpers",
+                "is_largest")
+        parts = {k: [] for k in keys}
+        occupied = int(self._all_gather(np.array([self.tree.occupied], np.uint64)).sum())
+        for off in range(0, b_total, chunk):
+            vals = v[off:off + chunk]
+            b = vals.shape[0]
+            if occupied + b > self.num_leaves:
+                raise ValueError("not enough empty slots")
+            root_before = self.root()
+            gathered = [self._all_gather(a) for a in self.tree.shard_insert_neighbors(vals)]
+            x, upd, low_old, largest = self.engine.shard_insert_plan(vals, occupied, *gathered)
+            sub_roots, sib_local = self.tree.shard_insert_apply(x, upd, d_local)
+            own = self.owner(x)
+            t = np.arange(2 * b)
+            sub_roots = self._all_gather(sub_roots)[own, t]
+            sib_local = self._all_gather(sib_local)[own, t] if d_local else np.zeros((2 * b, 0, 4), np.uint64)
+            roots, sib_cap = self.tree.shard_insert_cap(x, sub_roots, d_cap)
+            sib = np.concatenate([sib_local, sib_cap], axis=1)
+            helpers = (((x[:, None] >> np.arange(d, dtype=np.uint64)[None, :]) & np.uint64(1)) == 0).astype(np.uint8)
+            parts["old_roots"].append(np.concatenate([root_before[None, :], roots[1:-1:2]]))
+            parts["new_roots"].append(roots[1::2])
+            parts["low_idx"].append(x[0::2])
+            parts["low_leaves"].append(low_old)
+            parts["new_leaves"].append(upd[1::2])
+            parts["low_siblings"].append(sib[0::2])
+            parts["new_siblings"].append(sib[1::2])
+            parts["low_helpers"].append(helpers[0::2])
+            parts["new_helpers"].append(helpers[1::2])
+            parts["is_largest"].append(largest)
+            occupied += b
+        return {k: np.concatenate(p) if p else None for k, p in parts.items()}
+
     def query_slice(self, q):
         """by-query sharding of pure-compute batches (path folds, witness traces): this rank's slice of q queries"""
         per = -(-q // self.world)

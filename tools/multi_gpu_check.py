@@ -47,6 +47,13 @@ def main():
     leaf_hashes = eng.hash3(pre[idx.astype(np.int64)])
     sl, roots, states = st.trace_merkle_proofs(leaf_hashes, idx, sib)
     assert (roots == st.root()).all() and states.shape[1:] == (depth, 132, 3, 4)
+    # sharded insert batch == the single-GPU insert batch of the same tree, field by field
+    vals = synth.field_elements(min(3000, n - occupied), seed=99)
+    got = st.insert_batch(vals, chunk=1024)
+    want = whole.insert_batch(vals)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), f"sharded insert: {k}"
+    assert np.array_equal(st.root(), whole.root())
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU check ok: world={world} depth={depth} root={imt_b200.fe_to_int(st.root()):#x}", flush=True)
