@@ -10,7 +10,7 @@ import oracle as O
 
 class OracleTree:
     def __init__(self, pre):
-        self.pre = np.ascontiguousarray(pre, dtype=np.uint64).reshape(-1, 3, 4)
+        self.pre = np.array(pre, dtype=np.uint64).reshape(-1, 3, 4)  # a private copy: the insert steps update it in place
         self.n = self.pre.shape[0]
         self.local_depth = self.n.bit_length() - 1
         self.rank, self.world, self.cap = 0, 1, None
@@ -20,7 +20,7 @@ class OracleTree:
         self.tree = O.tree_build(O.hash3(self.pre, 4), 4)
 
     def rebuild_from_leaves(self, pre):
-        self.pre = np.ascontiguousarray(pre, dtype=np.uint64).reshape(-1, 3, 4)
+        self.pre = np.array(pre, dtype=np.uint64).reshape(-1, 3, 4)
         self.cap = None
         self._build()
 
@@ -87,8 +87,89 @@ class OracleTree:
         return keys, slots, flags
 
 
+    # ---- sharded inserts (the four per-chunk steps of include/imt_b200.h, restated with the oracle)
+    def shard_insert_neighbors(self, values):
+        v = O.to_ints(values)
+        ks = self._sorted()
+        only = [k for k, _ in ks]
+        b = len(v)
+        pk, sk = np.zeros((b, 4), np.uint64), np.zeros((b, 4), np.uint64)
+        ps, ss, fl = np.zeros(b, np.uint64), np.zeros(b, np.uint64), np.zeros(b, np.uint8)
+        for i, x in enumerate(v):
+            j = bisect.bisect_left(only, x)
+            js = j
+            if j < len(only) and only[j] == x:
+                fl[i] |= 2
+                js = j + 1
+            if j >= 1:
+                pk[i], ps[i] = O.fe(ks[j - 1][0]), ks[j - 1][1]
+                fl[i] |= 1
+            if js < len(only):
+                sk[i], ss[i] = O.fe(ks[js][0]), ks[js][1]
+                fl[i] |= 4
+        return pk, ps, sk, ss, fl
+
+    def _rehash(self):
+        self.tree = O.tree_build(O.hash3(self.pre, 2), 2)
+
+    def shard_insert_apply(self, x, upd, local_depth):
+        x = np.asarray(x, dtype=np.uint64)
+        base = self.rank * self.n
+        sub_roots = np.zeros((len(x), 4), np.uint64)
+        sib = np.zeros((len(x), local_depth, 4), np.uint64)
+        for t, g in enumerate(x):
+            local = int(g) - base
+            if 0 <= local < self.n:
+                s, _ = O.get_proof(self.tree, self.n, local)       # the path of a leaf does not depend on the leaf itself
+                sib[t] = s
+                self.pre[local] = upd[t]
+                self._rehash()                                     # the reference's own way: re-hash and rebuild (tiny trees only)
+                sub_roots[t] = self.tree[-1]
+        return sub_roots, sib
+
+    def shard_insert_cap(self, x, sub_roots, cap_depth):
+        x = np.asarray(x, dtype=np.uint64)
+        leaves = np.array(O.levels(self.cap, self.world)[0]) if self.world > 1 else np.array([self.tree[-1]])
+        roots = np.zeros((len(x), 4), np.uint64)
+        sib = np.zeros((len(x), cap_depth, 4), np.uint64)
+        for t, g in enumerate(x):
+            owner = int(g) // self.n
+            if self.world > 1:
+                s, _ = O.get_proof(self.cap, self.world, owner)
+                sib[t] = s
+                leaves[owner] = sub_roots[t]
+                self.cap = O.tree_build(np.ascontiguousarray(leaves), 1)
+                roots[t] = self.cap[-1]
+            else:
+                roots[t] = sub_roots[t]
+        return roots, sib
+
+
 class OracleEngine:
     device = 0
+
+    def shard_insert_plan(self, values, first_idx, pred_keys, pred_slots, succ_keys, succ_slots, flags):
+        v = O.to_ints(values)
+        b = len(v)
+        pk = np.asarray(pred_keys, dtype=np.uint64).reshape(-1, b, 4)
+        sk = np.asarray(succ_keys, dtype=np.uint64).reshape(-1, b, 4)
+        ps, ss, fl = (np.asarray(a).reshape(-1, b) for a in (pred_slots, succ_slots, flags))
+        x, upd = np.zeros(2 * b, np.uint64), np.zeros((2 * b, 3, 4), np.uint64)
+        low_old, largest = np.zeros((b, 3, 4), np.uint64), np.zeros(b, np.uint8)
+        for k in range(b):
+            preds = [(O.to_int(pk[r, k]), int(ps[r, k])) for r in range(pk.shape[0]) if fl[r, k] & 1]
+            succs = [(O.to_int(sk[r, k]), int(ss[r, k])) for r in range(pk.shape[0]) if fl[r, k] & 4]
+            preds += [(v[i], first_idx + i) for i in range(k) if v[i] < v[k]]
+            succs += [(v[i], first_idx + i) for i in range(k) if v[i] > v[k]]
+            if v[k] == 0 or any(fl[r, k] & 2 for r in range(pk.shape[0])) or v[k] in v[:k] or not preds:
+                raise ValueError("bad insert")
+            p, s = max(preds), (min(succs) if succs else (0, 0))
+            x[2 * k], x[2 * k + 1] = p[1], first_idx + k
+            low_old[k] = O.fes([p[0], s[0], s[1]])
+            upd[2 * k] = O.fes([p[0], v[k], first_idx + k])
+            upd[2 * k + 1] = O.fes([v[k], s[0], s[1]])
+            largest[k] = 0 if succs else 1
+        return x, upd, low_old, largest
 
     def build_from_leaves(self, pre):
         return OracleTree(pre)

@@ -61,13 +61,13 @@ def _worker(rank, world, port, depth, occupied, use_gpu, errors):
         leaf_hashes = O.hash3(pre[idx.astype(np.int64)], 4)
         sl, roots, _ = st.trace_merkle_proofs(leaf_hashes, idx, sib, want_states=False)
         assert (roots == whole[-1]).all() and sl == st.query_slice(len(idx))
-        if use_gpu:
-            # sharded insert batch (real engine only): against the oracle advancing the WHOLE tree one insert at a time
+        if True:
+            # sharded insert batch: against the oracle advancing the WHOLE tree one insert at a time
             free = n - occupied
-            b = min(free - 2, 70)
+            b = min(free - 2, 70 if use_gpu else 12)
             if b > 0:
                 ins_vals = synth.field_elements(b, seed=depth * 7 + world)
-                got = st.insert_batch(ins_vals, chunk=32)                  # several chunks, new slots crossing rank boundaries
+                got = st.insert_batch(ins_vals, chunk=32 if use_gpu else 5)                  # several chunks, new slots crossing rank boundaries
                 ost = O.InsertState(pre, threads=2)
                 names = [("old_roots", "old_root"), ("low_idx", "low_idx"), ("low_leaves", "low_leaf"), ("low_siblings", "low_proof"),
                          ("low_helpers", "low_helper"), ("new_roots", "new_root"), ("new_leaves", "new_leaf"), ("new_siblings", "new_proof"),
@@ -75,9 +75,10 @@ def _worker(rank, world, port, depth, occupied, use_gpu, errors):
                 for k in range(b):
                     want = ost.insert(ins_vals[k], occupied + k, incremental=True)
                     for g, w in names:
-                        assert np.array_equal(np.asarray(got[g][k]), np.asarray(want[w])), f"sharded insert {k}: {g}"
+                        assert np.array_equal(np.asarray(got[g][k]), np.asarray(want[w])), f"sharded insert {k}: {g} got {np.asarray(got[g][k]).tolist()} want {np.asarray(want[w]).tolist()}"
                 assert np.array_equal(st.root(), ost.root())
-                assert np.array_equal(st.tree.preimages(per), ost.pre[rank * per:(rank + 1) * per])
+                got_pre = st.tree.preimages(per) if use_gpu else st.tree.pre
+                assert np.array_equal(got_pre, ost.pre[rank * per:(rank + 1) * per])
                 qs2 = O.fes([rng.randrange(imt_b200.P) for _ in range(30)])
                 lo2, ma2 = st.low_leaf_lookup(qs2)                        # the per-rank indexes absorbed the new keys
                 for k in range(30):
@@ -86,7 +87,7 @@ def _worker(rank, world, port, depth, occupied, use_gpu, errors):
                 for k, i in enumerate(idx):
                     s2, h2 = O.get_proof(ost.tree, n, int(i))
                     assert np.array_equal(sib2[k], s2)
-                with pytest.raises(imt_b200.ImtError):
+                with pytest.raises(imt_b200.ImtError if use_gpu else ValueError):
                     st.insert_batch(ins_vals[:1])                          # already present
         # a rebuild makes the cap stale until the roots are exchanged again
         pre2 = synth.indexed_preimages(n, max(1, occupied // 2), seed=99)
