@@ -462,6 +462,20 @@ def main():
     # ---- e2e: the reference-facing call with HOST buffers (H2D of the leaves + D2H of the root inside the timed region)
     ms_e2e, _ = timed(step_e2e, a.steps, a.warmup)
     e2e = hashes_per_step * a.steps / (ms_e2e * 1e-3)
+    # the same call the reference's `IndexedMerkleTree::new` maps to: allocate, build, read the root, destroy — every step
+    def step_e2e_alloc():
+        t2 = eng.build_from_leaves_ptr(h_pre.data_ptr(), n)
+        if world == 1:
+            t2.root_dev(send)
+            h_root.copy_(send, non_blocking=True)
+            stream.synchronize()
+        t2.close()
+    ms_e2e_alloc = None
+    if world == 1:
+        t0 = time.perf_counter()
+        for _ in range(2):
+            step_e2e_alloc()
+        ms_e2e_alloc = (time.perf_counter() - t0) / 2 * 1e3
     root_hex = "".join(f"{int(x) & 0xFFFFFFFFFFFFFFFF:016x}" for x in reversed(h_root.tolist()))
 
     # ---- roofline of the dominant kernel (leaf hashing: half of all hashes in one launch)
@@ -503,7 +517,9 @@ def main():
                    "l2_policy": f"inputs larger than L2 ({n * 96 / 2**20:.0f} MiB of leaves per GPU per step)", "seed": synth.DEFAULT_SEED,
                    "fe_format": "montgomery"},
         "e2e": {"value": e2e, "unit": "hashes/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n_total * 96,
-                "d2h_bytes_per_step": 32 * world},
+                "d2h_bytes_per_step": 32 * world, "call": "imt_tree_rebuild_from_leaves (host leaves -> existing tree) + root read back",
+                "ms_per_step_with_alloc": ms_e2e_alloc,
+                "with_alloc_note": "wall clock of imt_tree_build_from_leaves + root + imt_tree_destroy (2.5 GiB cudaMalloc/cudaFree per step), N=1 only"},
         "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex,
     }
     if rank == 0 and not a.no_cpu_baseline:

@@ -161,6 +161,10 @@ class Engine:
         a = _fe_array(preimages, (3,))
         return self._tree(self._lib.imt_tree_build_from_leaves, _ptr(a), a.shape[0])
 
+    def build_from_leaves_ptr(self, host_ptr, n):
+        """host pointer (e.g. a pinned torch tensor's data_ptr()) to n x 3 FE"""
+        return self._tree(self._lib.imt_tree_build_from_leaves, ctypes.c_void_p(host_ptr), n)
+
     def build_from_leaves_dev(self, d_preimages, n):
         return self._tree(self._lib.imt_tree_build_from_leaves_dev, _dev_ptr(d_preimages), n)
 
