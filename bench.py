@@ -519,7 +519,7 @@ def main():
         "e2e": {"value": e2e, "unit": "hashes/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n_total * 96,
                 "d2h_bytes_per_step": 32 * world, "call": "imt_tree_rebuild_from_leaves (host leaves -> existing tree) + root read back",
                 "ms_per_step_with_alloc": ms_e2e_alloc,
-                "with_alloc_note": "wall clock of imt_tree_build_from_leaves + root + imt_tree_destroy (2.5 GiB cudaMalloc/cudaFree per step), N=1 only"},
+                "with_alloc_note": "wall clock of imt_tree_build_from_leaves + root + imt_tree_destroy per step (2.5 GiB of tree buffers recycled through the stream-ordered pool), N=1 only"},
         "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex,
     }
     if rank == 0 and not a.no_cpu_baseline:

@@ -120,9 +120,9 @@ imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
     t->n = n;
     t->depth = 0;
     while (((size_t)1 << t->depth) < n) ++t->depth;
-    cudaError_t e = cudaMalloc((void**)&t->d_levels, (2 * n - 1) * sizeof(Fr));
+    cudaError_t e = tree_malloc(ctx, (void**)&t->d_levels, (2 * n - 1) * sizeof(Fr));
     if (e == cudaSuccess && with_pre) {
-        e = cudaMalloc((void**)&t->d_pre, 3 * n * sizeof(Fr));
+        e = tree_malloc(ctx, (void**)&t->d_pre, 3 * n * sizeof(Fr));
         t->owns_pre = true;
     }
     if (e != cudaSuccess) {
@@ -488,14 +488,15 @@ extern "C" imt_status imt_tree_rebuild_from_leaves_dev(imt_tree* t, const void* 
 
 extern "C" void imt_tree_destroy(imt_tree* t) {
     if (!t) return;
-    if (t->ctx) cudaSetDevice(t->ctx->device);
-    if (t->d_levels) cudaFree(t->d_levels);
-    if (t->d_pre && t->owns_pre) cudaFree(t->d_pre);
-    if (t->d_cap) cudaFree(t->d_cap);
-    if (t->d_sorted_keys) cudaFree(t->d_sorted_keys);
-    if (t->d_sorted_slots) cudaFree(t->d_sorted_slots);
-    if (t->d_alt_keys) cudaFree(t->d_alt_keys);
-    if (t->d_alt_slots) cudaFree(t->d_alt_slots);
+    imt_ctx* ctx = t->ctx;  // a tree never outlives its context
+    cudaSetDevice(ctx->device);
+    if (t->d_levels) tree_free(ctx, t->d_levels);
+    if (t->d_pre && t->owns_pre) tree_free(ctx, t->d_pre);
+    if (t->d_cap) tree_free(ctx, t->d_cap);
+    if (t->d_sorted_keys) tree_free(ctx, t->d_sorted_keys);
+    if (t->d_sorted_slots) tree_free(ctx, t->d_sorted_slots);
+    if (t->d_alt_keys) tree_free(ctx, t->d_alt_keys);
+    if (t->d_alt_slots) tree_free(ctx, t->d_alt_slots);
     delete t;
 }
 
@@ -715,8 +716,8 @@ static imt_status attach_cap(imt_tree* t, unsigned rank, unsigned world, const v
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     t->cap_valid = false;
     if (t->cap_alloc_world != world) {
-        if (t->d_cap) cudaFree(t->d_cap), t->d_cap = nullptr;
-        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_cap, (2 * (size_t)world - 1) * sizeof(Fr)));
+        if (t->d_cap) tree_free(ctx, t->d_cap), t->d_cap = nullptr;
+        IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_cap, (2 * (size_t)world - 1) * sizeof(Fr)));
         t->cap_alloc_world = world;
     }
     if (t->rank != rank || t->world != world) invalidate_index(t);  // slot numbers of the index are global

@@ -602,13 +602,13 @@ imt_status ensure_index(imt_tree* t) {
     if (t->n > 0xffffffffull) return fail(ctx, IMT_ERR_INVALID_ARG, "index supports at most 2^32 slots");
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!t->d_sorted_keys || t->index_capacity < t->n) {
-        if (t->d_sorted_keys) cudaFree(t->d_sorted_keys), t->d_sorted_keys = nullptr;
-        if (t->d_sorted_slots) cudaFree(t->d_sorted_slots), t->d_sorted_slots = nullptr;
-        if (t->d_alt_keys) cudaFree(t->d_alt_keys), t->d_alt_keys = nullptr;
-        if (t->d_alt_slots) cudaFree(t->d_alt_slots), t->d_alt_slots = nullptr;
+        if (t->d_sorted_keys) tree_free(ctx, t->d_sorted_keys), t->d_sorted_keys = nullptr;
+        if (t->d_sorted_slots) tree_free(ctx, t->d_sorted_slots), t->d_sorted_slots = nullptr;
+        if (t->d_alt_keys) tree_free(ctx, t->d_alt_keys), t->d_alt_keys = nullptr;
+        if (t->d_alt_slots) tree_free(ctx, t->d_alt_slots), t->d_alt_slots = nullptr;
         t->index_capacity = 0;
-        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_keys, t->n * sizeof(Fr)));
-        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_sorted_slots, t->n * sizeof(uint32_t)));
+        IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_sorted_keys, t->n * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_sorted_slots, t->n * sizeof(uint32_t)));
         t->index_capacity = t->n;
     }
     DevBuf stats(ctx);  // [0] first empty, [1] last occupied, then the head flag
@@ -816,8 +816,8 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     if (out.low_idx) IMT_TRY_CUDA(ctx, low_idx.alloc(C * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, chunk_keys.alloc(C * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, chunk_slots.alloc(C * sizeof(uint32_t)));
-    if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
-    if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
+    if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
+    if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
 
     lap("alloc");
     for (size_t off = 0; off < b; off += C) {
@@ -1144,8 +1144,8 @@ extern "C" imt_status imt_shard_insert_apply(imt_tree* t, const uint64_t* x, con
         IMT_TRY_CUDA(ctx, staged.alloc(nk * sizeof(Fr)));
         IMT_TRY_CUDA(ctx, keys.alloc(nk * sizeof(Fr)));
         IMT_TRY_CUDA(ctx, slots.alloc(nk * sizeof(uint32_t)));
-        if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
-        if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, cudaMalloc((void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
+        if (!t->d_alt_keys) IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_alt_keys, t->index_capacity * sizeof(Fr)));
+        if (!t->d_alt_slots) IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_alt_slots, t->index_capacity * sizeof(uint32_t)));
         IMT_TRY_CUDA(ctx, cudaMemcpyAsync(staged.p, new_keys.data(), nk * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
         IMT_TRY_CUDA(ctx, cudaMemcpyAsync(slots.p, new_slots.data(), nk * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         IMT_TRY(launch_convert(ctx, staged.p, keys.p, nk, ctx->fmt, kFmtCanonical));

@@ -118,6 +118,18 @@ struct DevBuf {
     T* as() { return static_cast<T*>(p); }
 };
 
+// The long-lived buffers of a tree (levels, preimages, cap, sorted index) come from the same pool: a caller that maps
+// the reference's `IndexedMerkleTree::new` to build + destroy per call recycles memory instead of paying cudaMalloc /
+// cudaFree of 2.5 GiB (133 ms per depth-24 tree, measured).
+inline cudaError_t tree_malloc(imt_ctx* ctx, void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // usable from the copy stream right away
+    return e;
+}
+inline void tree_free(imt_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 // ---- implemented in imt_capi.cu
 imt_status clear_err(imt_ctx* ctx);
 // waits for the compute stream and turns the device error bits into a status
