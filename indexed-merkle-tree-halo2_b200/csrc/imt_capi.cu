@@ -62,7 +62,9 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
     return IMT_OK;
 }
 
-// threshold of the cooperative kernel; IMT_COOP_MAX_NODES overrides it (tuning / A-B measurements only)
+// Batches (tree levels, insert levels, API calls) with at most this many hashes cannot fill the GPU with one thread per
+// hash and cost one full hash latency each: they go to the 3-lanes-per-hash kernels (poseidon_coop.cuh), which trade
+// lanes for latency. IMT_COOP_MAX_NODES overrides the threshold (tuning / A-B measurements only).
 constexpr size_t kCoopMaxNodesDefault = 8192;
 size_t coop_max_nodes();
 
@@ -96,9 +98,6 @@ size_t coop_max_nodes() {
     }();
     return v;
 }
-
-// Levels with at most this many nodes cannot fill the GPU with one thread per hash and cost one full hash latency each:
-// they go to the 3-lanes-per-hash kernel (poseidon_coop.cuh), which trades lanes for latency.
 
 // one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
 imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
