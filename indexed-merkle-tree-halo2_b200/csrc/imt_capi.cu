@@ -138,17 +138,15 @@ imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
     imt_ctx* ctx = t->ctx;
     const size_t chunk = (size_t)1 << 19;  // 512 Ki leaves = 48 MiB per copy
     const char* src = static_cast<const char*>(preimages);
-    std::vector<cudaEvent_t> evs;
+    Event copied;  // re-recorded per chunk: cudaStreamWaitEvent captures the record that precedes it
+    IMT_TRY_CUDA(ctx, copied.create());
     imt_status st = IMT_OK;
     for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk) {
         const size_t cnt = (t->n - off < chunk) ? t->n - off : chunk;
-        cudaEvent_t ev;
-        IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        evs.push_back(ev);
         cudaError_t e = cudaMemcpyAsync(t->d_pre + 3 * off, src + 3 * off * sizeof(Fr), 3 * cnt * sizeof(Fr),
                                         cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(copied, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, copied, 0);
         if (e != cudaSuccess) {
             ctx->last_error = std::string("leaf staging: ") + cudaGetErrorString(e);
             st = IMT_ERR_CUDA;
@@ -156,11 +154,8 @@ imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
         }
         st = launch_hash_t<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, ctx->stream);
     }
+    cudaStreamSynchronize(ctx->copy_stream);  // the caller's buffer is free again when this returns
     if (st != IMT_OK) cudaStreamSynchronize(ctx->stream);
-    for (cudaEvent_t ev : evs) {
-        if (st == IMT_OK) cudaEventSynchronize(ev);
-        cudaEventDestroy(ev);
-    }
     return st;
 }
 
@@ -644,10 +639,10 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
         IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
         if (q > chunk) IMT_TRY_CUDA(ctx, buf1.alloc(chunk * per_query));
         void* bufs[2] = {buf0.p, buf1.p};
-        cudaEvent_t folded[2], drained[2];
+        Event folded[2], drained[2];
         for (int i = 0; i < 2; ++i) {
-            IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&folded[i], cudaEventDisableTiming));
-            IMT_TRY_CUDA(ctx, cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+            IMT_TRY_CUDA(ctx, folded[i].create());
+            IMT_TRY_CUDA(ctx, drained[i].create());
         }
         IMT_TRY(clear_err(ctx));
         cudaError_t e = cudaSuccess;
@@ -669,7 +664,6 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);
-        for (int i = 0; i < 2; ++i) cudaEventDestroy(folded[i]), cudaEventDestroy(drained[i]);
         if (e != cudaSuccess) {
             ctx->last_error = std::string("trace pipeline: ") + cudaGetErrorString(e);
             return IMT_ERR_CUDA;
@@ -757,9 +751,9 @@ extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_m
     const int blocks = prop.multiProcessorCount * 8, threads = 256;  // 64 resident warps per SM
     DevBuf out(ctx);
     IMT_TRY_CUDA(ctx, out.alloc((size_t)blocks * threads * sizeof(uint64_t)));
-    cudaEvent_t e0, e1;
-    IMT_TRY_CUDA(ctx, cudaEventCreate(&e0));
-    IMT_TRY_CUDA(ctx, cudaEventCreate(&e1));
+    Event e0, e1;
+    IMT_TRY_CUDA(ctx, e0.create(cudaEventDefault));
+    IMT_TRY_CUDA(ctx, e1.create(cudaEventDefault));
     int iters = 2000;
     float t_ms = 0.f, best_ms = 0.f;
     int best_iters = iters;
@@ -777,8 +771,6 @@ extern "C" imt_status imt_calibrate_imad(imt_ctx* ctx, double ms, double* wide_m
             iters = (int)(iters * (t_ms > 0.05 ? (ms / t_ms) * 1.1 : 8.0)) + 1;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (best_ms == 0.f) best_ms = t_ms, best_iters = iters;
     const double macs = (double)blocks * threads * (double)best_iters * 64.0;
     const double rate = macs / (best_ms * 1e-3);

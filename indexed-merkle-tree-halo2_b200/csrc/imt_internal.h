@@ -118,6 +118,19 @@ struct DevBuf {
     T* as() { return static_cast<T*>(p); }
 };
 
+// RAII CUDA event (destroyed on every return path)
+struct Event {
+    cudaEvent_t e = nullptr;
+    Event() = default;
+    Event(const Event&) = delete;
+    Event& operator=(const Event&) = delete;
+    ~Event() {
+        if (e) cudaEventDestroy(e);
+    }
+    cudaError_t create(unsigned flags = cudaEventDisableTiming) { return cudaEventCreateWithFlags(&e, flags); }
+    operator cudaEvent_t() const { return e; }
+};
+
 // The long-lived buffers of a tree (levels, preimages, cap, sorted index) come from the same pool: a caller that maps
 // the reference's `IndexedMerkleTree::new` to build + destroy per call recycles memory instead of paying cudaMalloc /
 // cudaFree of 2.5 GiB (133 ms per depth-24 tree, measured).
