@@ -89,9 +89,40 @@ imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* d_in, size_t n, void
 
 /* Witness trace of `hash_fix_len_array` (src/indexed_merkle_tree.rs:92, 194, 271, 299): for each of the n hashes
  * of `arity` (2 or 3) inputs, the 132 x 3 FE states (per permutation: after the pre-constant add, then after the
- * linear layer of each of the 4 + 57 + 4 rounds) and the digest. states may be NULL. */
+ * linear layer of each of the 4 + 57 + 4 rounds) and the digest. states may be NULL. Other input lengths and
+ * any-width contexts are forwarded to imt_poseidon_trace (state count: imt_trace_fe_per_hash). */
 imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests);
 imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests);
+
+/* ---------------------------------------------------------------- any-width instances ------------------------ */
+/* The reference's tree and chip are generic over the Poseidon instance: `IndexedMerkleTree<'a, F, const T, const RATE>`
+ * (src/utils.rs:5-10, 19), `verify_merkle_proof / verify_non_inclusion / insert_leaf<F, const T, const RATE>`
+ * (src/indexed_merkle_tree.rs:65, 127, 231); its tests instantiate <3, 2> with R_F = 8, R_P = 57 only
+ * (src/indexed_merkle_tree.rs:362-365), which is what imt_ctx_create gives (tuned kernels).
+ * imt_ctx_create_spec replaces `Poseidon::<Fr, T, RATE>::new(r_f, r_p)` for any other instance: t in 2..5,
+ * rate == t - 1, r_f even >= 2, r_f + r_p <= 256. EVERY entry point of this header then hashes with that instance
+ * (tree build, leaf hashing, paths, folds, traces, inserts, sharding cap) on the any-width kernels; a witness trace has
+ * (arity / rate + 1) x (1 + r_f + r_p) states of t FE per hash (imt_trace_fe_per_hash). */
+imt_status imt_ctx_create_spec(int device, imt_fe_format format, unsigned t, unsigned rate, unsigned r_f, unsigned r_p, imt_ctx** out);
+/* The instance of a context (any output pointer may be NULL); generic_kernels = 1 for imt_ctx_create_spec contexts. */
+imt_status imt_ctx_spec(const imt_ctx* ctx, unsigned* t, unsigned* rate, unsigned* r_f, unsigned* r_p, int* generic_kernels);
+/* FE per hash of `arity` inputs in a witness trace of this context (396 = 132 x 3 for <3, 2>(8, 57), arity 2 or 3). */
+imt_status imt_trace_fe_per_hash(const imt_ctx* ctx, size_t arity, size_t* fe);
+/* out[i] = { update(&in[arity*i .. arity*(i+1)]); squeeze_and_reset() } for ANY input length (arity >= 0): full
+ * rate-chunks are absorbed and permuted, the remainder plus the padding element 1 once more (pse-poseidon's sponge,
+ * call sites src/utils.rs:46-47, src/indexed_merkle_tree.rs:374-375). arity / rate + 1 permutations per hash. */
+imt_status imt_poseidon_hash(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* out);
+imt_status imt_poseidon_hash_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_out);
+/* imt_trace_hashes for any input length / instance: states = n x imt_trace_fe_per_hash(arity) FE (may be NULL). */
+imt_status imt_poseidon_trace(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* digests);
+imt_status imt_poseidon_trace_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_digests);
+/* The bare permutation on n states of t FE each, in place semantics (in -> out): what the published Poseidon test
+ * vectors (poseidonperm_x5_254_3 / _5) are stated on. Not used by the tree. */
+imt_status imt_poseidon_permute(imt_ctx* ctx, const void* in_states, size_t n, void* out_states);
+/* Host-only: the parameter array `Poseidon::new` derives for an instance, Montgomery form, in the order
+ * cap(2^64), one, pre[t], full[r_f][t], mds[t][t], pre_sparse[t][t], r_p x { c, row[t], col[t-1] }.
+ * out == NULL just returns the element count. No device is touched. */
+imt_status imt_spec_params_host(unsigned t, unsigned rate, unsigned r_f, unsigned r_p, void* out, size_t capacity_fe, size_t* count_fe);
 
 /* ---------------------------------------------------------------- native tree -------------------------------- */
 /* IndexedMerkleTree::new(hasher, leaves)  (src/utils.rs:20-57): all levels, bottom-up, kept on the device.

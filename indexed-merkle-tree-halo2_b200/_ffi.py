@@ -79,6 +79,16 @@ SIGNATURES = {
     "imt_shard_insert_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_shard_insert_cap": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_tree_leaves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_ctx_create_spec": (c_int, [c_int, c_int, c_uint, c_uint, c_uint, c_uint, ctypes.POINTER(c_void_p)]),
+    "imt_ctx_spec": (c_int, [c_void_p, ctypes.POINTER(c_uint), ctypes.POINTER(c_uint), ctypes.POINTER(c_uint), ctypes.POINTER(c_uint),
+                             ctypes.POINTER(c_int)]),
+    "imt_trace_fe_per_hash": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
+    "imt_poseidon_hash": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "imt_poseidon_hash_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "imt_poseidon_trace": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "imt_poseidon_trace_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "imt_poseidon_permute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "imt_spec_params_host": (c_int, [c_uint, c_uint, c_uint, c_uint, c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
     "imt_calibrate_imad": (c_int, [c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
-SOURCES = ["imt_capi.cu", "imt_indexed.cu", "poseidon_params.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "fr.cuh", "poseidon_params.h"]
+SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "poseidon_params.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
 OBJ_DIR = os.path.join(HERE, "build")
 
 

@@ -71,6 +71,7 @@ size_t coop_max_nodes();
 template <int ARITY>
 imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
     if (n == 0) return IMT_OK;
+    if (ctx->generic) return launch_spec_hash(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, nullptr, s);  // imt_ctx_create_spec
     imt_ctx::Timed tm{nullptr, nullptr, ARITY, n};
     if (ctx->timing) {
         IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.a));
@@ -290,6 +291,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->d_params) cudaFree(ctx->d_params);
+    if (ctx->d_spec) cudaFree(ctx->d_spec);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     delete ctx;
 }
@@ -375,7 +377,8 @@ extern "C" imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* in, size_
 
 extern "C" imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (arity != 2 && arity != 3) return fail(ctx, IMT_ERR_INVALID_ARG, "arity must be 2 or 3");
+    if (arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
+    if (ctx->generic || (arity != 2 && arity != 3)) return imt_poseidon_trace_dev(ctx, d_in, (size_t)arity, n, d_states, d_digests);
     if (n && !d_in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -392,11 +395,12 @@ extern "C" imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int a
 }
 extern "C" imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (arity != 2 && arity != 3) return fail(ctx, IMT_ERR_INVALID_ARG, "arity must be 2 or 3");
+    if (arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
+    if (ctx->generic || (arity != 2 && arity != 3)) return imt_poseidon_trace(ctx, in, (size_t)arity, n, states, digests);
     if (n && !in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
+    const size_t state_fe = trace_fe_per_hash(ctx, (size_t)arity);  // 132 x 3 for this instance
     DevBuf din(ctx), dst(ctx), ddg(ctx);
     IMT_TRY_CUDA(ctx, din.alloc(n * arity * sizeof(Fr)));
     if (states) IMT_TRY_CUDA(ctx, dst.alloc(n * state_fe * sizeof(Fr)));
@@ -579,6 +583,10 @@ extern "C" imt_status imt_tree_get_proofs_fe(imt_tree* t, const uint64_t* indice
 // one fold launch on the compute stream: few paths -> a quad per path (latency), many -> a thread per path (throughput)
 static void launch_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
                         unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states) {
+    if (ctx->generic) {  // any-width instance (its parameters were uploaded by imt_ctx_create_spec)
+        (void)launch_spec_fold(ctx, d_leaves, d_indices, d_roots, d_siblings, q, depth, d_ok, d_roots_out, d_states);
+        return;
+    }
     if (q <= coop_max_nodes()) {
         k_fold_paths_coop<<<grid_for(4 * q, 128), 128, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
                                                                          (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
@@ -613,7 +621,7 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
     if (q && (!leaves || !indices || (depth && !siblings) || (ok && !roots))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (q == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t state_fe = (size_t)IMT_STATES_PER_HASH * 3;
+    const size_t state_fe = trace_fe_per_hash(ctx, 2);  // 132 x 3 FE per hash for <3, 2>(8, 57)
     DevBuf dl(ctx), di(ctx), dr(ctx), ds(ctx), dok(ctx), dro(ctx);
     IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));

@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libimt_b200.so (not part of the C-ABI).
 //   imt_capi.cu     context, batched hashing, tree build, paths, folds, traces, sharding cap, calibration
 //   imt_indexed.cu  sorted-key index, low-leaf lookups, non-inclusion witnesses, batched inserts
+//   imt_spec.cu     any-width Poseidon instances (T = 2..5, run-time r_f / r_p / input length): kernels + entry points
 // All hashing kernels live in imt_capi.cu (one __constant__ copy of the Poseidon parameters); imt_indexed.cu prepares
 // operands and calls them through imt_host::launch_hash / launch_level.
 #pragma once
@@ -12,6 +13,7 @@
 
 #include "imt_b200.h"
 #include "poseidon.cuh"
+#include "poseidon_spec.cuh"
 
 struct imt_ctx {
     int device = 0;
@@ -22,6 +24,12 @@ struct imt_ctx {
     uint32_t* d_err = nullptr;           // device error bits, see kErr*
     uint32_t* h_err = nullptr;           // pinned mirror
     imt::PoseidonParams* d_params = nullptr;  // global-memory copy of the parameters (lane-dependent reads of the cooperative kernel)
+    // The Poseidon instance of this context. imt_ctx_create: <3, 2>(8, 57) on the tuned kernels (generic == false; the
+    // any-width kernels then only serve input lengths other than 2 and 3). imt_ctx_create_spec: every hash of the context
+    // runs on the any-width kernels of imt_spec.cu (generic == true).
+    imt::SpecLayout spec{3, 8, 57};
+    bool generic = false;
+    imt::Fr* d_spec = nullptr;  // SpecLayout-ordered parameter array (derived and uploaded on first use)
     uint64_t launches = 0;
     std::string last_error;
     // optional per-launch device timing of the hash kernels
@@ -159,5 +167,20 @@ imt_status launch_level(imt_ctx* ctx, const imt::Fr* d_src, imt::Fr* d_dst, size
 
 // ---- implemented in imt_indexed.cu
 void invalidate_index(imt_tree* t);
+
+// ---- implemented in imt_spec.cu (any-width instances)
+// permutations of one hash of `arity` inputs, and FE per hash of its witness trace
+inline size_t spec_perms(const imt_ctx* ctx, size_t arity) { return arity / (ctx->spec.t - 1) + 1; }
+inline size_t trace_fe_per_hash(const imt_ctx* ctx, size_t arity) {
+    return spec_perms(ctx, arity) * ctx->spec.states_per_perm() * ctx->spec.t;
+}
+// derives + uploads ctx->d_spec if it is not there yet
+imt_status ensure_spec(imt_ctx* ctx);
+// out[i] = squeeze(update(in[arity*i ..])) with the context's instance; d_states may be null
+imt_status launch_spec_hash(imt_ctx* ctx, size_t arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, void* d_states,
+                            cudaStream_t s);
+// batched verify_proof / compute_merkle_root (+ trace) with the context's instance
+imt_status launch_spec_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
+                            unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);
 
 }  // namespace imt_host

@@ -9,6 +9,8 @@
 #include "poseidon_params.h"
 
 #include <cstring>
+#include <utility>
+#include <vector>
 
 namespace imt {
 namespace {
@@ -249,5 +251,143 @@ void poseidon_params_generate(PoseidonParams* out) {
     const uint32_t cap[8] = {0, 0, 1, 0, 0, 0, 0, 0};  // 2^64
     store(out->cap, from_canonical(cap));
 }
+
+// ------------------------------------------------------------------------------------------------- any width
+// The same derivation for any instance `Poseidon::<Fr, T, RATE>::new(r_f, r_p)` — the reference's tree and chip are
+// generic over T and RATE (/root/reference/src/utils.rs:6, 19; src/indexed_merkle_tree.rs:65, 127, 231) although only
+// <3, 2>(8, 57) is instantiated (indexed_merkle_tree.rs:362-365). Output: one dense Fr array laid out by SpecLayout.
+namespace {
+
+struct Mat {
+    int n;
+    std::vector<F> v;  // row-major
+    explicit Mat(int n_) : n(n_), v((size_t)n_ * n_, kZero) {}
+    F& at(int i, int j) { return v[(size_t)i * n + j]; }
+    const F& at(int i, int j) const { return v[(size_t)i * n + j]; }
+};
+Mat transpose(const Mat& a) {
+    Mat r(a.n);
+    for (int i = 0; i < a.n; ++i)
+        for (int j = 0; j < a.n; ++j) r.at(j, i) = a.at(i, j);
+    return r;
+}
+Mat matmul(const Mat& a, const Mat& b) {
+    Mat r(a.n);
+    for (int i = 0; i < a.n; ++i)
+        for (int j = 0; j < a.n; ++j) {
+            F acc = kZero;
+            for (int k = 0; k < a.n; ++k) acc = add(acc, mul(a.at(i, k), b.at(k, j)));
+            r.at(i, j) = acc;
+        }
+    return r;
+}
+std::vector<F> matvec(const Mat& m, const std::vector<F>& x) {
+    std::vector<F> y((size_t)m.n, kZero);
+    for (int i = 0; i < m.n; ++i)
+        for (int j = 0; j < m.n; ++j) y[i] = add(y[i], mul(m.at(i, j), x[j]));
+    return y;
+}
+// Gauss-Jordan; false when singular
+bool invert(const Mat& m, Mat* out) {
+    const int n = m.n;
+    Mat a = m, b(n);
+    const F one = from_u64(1);
+    for (int i = 0; i < n; ++i) b.at(i, i) = one;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        while (piv < n && is_zero(a.at(piv, c))) ++piv;
+        if (piv == n) return false;
+        for (int j = 0; j < n; ++j) std::swap(a.at(c, j), a.at(piv, j)), std::swap(b.at(c, j), b.at(piv, j));
+        const F k = inverse(a.at(c, c));
+        for (int j = 0; j < n; ++j) a.at(c, j) = mul(a.at(c, j), k), b.at(c, j) = mul(b.at(c, j), k);
+        for (int r = 0; r < n; ++r) {
+            if (r == c || is_zero(a.at(r, c))) continue;
+            const F f = a.at(r, c);
+            for (int j = 0; j < n; ++j) {
+                a.at(r, j) = sub(a.at(r, j), mul(f, a.at(c, j)));
+                b.at(r, j) = sub(b.at(r, j), mul(f, b.at(c, j)));
+            }
+        }
+    }
+    *out = b;
+    return true;
+}
+
+}  // namespace
+
+bool poseidon_spec_generate(unsigned t_, unsigned r_f_, unsigned r_p_, Fr* out) {
+    const int t = (int)t_, r_f = (int)r_f_, r_p = (int)r_p_, half = r_f / 2, rounds = r_f + r_p;
+    const SpecLayout L{t_, r_f_, r_p_};
+    Grain grain(254, t_, r_f_, r_p_);
+    std::vector<std::vector<F>> rc((size_t)rounds, std::vector<F>((size_t)t));
+    for (int r = 0; r < rounds; ++r)
+        for (int i = 0; i < t; ++i) rc[r][i] = draw_rejecting(grain);
+    std::vector<F> xs((size_t)t), ys((size_t)t);
+    for (int i = 0; i < t; ++i) xs[i] = draw_reducing(grain);
+    for (int i = 0; i < t; ++i) ys[i] = draw_reducing(grain);
+    Mat mds(t), mds_inv(t);
+    for (int i = 0; i < t; ++i)
+        for (int j = 0; j < t; ++j) {
+            const F d = add(xs[i], ys[j]);
+            if (is_zero(d)) return false;
+            mds.at(i, j) = inverse(d);  // Cauchy matrix
+        }
+    if (!invert(mds, &mds_inv)) return false;
+
+    for (size_t i = 0; i < L.total(); ++i) std::memset(out[i].l, 0, 32);
+    const F one = from_u64(1);
+    const uint32_t cap[8] = {0, 0, 1, 0, 0, 0, 0, 0};  // 2^64
+    store(out[L.cap()], from_canonical(cap));
+    store(out[L.one()], one);
+    // ---- constants, re-associated so that every round adds its constants AFTER the S-box
+    for (int i = 0; i < t; ++i) store(out[L.pre(i)], rc[0][i]);
+    for (int r = 1; r < half; ++r) {
+        const std::vector<F> v = matvec(mds_inv, rc[r]);
+        for (int i = 0; i < t; ++i) store(out[L.full(r - 1, i)], v[i]);
+    }
+    std::vector<F> acc = rc[half + r_p];
+    for (int k = r_p - 1; k >= 0; --k) {
+        std::vector<F> v = matvec(mds_inv, acc);
+        store(out[L.partial_c(k)], v[0]);
+        v[0] = kZero;
+        for (int i = 0; i < t; ++i) acc[i] = add(v[i], rc[half + k][i]);
+    }
+    {
+        const std::vector<F> v = matvec(mds_inv, acc);
+        for (int i = 0; i < t; ++i) store(out[L.full(half - 1, i)], v[i]);
+    }
+    for (int r = 0; r < half - 1; ++r) {  // second half; the last full round adds nothing
+        const std::vector<F> v = matvec(mds_inv, rc[half + r_p + 1 + r]);
+        for (int i = 0; i < t; ++i) store(out[L.full(half + r, i)], v[i]);
+    }
+    for (int i = 0; i < t; ++i)
+        for (int j = 0; j < t; ++j) store(out[L.mds(i, j)], mds.at(i, j));
+    // ---- sparse factorisation, last partial round first (see poseidon_params_generate)
+    const Mat mt = transpose(mds);
+    Mat a = mt;
+    for (int k = r_p - 1; k >= 0; --k) {
+        Mat mh(t - 1), mh_inv(t - 1);
+        std::vector<F> w((size_t)(t - 1));
+        for (int i = 1; i < t; ++i) {
+            w[i - 1] = a.at(i, 0);
+            for (int j = 1; j < t; ++j) mh.at(i - 1, j - 1) = a.at(i, j);
+        }
+        if (t > 1 && !invert(mh, &mh_inv)) return false;
+        const std::vector<F> wh = matvec(mh_inv, w);
+        store(out[L.partial_row(k, 0)], a.at(0, 0));
+        for (int i = 1; i < t; ++i) store(out[L.partial_row(k, i)], wh[i - 1]);
+        for (int i = 1; i < t; ++i) store(out[L.partial_col(k, i - 1)], a.at(0, i));
+        Mat mp(t);
+        mp.at(0, 0) = one;
+        for (int i = 1; i < t; ++i)
+            for (int j = 1; j < t; ++j) mp.at(i, j) = mh.at(i - 1, j - 1);
+        a = matmul(mt, mp);
+    }
+    const Mat pre = transpose(a);
+    for (int i = 0; i < t; ++i)
+        for (int j = 0; j < t; ++j) store(out[L.pre_sparse(i, j)], pre.at(i, j));
+    return true;
+}
+
 
 }  // namespace imt

@@ -58,18 +58,35 @@ def _dev_ptr(t):
 
 
 class Engine:
-    """One imt_ctx: Poseidon::<Fr,3,2>::new(8,57) + a GPU. Not thread-safe (mirrors the reference's &mut hasher)."""
+    """One imt_ctx: Poseidon::<Fr,T,RATE>::new(r_f, r_p) + a GPU. Not thread-safe (mirrors the reference's &mut hasher).
 
-    def __init__(self, device=0, fmt="canonical"):
+    The default is the reference's instance <3, 2>(8, 57) on the tuned kernels (imt_ctx_create). Any other instance
+    (t in 2..5, rate = t - 1) — or the same one with generic=True — runs every hash on the any-width kernels
+    (imt_ctx_create_spec): utils.rs:6, 19 and indexed_merkle_tree.rs:65, 127, 231 are generic over T and RATE."""
+
+    def __init__(self, device=0, fmt="canonical", t=3, rate=2, r_f=8, r_p=57, generic=False):
         self._lib = _ffi.load()
         self.fmt = {"canonical": _ffi.FE_CANONICAL, "montgomery": _ffi.FE_MONTGOMERY}[fmt]
         h = ctypes.c_void_p()
-        st = self._lib.imt_ctx_create(int(device), self.fmt, ctypes.byref(h))
+        self.t, self.rate, self.r_f, self.r_p = int(t), int(rate), int(r_f), int(r_p)
+        self.generic = bool(generic) or (self.t, self.rate, self.r_f, self.r_p) != (3, 2, 8, 57)
+        if self.generic:
+            st = self._lib.imt_ctx_create_spec(int(device), self.fmt, self.t, self.rate, self.r_f, self.r_p, ctypes.byref(h))
+            if st == _ffi.ERR_INVALID_ARG:
+                raise ImtError(st, f"unsupported Poseidon instance T={t} RATE={rate} R_F={r_f} R_P={r_p}: need 2 <= T <= 5, "
+                                   "RATE = T - 1, R_F even, R_F + R_P <= 256")
+        else:
+            st = self._lib.imt_ctx_create(int(device), self.fmt, ctypes.byref(h))
         if st != _ffi.OK:
             raise ImtError(st, f"imt_ctx_create(device={device}) failed with status {st}: a CUDA device is required, "
                                "there is no CPU fallback")
         self._h = h
         self.device = int(device)
+        self.states_per_perm = 1 + self.r_f + self.r_p
+
+    def states_per_hash(self, arity):
+        """traced states (of t FE each) of one hash of `arity` inputs: (arity // rate + 1) permutations x (1 + r_f + r_p)"""
+        return (arity // self.rate + 1) * self.states_per_perm
 
     def close(self):
         if getattr(self, "_h", None):
@@ -128,6 +145,24 @@ class Engine:
         self._check(self._lib.imt_poseidon_hash3(self._h, _ptr(a), a.shape[0], _ptr(out)))
         return out
 
+    def hash(self, inputs, arity, n=None):
+        """update(&inputs[i]) + squeeze_and_reset() for any input length (arity >= 0); inputs: (n, arity, 4).
+        With arity 0 (squeeze of an empty sponge) pass the number of hashes as n."""
+        a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1 if arity else (n or 1), arity, 4)
+        out = np.empty((a.shape[0], 4), np.uint64)
+        self._check(self._lib.imt_poseidon_hash(self._h, _ptr(a) if arity else None, arity, a.shape[0], _ptr(out)))
+        return out
+
+    def hash_dev(self, d_in, arity, n, d_out):
+        self._check(self._lib.imt_poseidon_hash_dev(self._h, _dev_ptr(d_in), arity, n, _dev_ptr(d_out)))
+
+    def permute(self, states):
+        """the bare permutation on (n, t, 4) states"""
+        a = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, self.t, 4)
+        out = np.empty_like(a)
+        self._check(self._lib.imt_poseidon_permute(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
     def hash2_dev(self, d_in, n, d_out):
         self._check(self._lib.imt_poseidon_hash2_dev(self._h, _dev_ptr(d_in), n, _dev_ptr(d_out)))
 
@@ -135,9 +170,9 @@ class Engine:
         self._check(self._lib.imt_poseidon_hash3_dev(self._h, _dev_ptr(d_in), n, _dev_ptr(d_out)))
 
     def trace_hashes(self, inputs, arity, want_states=True):
-        a = _fe_array(inputs, (arity,))
+        a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, arity, 4)
         n = a.shape[0]
-        states = np.empty((n, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
+        states = np.empty((n, self.states_per_hash(arity), self.t, 4), np.uint64) if want_states else None
         digests = np.empty((n, 4), np.uint64)
         self._check(self._lib.imt_trace_hashes(self._h, _ptr(a), arity, n, _ptr(states), _ptr(digests)))
         return digests, states
@@ -205,12 +240,13 @@ class Engine:
         idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(q)
         sib = _fe_array(siblings, ()).reshape(q, -1, 4)
         depth = sib.shape[1]
+        shape = (q, depth, self.states_per_hash(2), self.t, 4)
         if out_states is not None:
-            if out_states.shape != (q, depth, STATES_PER_HASH, 3, 4) or out_states.dtype != np.uint64 or not out_states.flags.c_contiguous:
-                raise ValueError("out_states must be a C-contiguous uint64 array of shape (q, depth, 132, 3, 4)")
+            if out_states.shape != shape or out_states.dtype != np.uint64 or not out_states.flags.c_contiguous:
+                raise ValueError(f"out_states must be a C-contiguous uint64 array of shape {shape}")
             states = out_states
         else:
-            states = np.empty((q, depth, STATES_PER_HASH, 3, 4), np.uint64) if want_states else None
+            states = np.empty(shape, np.uint64) if want_states else None
         roots = np.empty((q, 4), np.uint64)
         self._check(self._lib.imt_trace_merkle_proofs(self._h, _ptr(lv), _ptr(idx), _ptr(sib), q, depth, _ptr(states), _ptr(roots)))
         return roots, states

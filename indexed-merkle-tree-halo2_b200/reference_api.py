@@ -12,29 +12,30 @@ import numpy as np
 from .engine import Engine, ImtError, P, fe_from_int, fe_to_int, fes_from_ints, fes_to_ints
 from . import _ffi
 
-_default_engine = None
+_engines = {}
 
 
-def default_engine():
-    global _default_engine
-    if _default_engine is None:
-        _default_engine = Engine(0, "canonical")
-    return _default_engine
+def default_engine(t=3, rate=2, r_f=8, r_p=57):
+    """one canonical-format engine per Poseidon instance, on device 0"""
+    key = (t, rate, r_f, r_p)
+    if key not in _engines:
+        _engines[key] = Engine(0, "canonical", t=t, rate=rate, r_f=r_f, r_p=r_p)
+    return _engines[key]
 
 
 class Poseidon:
-    """`Poseidon::<Fr, 3, 2>::new(r_f, r_p)` + `update` + `squeeze_and_reset` (indexed_merkle_tree.rs:370-376).
+    """`Poseidon::<Fr, T, RATE>::new(r_f, r_p)` + `update` + `squeeze_and_reset` (indexed_merkle_tree.rs:370-376).
 
-    The sponge state is only ever materialised on the GPU: `update` buffers, `squeeze_and_reset` runs the whole
-    fixed-length hash (two permutations) as one kernel. Supported input lengths are the ones the reference uses: 2
-    (node hashing, utils.rs:46) and 3 (leaf hashing, indexed_merkle_tree.rs:374)."""
+    The sponge state is only ever materialised on the GPU: `update` buffers, `squeeze_and_reset` runs the whole hash
+    (len // RATE + 1 permutations) as one kernel. The reference's instance <3, 2>(8, 57) with its input lengths 2 (node
+    hashing, utils.rs:46) and 3 (leaf hashing, indexed_merkle_tree.rs:374) takes the tuned kernels; any other length or
+    instance (T in 2..5, RATE = T - 1) the any-width ones."""
 
-    T, RATE = 3, 2
-
-    def __init__(self, r_f=8, r_p=57, engine=None):
-        if (r_f, r_p) != (8, 57):
-            raise ValueError("only the reference's instantiation R_F=8, R_P=57 (indexed_merkle_tree.rs:362-365) is built")
-        self.engine = engine or default_engine()
+    def __init__(self, r_f=8, r_p=57, engine=None, t=3, rate=2):
+        self.T, self.RATE = t, rate
+        self.engine = engine or default_engine(t, rate, r_f, r_p)
+        if (self.engine.t, self.engine.rate, self.engine.r_f, self.engine.r_p) != (t, rate, r_f, r_p):
+            raise ValueError("the engine was created for a different Poseidon instance")
         self._buf = []
 
     def update(self, elements):
@@ -46,11 +47,7 @@ class Poseidon:
 
     def squeeze_and_reset(self):
         buf, self._buf = self._buf, []
-        if len(buf) == 2:
-            return fe_to_int(self.engine.hash2(fes_from_ints(buf))[0])
-        if len(buf) == 3:
-            return fe_to_int(self.engine.hash3(fes_from_ints(buf))[0])
-        raise NotImplementedError("only 2- and 3-element absorbs (the reference's call sites) run on the GPU path")
+        return fe_to_int(self.engine.hash(fes_from_ints(buf), len(buf))[0])
 
 
 @dataclass

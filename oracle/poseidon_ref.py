@@ -233,36 +233,66 @@ def permute(state, sp=None):
 
 # --------------------------------------------------------------------------- sponge (pse-poseidon poseidon.rs)
 class Poseidon:
-    """Mirror of Poseidon::<Fr,3,2>: new / update / squeeze_and_reset (IMT:370-376)."""
+    """Mirror of Poseidon::<Fr,T,RATE>: new / update / squeeze_and_reset (IMT:370-376). Default <3,2>(8,57);
+    pass sp = Spec(r_f, r_p, t) for another instance (RATE = t - 1; utils.rs:6, 19 are generic over T and RATE)."""
 
-    def __init__(self, r_f=R_F, r_p=R_P):
-        assert (r_f, r_p) == (R_F, R_P)
+    def __init__(self, r_f=R_F, r_p=R_P, sp=None):
+        self.sp = sp or spec()
+        assert sp is not None or (r_f, r_p) == (R_F, R_P)
+        self.rate = self.sp.t - 1
         self._reset()
 
     def _reset(self):
-        self.state = [1 << 64, 0, 0]
+        self.state = [1 << 64] + [0] * (self.sp.t - 1)
         self.absorbing = []
 
     def update(self, elements):
         buf = self.absorbing + [e % P for e in elements]
         self.absorbing = []
-        for i in range(0, len(buf), RATE):
-            chunk = buf[i:i + RATE]
-            if len(chunk) < RATE:
+        for i in range(0, len(buf), self.rate):
+            chunk = buf[i:i + self.rate]
+            if len(chunk) < self.rate:
                 self.absorbing = chunk
             else:
                 for j, e in enumerate(chunk):
                     self.state[1 + j] = (self.state[1 + j] + e) % P
-                self.state = permute(self.state)
+                self.state = permute(self.state, self.sp)
 
     def squeeze_and_reset(self):
         last = self.absorbing + [1]
         for j, e in enumerate(last):
             self.state[1 + j] = (self.state[1 + j] + e) % P
-        self.state = permute(self.state)
+        self.state = permute(self.state, self.sp)
         out = self.state[1]
         self._reset()
         return out
+
+
+def hash_n(inputs, sp=None):
+    """update(inputs) + squeeze_and_reset() for any input length and instance"""
+    h = Poseidon(sp=sp)
+    h.update(list(inputs))
+    return h.squeeze_and_reset()
+
+
+def hash_trace_n(inputs, sp=None):
+    """digest + every traced state ((len // rate + 1) x (1 + r_f + r_p) states of t values) of one hash, any instance"""
+    sp = sp or spec()
+    rate = sp.t - 1
+    s = [1 << 64] + [0] * rate
+    buf = [e % P for e in inputs]
+    states = []
+    while True:
+        chunk, buf = buf[:rate], buf[rate:]
+        last = len(chunk) < rate
+        if last:
+            chunk = chunk + [1]
+        for j, e in enumerate(chunk):
+            s[1 + j] = (s[1 + j] + e) % P
+        s, tr = permute_trace(s, sp)
+        states += tr
+        if last:
+            return s[1], states
 
 
 def hash2(l, r):
@@ -292,7 +322,8 @@ def hash_trace(inputs):
 
 # --------------------------------------------------------------------------- native tree (utils.rs)
 class IndexedMerkleTree:
-    def __init__(self, leaves):  # utils.rs:20-57
+    def __init__(self, leaves, h2=None):  # utils.rs:20-57; h2: node hash of another Poseidon instance
+        hash2 = self._h2 = h2 or globals()["hash2"]
         if len(leaves) == 0:
             raise ValueError("Cannot create Merkle Tree with no leaves")
         if len(leaves) == 1:
@@ -320,6 +351,7 @@ class IndexedMerkleTree:
         return proof, helper
 
     def verify_proof(self, leaf, index, root, proof):  # utils.rs:87-107
+        hash2 = self._h2
         h = leaf
         for sib in proof:
             h = hash2(h, sib) if index % 2 == 0 else hash2(sib, h)
