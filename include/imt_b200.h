@@ -136,6 +136,7 @@ imt_status imt_tree_build_from_leaves_dev(imt_ctx* ctx, const void* d_preimages,
 /* Re-run the build into an existing tree of the same size (no allocation): the steady-state call bench.py times. */
 imt_status imt_tree_rebuild_from_leaves(imt_tree* tree, const void* preimages);
 imt_status imt_tree_rebuild_from_leaves_dev(imt_tree* tree, const void* d_preimages);
+/* A tree points at its context: destroy every tree BEFORE imt_ctx_destroy (the Rust wrapper's lifetime 'a does this). */
 void imt_tree_destroy(imt_tree* tree);
 
 size_t imt_tree_num_leaves(const imt_tree* tree);
@@ -208,6 +209,14 @@ typedef struct imt_insert_witness {
     uint8_t* is_largest;
 } imt_insert_witness;
 imt_status imt_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w);
+
+/* The 128-bit limb witnesses of verify_non_inclusion (src/indexed_merkle_tree.rs:143-172, 206-222; is_less_than :98-125),
+ * batched: for each of the b pairs (low_leaves[3i..3i+3) = val,next_val,next_idx ; new_vals[i]) writes 6 FE
+ *   nl_q, nl_r, ll_q, ll_r, llv_q, llv_r      (x = x_q * 2^128 + x_r; nl = new value, ll = low.next_val, llv = low.val)
+ * in the order the chip loads them, and (flags may be NULL) 3 bytes: nl < ll (is_next_val_greater, :178),
+ * llv < nl (check_less_than, :226), and whether the pair passes both prover-side assertions (:180-191 with
+ * is_new_leaf_largest = (low.next_val == 0), :226-228) — a witness that fails them makes the chip panic before MockProver. */
+imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leaves, const void* new_vals, size_t b, void* limbs, uint8_t* flags);
 
 /* ---------------------------------------------------------------- subtree sharding (one process per GPU) ----- */
 /* A depth-d tree over N = 2^k ranks: rank g owns leaves [g n/N, (g+1) n/N) and builds that subtree with the calls

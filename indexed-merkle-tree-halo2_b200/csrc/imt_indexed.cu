@@ -272,6 +272,47 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__
     if (is_largest) is_largest[i] = ((w[2].x | w[2].y | w[2].z | w[2].w | w[3].x | w[3].y | w[3].z | w[3].w) == 0) ? 1 : 0;  // IMT:736-741
 }
 
+// The 128-bit limb witnesses verify_non_inclusion assigns (indexed_merkle_tree.rs:143-172, 206-222): for every (low leaf,
+// new value) pair  nl = new value, ll = low.next_val, llv = low.val  each split as q * 2^128 + r, in the order the chip loads
+// them: nl_q, nl_r, ll_q, ll_r, llv_q, llv_r; plus the three bits it derives from them (is_less_than, IMT:98-125):
+// flags[3i] = nl < ll (is_next_val_greater, IMT:178), flags[3i+1] = llv < nl (check_less_than, IMT:226), flags[3i+2] = the
+// witness satisfies both prover-side assertions (IMT:180-191 with is_new_leaf_largest = (ll == 0), IMT:226-228).
+__global__ void __launch_bounds__(256) k_limb_witness(const uint4* __restrict__ low_leaves, const uint4* __restrict__ new_vals, size_t b, int fmt,
+                                                      uint4* __restrict__ limbs, uint8_t* __restrict__ flags, uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    uint32_t v[3][8];  // nl, ll, llv as canonical integers
+    load_fe(v[0], new_vals + 2 * i);
+    load_fe(v[1], low_leaves + 2 * (3 * i + 1));
+    load_fe(v[2], low_leaves + 2 * (3 * i));
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        ok &= is_canonical(v[k]);
+        if (fmt == kFmtMontgomery) from_mont(v[k], v[k]);
+    }
+    if (!ok) atomicOr(err, kErrNonCanonical);
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        uint32_t q[8] = {v[k][4], v[k][5], v[k][6], v[k][7], 0, 0, 0, 0};
+        uint32_t r[8] = {v[k][0], v[k][1], v[k][2], v[k][3], 0, 0, 0, 0};
+        if (fmt == kFmtMontgomery) {
+            to_mont(q, q);
+            canonicalize(q);
+            to_mont(r, r);
+            canonicalize(r);
+        }
+        store_fe(limbs + 2 * (6 * i + 2 * k), q);
+        store_fe(limbs + 2 * (6 * i + 2 * k + 1), r);
+    }
+    if (flags) {
+        const bool nl_lt_ll = cmp256(v[0], v[1]) < 0, llv_lt_nl = cmp256(v[2], v[0]) < 0;
+        flags[3 * i] = nl_lt_ll;
+        flags[3 * i + 1] = llv_lt_nl;
+        flags[3 * i + 2] = (zero256(v[1]) || nl_lt_ll) && llv_lt_nl;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------- inserts
 // whole-batch validation on the sorted batch: no zero, no repeats, none already in the tree
 __global__ void __launch_bounds__(256) k_ins_validate(const uint4* __restrict__ sorted_vals, size_t b, const uint4* __restrict__ keys, size_t m,
@@ -988,6 +1029,30 @@ extern "C" imt_status imt_tree_leaves(imt_tree* t, const uint64_t* indices, size
     IMT_TRY(finish(ctx));
     if (leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(leaves, dl.p, q * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (is_largest) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dg.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leaves, const void* new_vals, size_t b, void* limbs, uint8_t* flags) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (b && (!low_leaves || !new_vals || !limbs)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dl(ctx), dv(ctx), dout(ctx), df(ctx);
+    IMT_TRY_CUDA(ctx, dl.alloc(b * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dv.alloc(b * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dout.alloc(b * 6 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, df.alloc(b * 3));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dl.p, low_leaves, b * 3 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, new_vals, b * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    k_limb_witness<<<grid_for(b, 256), 256, 0, ctx->stream>>>(dl.as<uint4>(), dv.as<uint4>(), b, ctx->fmt, dout.as<uint4>(), df.as<uint8_t>(),
+                                                              ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(finish(ctx));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limbs, dout.p, b * 6 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(flags, df.p, b * 3, cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }

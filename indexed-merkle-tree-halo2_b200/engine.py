@@ -3,6 +3,7 @@
 Field elements are rows of 4 little-endian uint64 words (32 bytes) in the engine's format (canonical by default).
 """
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -81,6 +82,7 @@ class Engine:
             raise ImtError(st, f"imt_ctx_create(device={device}) failed with status {st}: a CUDA device is required, "
                                "there is no CPU fallback")
         self._h = h
+        self._trees = weakref.WeakSet()   # a tree holds a pointer to its context: close() destroys the trees first
         self.device = int(device)
         self.states_per_perm = 1 + self.r_f + self.r_p
 
@@ -90,6 +92,8 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for t in list(getattr(self, "_trees", ())):
+                t.close()
             self._lib.imt_ctx_destroy(self._h)
             self._h = None
 
@@ -211,6 +215,9 @@ class Engine:
         result against the stored root."""
         with np.load(path) as z:
             pre, root, fmt = z["preimages"], z["root"], int(z["format"])
+            inst = tuple(int(x) for x in z["instance"]) if "instance" in z else (3, 2, 8, 57)
+        if inst != (self.t, self.rate, self.r_f, self.r_p):
+            raise ValueError(f"checkpoint was written with Poseidon instance {inst}")
         if fmt != self.fmt:
             raise ValueError("checkpoint was written by an engine of the other field-element format")
         tree = self.build_from_leaves(pre)
@@ -284,9 +291,20 @@ class Engine:
         r_zero, t_zero_path = self.trace_merkle_proofs(np.broadcast_to(h_zero, (b, 4)), new_idx, w["new_siblings"])  # IMT:286-294
         h_new, t_new = self.trace_hashes(w["new_leaves"], 3)                # new leaf hash                            IMT:299-303
         r_new, t_new_path = self.trace_merkle_proofs(h_new, new_idx, w["new_siblings"])                 # new root           IMT:305-313
-        return dict(low_leaf=t_low, low_path=t_low_path, new_low_leaf=t_nl, interim_path=t_int_path, zero_path=t_zero_path,
+        limbs, limb_flags = self.non_inclusion_limbs(w["low_leaves"], w["new_leaves"][:, 0])            # hi/lo splits       IMT:143-172, 206-222
+        return dict(limbs=limbs, limb_flags=limb_flags, low_leaf=t_low, low_path=t_low_path, new_low_leaf=t_nl, interim_path=t_int_path, zero_path=t_zero_path,
                     new_leaf=t_new, new_path=t_new_path, old_root=r_old, interim_root=r_int, zero_leaf_root=r_zero, new_root=r_new,
                     new_low_leaf_preimage=new_low)
+
+    def non_inclusion_limbs(self, low_leaves, new_vals):
+        """128-bit limb witnesses of verify_non_inclusion (indexed_merkle_tree.rs:143-172, 206-222): (b, 6, 4) FE in the
+        chip's load order nl_q, nl_r, ll_q, ll_r, llv_q, llv_r and (b, 3) flags [nl < ll, llv < nl, passes the assertions]"""
+        lv = _fe_array(low_leaves, (3,))
+        nv = _fe_array(new_vals, ())
+        b = nv.shape[0]
+        limbs, flags = np.empty((b, 6, 4), np.uint64), np.empty((b, 3), np.uint8)
+        self._check(self._lib.imt_non_inclusion_limbs(self._h, _ptr(lv), _ptr(nv), b, _ptr(limbs), _ptr(flags)))
+        return limbs, flags.astype(bool)
 
     def shard_insert_plan(self, values, first_idx, pred_keys, pred_slots, succ_keys, succ_slots, flags):
         """replicated plan of a sharded insert chunk from the gathered [world][b] neighbour arrays"""
@@ -330,10 +348,12 @@ class Tree:
         self.engine = engine
         self._lib = engine._lib
         self._h = handle
+        engine._trees.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.imt_tree_destroy(self._h)
+            if getattr(self.engine, "_h", None):  # the context is gone => Engine.close() already destroyed this tree
+                self._lib.imt_tree_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -376,7 +396,9 @@ class Tree:
         next_idx (utils.rs:12-17), 32 little-endian bytes each in the engine's format (canonical = halo2curves `to_repr`) —
         plus the root. The levels are NOT stored: load_tree() re-hashes (0.55 s at depth 24) and verifies the root."""
         n = self.num_leaves
-        np.savez(path, preimages=self.preimages(n), root=self.root(), format=np.int64(self.engine.fmt))
+        e = self.engine
+        np.savez(path, preimages=self.preimages(n), root=self.root(), format=np.int64(e.fmt),
+                 instance=np.array([e.t, e.rate, e.r_f, e.r_p], np.int64))
 
     def rebuild_from_leaves(self, preimages):
         a = _fe_array(preimages, (3,))

@@ -198,6 +198,12 @@ def test_insert_leaf_witness_traces(eng, eng_mont):
         tr = e.trace_insert_witness(w, m)
         assert np.array_equal(tr["old_root"], w["old_roots"]) and np.array_equal(tr["new_root"], w["new_roots"])
         assert np.array_equal(tr["zero_leaf_root"], tr["interim_root"])          # IMT:286-294 holds on GPU-made witnesses
+        assert tr["limb_flags"][:, 2].all()                                      # every witness passes the chip's assertions
+        for k in range(b):                                                       # hi/lo limb splits, IMT:143-172, 206-222
+            low, new = O.to_ints(dec(w["low_leaves"][k])), O.to_ints(dec(w["new_leaves"][k]))
+            want = [x for v in (new[0], low[1], low[0]) for x in (v >> 128, v & ((1 << 128) - 1))]
+            assert O.to_ints(dec(tr["limbs"][k])) == want
+            assert list(tr["limb_flags"][k][:2]) == [new[0] < low[1], low[0] < new[0]]
         for k in (0, 3, b - 1):
             low, new = dec(w["low_leaves"][k]), dec(w["new_leaves"][k])
             new_low = np.stack([low[0], new[0], O.fe(m + k)])
@@ -214,6 +220,34 @@ def test_insert_leaf_witness_traces(eng, eng_mont):
                     h, ws = O.hash_trace(pair)
                     assert np.array_equal(dec(tr[path_name][k, lvl]), ws), (k, path_name, lvl)
                     idx //= 2
+
+
+def test_non_inclusion_limbs_edge_values(eng, eng_mont):
+    """imt_non_inclusion_limbs on hand-picked pairs: equal high limbs, equal values, the largest-leaf case (next_val = 0)
+    and a pair that violates the chip's ordering assertion (IMT:180-191, 226-228)"""
+    M = (1 << 128)
+    cases = [  # (low.val, low.next_val, new value)      passes?
+        (5, 9, 7, True),
+        (5 * M + 1, 5 * M + 9, 5 * M + 3, True),       # same high limb: decided by the low limbs
+        (3 * M + 7, 0, P - 1, True),                   # low leaf is the largest: next_val == 0
+        (5, 9, 9, False),                              # new == next_val
+        (5, 9, 5, False),                              # new == low.val
+        (7 * M, 9 * M, 6 * M + (M - 1), False),        # new < low.val
+        (2, P - 1, P - 2, True),
+    ]
+    low = O.fes([x for lv, nv, _, _ in cases for x in (lv, nv, 3)]).reshape(-1, 3, 4)
+    new = O.fes([c[2] for c in cases])
+    for e, enc, dec in ((eng, lambda a: a, lambda a: a), (eng_mont, to_mont, from_mont)):
+        limbs, flags = e.non_inclusion_limbs(enc(low), enc(new))
+        for k, (lv, nv, v, ok) in enumerate(cases):
+            assert O.to_ints(dec(limbs[k])) == [v >> 128, v % M, nv >> 128, nv % M, lv >> 128, lv % M]
+            assert list(flags[k]) == [v < nv, lv < v, ok]
+    with pytest.raises(imt_b200.ImtError) as ex:
+        bad = new.copy()
+        bad[0] = O.fe(0)
+        bad[0, 3] = np.uint64(0xFFFFFFFFFFFFFFFF)                                # >= p
+        eng.non_inclusion_limbs(low, bad)
+    assert ex.value.status == _ffi.ERR_NON_CANONICAL
 
 
 def test_insert_errors_leave_the_tree_untouched(eng):
