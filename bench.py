@@ -321,8 +321,18 @@ def run_lookups(a):
     # e2e: host values in, low_idx + witnesses out
     h_q = d_vals.cpu().numpy().view(np.uint64)
     t0 = time.perf_counter()
-    o = tree.non_inclusion_paths(h_q)
-    t_e2e = time.perf_counter() - t0
+    o = tree.non_inclusion_paths(h_q)                                            # fresh pageable numpy outputs (page faults included)
+    t_e2e_fresh = time.perf_counter() - t0
+    assert np.array_equal(o["low_idx"], d_low.cpu().numpy().astype(np.uint64))
+    bufs = tree.non_inclusion_buffers(q, depth, pinned=True)                      # reusable page-locked outputs: the steady-state call
+    h_qp = torch.empty((q, 4), dtype=torch.int64, pin_memory=True)
+    h_qp.numpy().view(np.uint64)[:] = h_q
+    e2e_times = []
+    for _ in range(1 + a.steps):
+        t0 = time.perf_counter()
+        o = tree.non_inclusion_paths(h_qp.numpy().view(np.uint64), out=bufs)
+        e2e_times.append(time.perf_counter() - t0)
+    t_e2e = min(e2e_times[1:])
     assert np.array_equal(o["low_idx"], d_low.cpu().numpy().astype(np.uint64))
     # inserts: each step one batch of 4096 (host API: values in, full witness bundle out)
     ins = []
@@ -343,7 +353,8 @@ def run_lookups(a):
                                f"then {b} inserts per batch with per-insert roots", "depth": depth, "queries": q, "occupied": m,
                    "l2_policy": f"sorted index {m * 36 / 2**20:.0f} MiB, random probes", "seed": synth.DEFAULT_SEED, "fe_format": "canonical"},
         "e2e": {"value": q / t_e2e, "unit": "lookups/s", "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": q * 32,
-                "d2h_bytes_per_step": q * (8 + 1 + 96 + depth * 33 + 1), "note": "imt_non_inclusion_paths: lookup + low leaf + path + is_largest per value"},
+                "d2h_bytes_per_step": q * (8 + 1 + 96 + depth * 33 + 1), "note": "imt_non_inclusion_paths: lookup + low leaf + path + is_largest per value, into reused page-locked host buffers",
+                "ms_per_step_fresh_pageable_outputs": t_e2e_fresh * 1e3},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_low_leaf_lookup", "achieved": q * probes * 32 / (t_lookup * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": q * probes * 32 / (t_lookup * 1e-3) / 1e9 / hbm, "traffic": None,

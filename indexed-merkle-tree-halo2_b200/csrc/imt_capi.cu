@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -252,12 +253,9 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (!ctx) return IMT_ERR_CUDA;
     ctx->device = device;
     ctx->fmt = (int)format;
-    static PoseidonParams host_params;  // derived once per process
-    static bool have_params = false;
-    if (!have_params) {
-        poseidon_params_generate(&host_params);
-        have_params = true;
-    }
+    static PoseidonParams host_params;  // derived once per process; contexts may be created from several host threads
+    static std::once_flag params_once;
+    std::call_once(params_once, [] { poseidon_params_generate(&host_params); });
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) {  // scratch buffers come from the default pool: keep freed memory cached instead of returning it to the OS
         cudaMemPool_t pool;

@@ -446,11 +446,28 @@ class Tree:
         self.engine._check(self._lib.imt_low_leaf_lookup(self._h, _ptr(v), q, _ptr(low), _ptr(matched)))
         return low, matched.astype(bool)
 
-    def non_inclusion_paths(self, values):
+    @staticmethod
+    def non_inclusion_buffers(q, depth, pinned=False):
+        """output buffers of non_inclusion_paths for q queries; pinned=True allocates page-locked host memory (torch), which
+        the device fills at PCIe speed and which can be reused across calls (fresh pageable arrays cost a page fault per 4 KB)"""
+        shapes = dict(low_idx=((q,), np.uint64), matched=((q,), np.uint8), low_leaves=((q, 3, 4), np.uint64),
+                      siblings=((q, depth, 4), np.uint64), helpers=((q, depth), np.uint8), is_largest=((q,), np.uint8))
+        if not pinned:
+            return {k: np.empty(sh, dt) for k, (sh, dt) in shapes.items()}
+        import torch
+        keep = {k: torch.empty(sh, dtype=torch.int64 if dt == np.uint64 else torch.uint8, pin_memory=True) for k, (sh, dt) in shapes.items()}
+        out = {k: (t.numpy().view(np.uint64) if shapes[k][1] == np.uint64 else t.numpy()) for k, t in keep.items()}
+        out["_pinned"] = keep  # keeps the page-locked allocations alive
+        return out
+
+    def non_inclusion_paths(self, values, out=None):
+        """low leaf + its Merkle path + flags for every value (verify_non_inclusion's witnesses, IMT:127-137).
+        out: buffers from non_inclusion_buffers() to fill instead of allocating new arrays."""
         v = _fe_array(values, ())
         q, d = v.shape[0], self.depth
-        o = dict(low_idx=np.empty(q, np.uint64), matched=np.empty(q, np.uint8), low_leaves=np.empty((q, 3, 4), np.uint64),
-                 siblings=np.empty((q, d, 4), np.uint64), helpers=np.empty((q, d), np.uint8), is_largest=np.empty(q, np.uint8))
+        o = out if out is not None else self.non_inclusion_buffers(q, d)
+        if o["siblings"].shape != (q, d, 4) or o["low_idx"].shape != (q,):
+            raise ValueError("out buffers were made for another batch size / depth")
         self.engine._check(self._lib.imt_non_inclusion_paths(self._h, _ptr(v), q, _ptr(o["low_idx"]), _ptr(o["matched"]),
                                                              _ptr(o["low_leaves"]), _ptr(o["siblings"]), _ptr(o["helpers"]),
                                                              _ptr(o["is_largest"])))
