@@ -173,6 +173,13 @@ imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint6
 imt_status imt_trace_merkle_proofs_dev(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_siblings,
                                        size_t q, unsigned depth, void* d_states, void* d_roots);
 
+/* The same traces for leaves OF A TREE, by index: get_proof (src/utils.rs:63-85) + the verify_merkle_proof witness
+ * (src/indexed_merkle_tree.rs:65-96) in one call. Every operand of every hash is a stored node, so the q x depth traced
+ * hashes run independently on the device instead of as q serial folds. states[q][depth][fe per hash] FE — byte-identical
+ * to imt_tree_get_proofs followed by imt_trace_merkle_proofs on the tree's leaf hashes. */
+imt_status imt_tree_trace_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* states);
+imt_status imt_tree_trace_proofs_dev(imt_tree* tree, const uint64_t* d_indices, size_t q, void* d_states);
+
 /* ---------------------------------------------------------------- indexed-leaf logic ------------------------- */
 /* Low-leaf (predecessor) lookup, the read-only half of update_idx_leaf (src/indexed_merkle_tree.rs:632-660):
  * low_idx[i] = first slot with  val < v && (next_val > v || next_val == 0)  (or slot 0 for the very first insert).

@@ -66,6 +66,8 @@ SIGNATURES = {
     "imt_tree_occupied": (c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
     "imt_non_inclusion_paths": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "imt_insert_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, ctypes.POINTER(InsertWitness)]),
+    "imt_tree_trace_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "imt_tree_trace_proofs_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "imt_non_inclusion_limbs": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_tree_subtree_root_dev": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "imt_tree_attach_cap": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),

@@ -609,10 +609,49 @@ static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint6
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return finish(ctx);
 }
-// Host-buffer front end of the path fold. Without traces it is one launch. With traces the output is 12 672 bytes per
-// hash (19.9 GB for 2^16 depth-24 paths), so the batch is cut into chunks of queries: chunk c is folded into one of two
-// device buffers while the copy stream drains chunk c-1 to the caller's memory — device memory stays bounded and the
-// PCIe transfer, which is the bound of this call, overlaps the hashing.
+// Trace output is 12 672 bytes per hash (19.9 GB for 2^16 depth-24 paths), far more than a caller wants resident: the
+// batch is cut into chunks of queries, chunk c is produced by `launch(first query, count, device buffer)` into one of two
+// device buffers while the copy stream drains chunk c-1 to the caller's memory — device memory stays bounded and the PCIe
+// transfer, which is the bound of these calls, overlaps the hashing.
+template <class Launch>
+static imt_status drain_chunks(imt_ctx* ctx, size_t q, size_t per_query, void* host_out, Launch launch) {
+    size_t chunk = 8192;  // queries per launch: enough warps to hide most of the hash latency, 2.5 GB of trace at depth 24
+    while (chunk > 64 && chunk * per_query > ((size_t)3 << 30)) chunk >>= 1;
+    if (chunk > q) chunk = q;
+    DevBuf buf0(ctx), buf1(ctx);
+    IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
+    if (q > chunk) IMT_TRY_CUDA(ctx, buf1.alloc(chunk * per_query));
+    void* bufs[2] = {buf0.p, buf1.p};
+    Event produced[2], drained[2];
+    for (int i = 0; i < 2; ++i) {
+        IMT_TRY_CUDA(ctx, produced[i].create());
+        IMT_TRY_CUDA(ctx, drained[i].create());
+    }
+    cudaError_t e = cudaSuccess;
+    size_t c = 0;
+    for (size_t off = 0; off < q && e == cudaSuccess; off += chunk, ++c) {
+        const size_t cq = q - off < chunk ? q - off : chunk;
+        const int b = (int)(c & 1);
+        if (c >= 2) e = cudaStreamWaitEvent(ctx->stream, drained[b], 0);  // the buffer is free once its previous chunk left
+        if (e != cudaSuccess) break;
+        launch(off, cq, bufs[b]);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(produced[b], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, produced[b], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char*)host_out + off * per_query, bufs[b], cq * per_query, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(drained[b], ctx->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = std::string("trace pipeline: ") + cudaGetErrorString(e);
+        return IMT_ERR_CUDA;
+    }
+    return IMT_OK;
+}
+
+// Host-buffer front end of the path fold. Without traces it is one launch; with traces it runs through drain_chunks.
 static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* roots, const void* siblings,
                              size_t q, unsigned depth, uint8_t* ok, void* roots_out, void* states) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
@@ -638,42 +677,12 @@ static imt_status fold_paths(imt_ctx* ctx, const void* leaves, const uint64_t* i
                                roots_out ? dro.p : nullptr, nullptr));
     } else {
         const size_t per_query = (size_t)depth * state_fe * sizeof(Fr);
-        size_t chunk = 8192;  // queries per launch: enough warps to hide most of the hash latency, 2.5 GB of trace at depth 24
-        while (chunk > 64 && chunk * per_query > ((size_t)3 << 30)) chunk >>= 1;
-        if (chunk > q) chunk = q;
-        DevBuf buf0(ctx), buf1(ctx);
-        IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
-        if (q > chunk) IMT_TRY_CUDA(ctx, buf1.alloc(chunk * per_query));
-        void* bufs[2] = {buf0.p, buf1.p};
-        Event folded[2], drained[2];
-        for (int i = 0; i < 2; ++i) {
-            IMT_TRY_CUDA(ctx, folded[i].create());
-            IMT_TRY_CUDA(ctx, drained[i].create());
-        }
         IMT_TRY(clear_err(ctx));
-        cudaError_t e = cudaSuccess;
-        size_t c = 0;
-        for (size_t off = 0; off < q && e == cudaSuccess; off += chunk, ++c) {
-            const size_t cq = q - off < chunk ? q - off : chunk;
-            const int b = (int)(c & 1);
-            if (c >= 2) e = cudaStreamWaitEvent(ctx->stream, drained[b], 0);  // the buffer is free once its previous chunk left
-            if (e != cudaSuccess) break;
+        IMT_TRY(drain_chunks(ctx, q, per_query, states, [&](size_t off, size_t cq, void* d_buf) {
             launch_fold(ctx, dl.as<uint4>() + 2 * off, di.as<uint64_t>() + off, ok ? dr.as<uint4>() + 2 * off : nullptr,
                         ds.as<uint4>() + 2 * off * depth, cq, depth, ok ? dok.as<uint8_t>() + off : nullptr,
-                        roots_out ? dro.as<uint4>() + 2 * off : nullptr, bufs[b]);
-            e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaEventRecord(folded[b], ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, folded[b], 0);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync((char*)states + off * per_query, bufs[b], cq * per_query, cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (e == cudaSuccess) e = cudaEventRecord(drained[b], ctx->copy_stream);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
-        cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            ctx->last_error = std::string("trace pipeline: ") + cudaGetErrorString(e);
-            return IMT_ERR_CUDA;
-        }
+                        roots_out ? dro.as<uint4>() + 2 * off : nullptr, d_buf);
+        }));
         IMT_TRY(finish(ctx));
     }
     if (ok) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(ok, dok.p, q, cudaMemcpyDeviceToHost, ctx->stream));
@@ -698,6 +707,53 @@ extern "C" imt_status imt_verify_proofs(imt_ctx* ctx, const void* leaves, const 
 extern "C" imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, const uint64_t* indices, const void* siblings,
                                               size_t q, unsigned depth, void* states, void* roots) {
     return fold_paths(ctx, leaves, indices, nullptr, siblings, q, depth, nullptr, roots, states);
+}
+
+// Witness traces of verify_merkle_proof for leaves OF THIS TREE (indexed_merkle_tree.rs:65-96 with the paths of utils.rs:63-85):
+// all operands are stored levels, so the q x depth traced hashes run independently (k_trace_tree_paths) instead of as q
+// serial folds. states[q][depth][fe per hash]; identical bytes to imt_tree_get_proofs + imt_trace_merkle_proofs.
+static imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states) {
+    imt_ctx* ctx = t->ctx;
+    const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
+    const unsigned depth = t->depth + cap_depth;
+    if (q == 0 || depth == 0) return IMT_OK;
+    if (ctx->generic) return launch_spec_tree_trace(t, d_idx, q, d_states);
+    k_trace_tree_paths<<<grid_for(q * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+        (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, d_idx, q, ctx->fmt,
+        (uint4*)d_states, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+extern "C" imt_status imt_tree_trace_proofs_dev(imt_tree* t, const uint64_t* d_indices, size_t q, void* d_states) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!d_indices || !d_states)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_tree_trace(t, d_indices, q, d_states));
+    return finish(ctx);
+}
+extern "C" imt_status imt_tree_trace_proofs(imt_tree* t, const uint64_t* indices, size_t q, void* states) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!indices || !states)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    const unsigned depth = t->depth + (t->cap_valid ? t->cap_depth : 0);
+    if (q == 0 || depth == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf di(ctx);
+    IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    const size_t per_query = (size_t)depth * trace_fe_per_hash(ctx, 2) * sizeof(Fr);
+    imt_status st = IMT_OK;
+    IMT_TRY(drain_chunks(ctx, q, per_query, states, [&](size_t off, size_t cq, void* d_buf) {
+        const imt_status s1 = launch_tree_trace(t, di.as<uint64_t>() + off, cq, d_buf);
+        if (s1 != IMT_OK) st = s1;
+    }));
+    IMT_TRY(st);
+    return finish(ctx);
 }
 
 // ------------------------------------------------------------------------------------------------- sharding

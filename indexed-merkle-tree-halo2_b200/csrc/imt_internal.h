@@ -179,6 +179,8 @@ imt_status ensure_spec(imt_ctx* ctx);
 // out[i] = squeeze(update(in[arity*i ..])) with the context's instance; d_states may be null
 imt_status launch_spec_hash(imt_ctx* ctx, size_t arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, void* d_states,
                             cudaStream_t s);
+// witness traces of the paths of a resident tree, one thread per (query, level), with the context's instance
+imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states);
 // batched verify_proof / compute_merkle_root (+ trace) with the context's instance
 imt_status launch_spec_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
                             unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);

@@ -160,6 +160,35 @@ __global__ void __launch_bounds__(kHashThreads) k_spec_fold(const uint4* __restr
     }
 }
 
+// k_trace_tree_paths (kernels.cuh) for any width: the traced hashes of the paths of a resident tree are independent
+template <int T>
+__global__ void __launch_bounds__(kHashThreads) k_spec_trace_tree_paths(const uint4* __restrict__ levels, const uint4* __restrict__ cap,
+                                                                        size_t n_local, unsigned depth_local, unsigned cap_depth, unsigned rank,
+                                                                        const uint64_t* __restrict__ idx, size_t q, const Fr* __restrict__ P,
+                                                                        SpecLayout L, int fmt, uint4* __restrict__ states, size_t state_fe,
+                                                                        uint32_t* __restrict__ err) {
+    const unsigned depth = depth_local + cap_depth;
+    const size_t t = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (t >= q * depth) return;
+    const size_t qi = t / depth;
+    const unsigned lvl = (unsigned)(t % depth);
+    const uint64_t g = idx[qi];
+    const uint64_t base = (uint64_t)rank * n_local;
+    if (g < base || g >= base + n_local) {
+        atomicOr(err, kErrIndexOob);
+        return;
+    }
+    const uint4* src;
+    if (lvl < depth_local) src = levels + 2 * (level_offset(n_local, lvl) + (((g - base) >> lvl) & ~(uint64_t)1));
+    else src = cap + 2 * (level_offset((size_t)1 << cap_depth, lvl - depth_local) + (((uint64_t)rank >> (lvl - depth_local)) & ~(uint64_t)1));
+    uint32_t lo[8], hi[8], d[8];
+    load_fe(lo, src);
+    load_fe(hi, src + 2);
+    SpecPairLoad load{lo, hi};
+    SpecTraceSink<T> sink{states + 2 * state_fe * t, fmt};
+    spec_sponge<T>(d, 2, load, P, L, sink);
+}
+
 }  // namespace imt
 
 namespace imt_host {
@@ -217,6 +246,21 @@ imt_status launch_spec_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* 
     IMT_SPEC_DISPATCH(L.t, (k_spec_fold<T><<<grid_for(q, threads), threads, 0, ctx->stream>>>(
                                (const uint4*)d_leaves, d_indices, (const uint4*)d_siblings, (const uint4*)d_roots, q, depth, ctx->d_spec, L,
                                ctx->fmt, d_ok, (uint4*)d_roots_out, (uint4*)d_states, state_fe, ctx->d_err)));
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+
+imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states) {
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY(ensure_spec(ctx));
+    const SpecLayout L = ctx->spec;
+    const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
+    const unsigned depth = t->depth + cap_depth;
+    const size_t state_fe = trace_fe_per_hash(ctx, 2);
+    IMT_SPEC_DISPATCH(L.t, (k_spec_trace_tree_paths<T><<<grid_for(q * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+                               (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u,
+                               d_idx, q, ctx->d_spec, L, ctx->fmt, (uint4*)d_states, state_fe, ctx->d_err)));
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;

@@ -169,6 +169,35 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
     }
 }
 
+// Witness traces of verify_merkle_proof (indexed_merkle_tree.rs:65-96) for paths of a tree that is resident on the device:
+// hash l of the fold for leaf index g is H(level[l][2k], level[l][2k+1]) with k = g >> (l + 1), and both operands are already
+// stored — so the q x depth hashes are INDEPENDENT. One thread per (query, level): a 2^16-path batch runs 1.5 M threads at
+// full occupancy instead of 65 536 serial folds. Same bytes out as k_fold_paths with the state sink.
+__global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* __restrict__ levels, const uint4* __restrict__ cap,
+                                                                   size_t n_local, unsigned depth_local, unsigned cap_depth, unsigned rank,
+                                                                   const uint64_t* __restrict__ idx, size_t q, int fmt,
+                                                                   uint4* __restrict__ states, uint32_t* __restrict__ err) {
+    const unsigned depth = depth_local + cap_depth;
+    const size_t t = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (t >= q * depth) return;
+    const size_t qi = t / depth;
+    const unsigned lvl = (unsigned)(t % depth);
+    const uint64_t g = idx[qi];
+    const uint64_t base = (uint64_t)rank * n_local;
+    if (g < base || g >= base + n_local) {
+        atomicOr(err, kErrIndexOob);
+        return;
+    }
+    const uint4* src;
+    if (lvl < depth_local) src = levels + 2 * (level_offset(n_local, lvl) + (((g - base) >> lvl) & ~(uint64_t)1));
+    else src = cap + 2 * (level_offset((size_t)1 << cap_depth, lvl - depth_local) + (((uint64_t)rank >> (lvl - depth_local)) & ~(uint64_t)1));
+    uint32_t x[2][8], d[8];
+    load_fe(x[0], src);      // tree levels are Montgomery, canonical
+    load_fe(x[1], src + 2);
+    TraceSink sink{states + t * (size_t)(kStatesPerHash * 3 * 2), fmt};
+    hash_fixed<2>(d, x, c_params, sink);
+}
+
 // Format conversion of a dense FE array (used for roots / levels / preimages crossing the boundary)
 __global__ void k_convert(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int from_fmt, int to_fmt,
                           uint32_t* __restrict__ err) {

@@ -423,6 +423,22 @@ class Tree:
             self.engine._check(self._lib.imt_tree_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
         return sib, hel
 
+    def trace_proofs(self, indices, out_states=None):
+        """witness traces of verify_merkle_proof for leaves of this tree, by index: (q, depth, states per hash, t, 4).
+        Every traced hash reads stored nodes, so they all run in parallel (imt_tree_trace_proofs)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        shape = (q, self.depth, self.engine.states_per_hash(2), self.engine.t, 4)
+        if out_states is not None:
+            if out_states.shape != shape or out_states.dtype != np.uint64 or not out_states.flags.c_contiguous:
+                raise ValueError(f"out_states must be a C-contiguous uint64 array of shape {shape}")
+        states = out_states if out_states is not None else np.empty(shape, np.uint64)
+        self.engine._check(self._lib.imt_tree_trace_proofs(self._h, _ptr(idx), q, _ptr(states)))
+        return states
+
+    def trace_proofs_dev(self, d_indices, q, d_states):
+        self.engine._check(self._lib.imt_tree_trace_proofs_dev(self._h, _dev_ptr(d_indices), q, _dev_ptr(d_states)))
+
     def get_proofs_dev(self, d_indices, q, d_siblings, d_helpers=None):
         self.engine._check(self._lib.imt_tree_get_proofs_dev(self._h, _dev_ptr(d_indices), q, _dev_ptr(d_siblings),
                                                              _dev_ptr(d_helpers) if d_helpers is not None else None))

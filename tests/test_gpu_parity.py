@@ -210,6 +210,51 @@ def test_merkle_proof_traces(eng):
         assert np.array_equal(roots[k], h) and np.array_equal(h, t.root())
 
 
+def test_tree_trace_proofs_equal_get_proof_plus_fold_trace(eng, eng_mont):
+    """imt_tree_trace_proofs (one independent traced hash per (query, level), operands read from the stored levels) must
+    give the bytes of get_proof + the serial fold trace — both formats, a sharded tree with a cap, an any-width context"""
+    depth, n = 7, 128
+    pre = synth.indexed_preimages(n, 90, seed=31)
+    idx = np.array([0, 1, 2, 77, 126, 127, 77], np.uint64)
+    for e, enc in ((eng, lambda a: a), (eng_mont, to_mont)):
+        t = e.build_from_leaves(enc(pre))
+        sib, _ = t.get_proofs(idx)
+        leaves = t.level(0, n)[idx.astype(np.int64)]
+        roots, want = e.trace_merkle_proofs(leaves, idx, sib)
+        got = t.trace_proofs(idx)
+        assert got.shape == (len(idx), depth, 132, 3, 4) and np.array_equal(got, want)
+        assert np.array_equal(got[:, -1, -1, 1], roots)                 # the last traced state of every path holds the root
+        with pytest.raises(imt_b200.ImtError) as ex:
+            t.trace_proofs(np.array([n], np.uint64))
+        assert ex.value.status == _ffi.ERR_INDEX_OOB
+    # sharded: the cap levels of the path come from the replicated cap
+    world, per = 4, n // 4
+    whole = eng.build_from_leaves(pre)
+    shards = [eng.build_from_leaves(pre[r * per:(r + 1) * per]) for r in range(world)]
+    sub_roots = np.stack([s.root() for s in shards])
+    for r, s in enumerate(shards):
+        s.attach_cap(r, world, sub_roots)
+        own = np.array([r * per, r * per + 5, (r + 1) * per - 1], np.uint64)
+        assert np.array_equal(s.trace_proofs(own), whole.trace_proofs(own))
+    # any-width context
+    g = imt_b200.Engine(0, "canonical", t=4, rate=3, r_f=8, r_p=56)
+    tg = g.build_from_leaves(pre)
+    sib, _ = tg.get_proofs(idx)
+    _, want = g.trace_merkle_proofs(tg.level(0, n)[idx.astype(np.int64)], idx, sib)
+    assert np.array_equal(tg.trace_proofs(idx), want) and want.shape == (len(idx), depth, 65, 4, 4)
+    g.close()
+
+
+def test_tree_trace_proofs_chunked_pipeline(eng_mont):
+    """more queries than one pipeline chunk (8192): the double-buffered host path must deliver every chunk"""
+    depth, n, q = 4, 16, 8192 * 2 + 100
+    t = eng_mont.build_from_hashes(to_mont(synth.field_elements(n, seed=8)))
+    idx = (np.arange(q, dtype=np.uint64) * np.uint64(7)) % np.uint64(n)
+    got = t.trace_proofs(idx)
+    ref = t.trace_proofs(np.arange(n, dtype=np.uint64))
+    assert np.array_equal(got, ref[idx.astype(np.int64)])
+
+
 def test_reference_api_mirror_runs_the_reference_test_scenario():
     """The native half of test_insert_leaf_multiple_round (indexed_merkle_tree.rs:679-741), written against the same
     names the reference uses, with its O(n) re-hash + rebuild per round — all hashing on the GPU."""
