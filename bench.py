@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 MACS_PER_HASH = 163_200          # 2 perms x 600 Montgomery muls x 136 32x32->64 MACs
 EXECUTED_MACS_PER_HASH = 123_792  # what the kernels issue: squarings are 36 products, 3-term dot products reduce once (ncu: profiles/)
 LEAF_DRAM_BYTES_PER_HASH = 132.6  # dram__bytes_read+write of k_hash<3> per leaf: 2.225 GB / 2^24 leaves, ncu --set full (profiles/r01c_summary.md)
+TRACE_DRAM_BYTES_PER_HASH = 12568.0  # dram__bytes_read+write of k_trace_tree_paths per traced hash: 4.118 GB / 327 680 hashes (profiles/r01e_summary.md); algorithmic 12 672 + 64
 METRIC = "poseidon_hashes_per_s_depth24_tree_build"
 
 
@@ -277,7 +278,9 @@ def run_paths(a):
                 "h2d_bytes_per_step": qe * (8 + 32 + depth * 32), "d2h_bytes_per_step": qe * depth * (32 + 1 + 132 * 96)},
         "gpu_launches": launches_tree,
         "roofline": {"bound": "imad", "kernel": "k_trace_tree_paths", "achieved": hashes * MACS_PER_HASH / (t_tree * 1e-3) / 1e9, "peak": imad_rate / 1e9,
-                     "unit": "GMAC/s", "frac": hashes * MACS_PER_HASH / (t_tree * 1e-3) / imad_rate, "traffic": None,
+                     "unit": "GMAC/s", "frac": hashes * MACS_PER_HASH / (t_tree * 1e-3) / imad_rate, "traffic": TRACE_DRAM_BYTES_PER_HASH * hashes,
+                     "traffic_note": "bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel per traced hash (12 568 B, one --set full "
+                                     "capture, profiles/r01e_summary.md) x hashes per launch; algorithmic 12 672 B written + 64 B read per hash",
                      "peak_source": f"imt_calibrate_imad in this run ({imad_mhz:.0f} MHz implied)",
                      "hbm": {"achieved_gbs": trace_bytes / (t_tree * 1e-3) / 1e9, "peak_gbs": hbm, "frac": trace_bytes / (t_tree * 1e-3) / 1e9 / hbm}},
         "parts": {"get_proofs_ms": t_gather, "serial_fold_trace_ms": t_trace, "serial_fold_trace_hashes_per_s": hashes / (t_trace * 1e-3),

@@ -129,6 +129,7 @@ def main():
     full(tag, md)
     full(tag, md, "k_coop", "Cooperative kernel (3 lanes per hash): levels of 8192, 4096, ... nodes")
     full(tag, md, "k_trace", "Witness-trace fold (k_fold_paths with the state sink): 2^14 paths of the depth-20 tree")
+    full(tag, md, "k_tree_trace", "Witness traces from the resident tree (k_trace_tree_paths): 2^14 paths of the depth-20 tree, one thread per (query, level)")
     os.makedirs(OUT, exist_ok=True)
     out = os.path.join(OUT, f"{tag}_summary.md")
     open(out, "w").write("\n".join(md) + "\n")
