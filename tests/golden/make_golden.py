@@ -20,7 +20,25 @@ import imt_b200  # noqa: E402  (synthetic-input definitions only; no GPU is touc
 from imt_b200 import synth  # noqa: E402
 
 
+def spec_vectors():
+    """any-width instances: published permutation vectors + sponge digests from the Python oracle"""
+    out = {"published_perm_x5_254_3_input_0_1_2": [hex(v) for v in R.permute([0, 1, 2])],
+           "published_perm_x5_254_5_input_0_to_4": [hex(v) for v in R.permute([0, 1, 2, 3, 4], R.Spec(8, 60, 5))], "hashes": {}}
+    for t, r_f, r_p in ((2, 8, 56), (3, 8, 57), (4, 8, 56), (5, 8, 60)):
+        sp = R.Spec(r_f, r_p, t)
+        out["hashes"][f"{t},{r_f},{r_p}"] = {str(k): str(R.hash_n(list(range(1, k + 1)), sp)) for k in range(0, 7)}
+    return out
+
+
 def main():
+    if "--spec-only" in sys.argv:  # refresh only the any-width vectors, keep everything else byte for byte
+        path = os.path.join(HERE, "golden.json")
+        g = json.load(open(path))
+        g["spec"] = spec_vectors()
+        with open(path, "w") as f:
+            json.dump(g, f, indent=1)
+        print("updated golden.json: spec")
+        return
     th = O.max_threads()
     g = {"seed": synth.DEFAULT_SEED, "kat_h3_zero": str(R.KAT_H3_ZERO)}
     g["h2_0_0"] = str(R.hash2(0, 0))
@@ -54,6 +72,7 @@ def main():
     if "24" not in roots and "24" in old:
         roots["24"] = old["24"]
     g["build_roots"] = roots
+    g["spec"] = spec_vectors()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote golden.json")

@@ -7,7 +7,7 @@ import pytest
 import imt_b200
 from imt_b200 import synth
 import poseidon_ref as R
-from test_spec_params import KAT_T3, KAT_T5
+from test_spec_params import KAT_T3, KAT_T5, GOLD
 
 pytestmark = pytest.mark.gpu
 P = imt_b200.P
@@ -36,6 +36,18 @@ def test_published_permutation_vectors_on_the_gpu():
     # the tuned context reaches the same permutation through its lazily derived any-width parameters
     d = imt_b200.Engine(0, "canonical")
     assert ints(d.permute(imt_b200.fes_from_ints([0, 1, 2]))) == KAT_T3
+
+
+def test_golden_digests_of_every_instance():
+    """committed vectors (tests/golden/golden.json, written by make_golden.py --spec-only): H(1, ..., k) for k = 0..6"""
+    for key, digests in GOLD["hashes"].items():
+        t, r_f, r_p = (int(x) for x in key.split(","))
+        e = engine(t, r_f, r_p)
+        for k, d in digests.items():
+            k = int(k)
+            got = e.hash(imt_b200.fes_from_ints(list(range(1, k + 1))).reshape(1, k, 4), k, n=1)
+            assert imt_b200.fe_to_int(got[0]) == int(d), (key, k)
+        e.close()
 
 
 @pytest.mark.parametrize("t,r_f,r_p", INSTANCES)

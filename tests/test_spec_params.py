@@ -4,6 +4,8 @@ permutation of [0, 1, 2] / [0, 1, 2, 3, 4] over the BN254 scalar field with R_F 
 is independent of the reference's own known-answer (indexed_merkle_tree.rs:247-251) — and checks the library's HOST
 parameter derivation (imt_spec_params_host: no device work) against the oracle's for every supported width."""
 import ctypes
+import json
+import os
 
 import numpy as np
 import pytest
@@ -23,6 +25,7 @@ KAT_T5 = [0x299c867db6c1fdd79dcefa40e4510b9837e60ebb1ce0663dbaa525df65250465,
           0x24febb87fed7462e23f6665ff9a0111f4044c38ee1672c1ac6b0637d34f24907,
           0x0eb08f6d809668a981c186beaf6110060707059576406b248e5d9cf6e78b3d3e,
           0x07748bc6877c9b82c8b98666ee9d0626ec7f5be4205f79ee8528ef1c4a376fc7]
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))["spec"]
 INSTANCES = [(2, 8, 56), (3, 8, 57), (4, 8, 56), (5, 8, 60), (3, 6, 10), (4, 2, 0)]
 
 
@@ -32,6 +35,17 @@ def test_published_permutation_vectors_pin_the_python_oracle():
     sp5 = R.Spec(8, 60, 5)
     assert R.permute_naive([0, 1, 2, 3, 4], sp5) == KAT_T5
     assert R.permute([0, 1, 2, 3, 4], sp5) == KAT_T5
+
+
+def test_golden_fixture_holds_the_published_vectors_and_the_oracle_digests():
+    assert [int(x, 16) for x in GOLD["published_perm_x5_254_3_input_0_1_2"]] == KAT_T3
+    assert [int(x, 16) for x in GOLD["published_perm_x5_254_5_input_0_to_4"]] == KAT_T5
+    for key, digests in GOLD["hashes"].items():
+        t, r_f, r_p = (int(x) for x in key.split(","))
+        sp = R.Spec(r_f, r_p, t)
+        for k, d in digests.items():
+            assert R.hash_n(list(range(1, int(k) + 1)), sp) == int(d)
+    assert int(GOLD["hashes"]["3,8,57"]["3"]) == R.hash3(1, 2, 3) and int(GOLD["hashes"]["3,8,57"]["2"]) == R.hash2(1, 2)
 
 
 def test_published_permutation_vector_pins_the_c_oracle():
