@@ -188,6 +188,17 @@ class ShardedTree:
         per = -(-q // self.world)
         return slice(min(q, self.rank * per), min(q, (self.rank + 1) * per))
 
+    def trace_proofs(self, indices):
+        """verify_merkle_proof witness traces (IMT:65-96) for GLOBAL leaf indices, sharded by leaf owner with NO exchange:
+        the owner reads every operand from its stored subtree levels / the replicated cap and runs the q x depth traced
+        hashes independently (imt_tree_trace_proofs). Returns (mine, states): `mine` = positions into `indices` of the
+        queries this rank owns, states[len(mine), depth, states per hash, t, 4] their traces — they stay on this rank."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        if idx.size and int(idx.max()) >= self.num_leaves:
+            raise IndexError("index out of bounds")
+        mine = np.nonzero(self.owner(idx) == self.rank)[0]
+        return mine, self.tree.trace_proofs(idx[mine])
+
     def trace_merkle_proofs(self, leaves, indices, siblings, want_states=True):
         """compute_merkle_root traces (IMT:78-96) of this rank's query slice: (slice, roots, states). The traces stay
         on the rank that produced them (19.9 GB for 2^16 depth-24 paths is not gathered)."""

@@ -53,6 +53,26 @@ class OracleTree:
                 sib[k, self.local_depth:], hel[k, self.local_depth:] = s, h
         return sib, hel
 
+    def trace_proofs(self, indices):
+        """traces of the paths of this (sub)tree: every hash of the fold, operands read from the stored levels"""
+        idx = np.asarray(indices, dtype=np.uint64).reshape(-1)
+        out = np.zeros((idx.size, self.depth, 132, 3, 4), np.uint64)
+        base = self.rank * self.n if self.cap is not None else 0
+        lv_off = lambda n, l: 2 * n - 2 * (n >> l)  # noqa: E731  FE offset of level l in the concatenated tree
+        for k, g in enumerate(idx):
+            local = int(g) - base
+            for l in range(self.depth):
+                if l < self.local_depth:
+                    tree, n, node = self.tree, self.n, (local >> l) & ~1
+                    off = lv_off(n, l) + node
+                else:
+                    cl = l - self.local_depth
+                    tree, n, node = self.cap, self.world, (self.rank >> cl) & ~1
+                    off = lv_off(n, cl) + node
+                flat = np.asarray(tree).reshape(-1, 4)
+                out[k, l] = O.hash_trace(flat[off:off + 2])[1]
+        return out
+
     def leaves(self, indices):
         idx = np.asarray(indices, dtype=np.int64).reshape(-1) - (self.rank * self.n if self.world > 1 else 0)
         out = self.pre[idx]

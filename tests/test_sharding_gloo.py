@@ -61,6 +61,16 @@ def _worker(rank, world, port, depth, occupied, use_gpu, errors):
         leaf_hashes = O.hash3(pre[idx.astype(np.int64)], 4)
         sl, roots, _ = st.trace_merkle_proofs(leaf_hashes, idx, sib, want_states=False)
         assert (roots == whole[-1]).all() and sl == st.query_slice(len(idx))
+        # by-owner sharding of the path traces: each rank traces the leaves it owns from its stored levels + the cap
+        mine, states = st.trace_proofs(idx)
+        assert sorted(mine.tolist()) == [k for k, i in enumerate(idx) if int(i) // per == rank]
+        for k, tr in zip(mine[:6], states[:6]):
+            h, ix = O.hash3(pre[int(idx[k])][None], 1)[0], int(idx[k])
+            for lvl in range(depth):
+                pair = np.stack([h, sib[k, lvl]]) if ix % 2 == 0 else np.stack([sib[k, lvl], h])
+                h, ws = O.hash_trace(pair)
+                assert np.array_equal(tr[lvl], ws), f"trace of leaf {int(idx[k])} level {lvl}"
+                ix //= 2
         if True:
             # sharded insert batch: against the oracle advancing the WHOLE tree one insert at a time
             free = n - occupied
