@@ -47,6 +47,10 @@ def main():
     leaf_hashes = eng.hash3(pre[idx.astype(np.int64)])
     sl, roots, states = st.trace_merkle_proofs(leaf_hashes, idx, sib)
     assert (roots == st.root()).all() and states.shape[1:] == (depth, 132, 3, 4)
+    # traces sharded by leaf owner (operands read from the stored levels + the cap) == the serial fold traces of those queries
+    mine, own_states = st.trace_proofs(idx)
+    _, want_states = eng.trace_merkle_proofs(leaf_hashes[mine], idx[mine], sib[mine])
+    assert np.array_equal(own_states, want_states), "owner-sharded traces differ from the fold traces"
     # sharded insert batch == the single-GPU insert batch of the same tree, field by field
     vals = synth.field_elements(min(3000, n - occupied), seed=99)
     got = st.insert_batch(vals, chunk=1024)
