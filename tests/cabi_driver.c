@@ -80,7 +80,37 @@ int main(void) {
     uint8_t matched, hel[3], lg;
     CHECK(imt_non_inclusion_paths(tree, q, 1, &li, &matched, ll, sib, hel, &lg));
     printf("non_inclusion low_idx %" PRIu64 " val %" PRIu64 " next %" PRIu64 " matched %d largest %d\n", li, ll[0], ll[4], (int)matched, (int)lg);
+    /* verify_merkle_proof witness of leaf 3 straight from the tree: depth x 132 x 3 FE; the last state holds the root */
+    static uint64_t states[3 * 132 * 3 * 4];
+    uint64_t leaf3 = 3;
+    CHECK(imt_tree_trace_proofs(tree, &leaf3, 1, states));
+    CHECK(imt_tree_root(tree, root));
+    printf("trace_ends_in_root %d\n", memcmp(states + ((2 * 132 + 131) * 3 + 1) * 4, root, 32) == 0);
+    /* 128-bit limb witnesses of verify_non_inclusion for (low leaf 20 -> 30, new value 25) */
+    uint64_t limbs[6 * 4];
+    uint8_t flags[3];
+    CHECK(imt_non_inclusion_limbs(ctx, ll, q, 1, limbs, flags));
+    printf("limbs nl_r %" PRIu64 " ll_r %" PRIu64 " llv_r %" PRIu64 " flags %d%d%d\n", limbs[4], limbs[12], limbs[20], flags[0], flags[1], flags[2]);
     imt_tree_destroy(tree);
+    /* another Poseidon instance (utils.rs:6, 19 are generic over T and RATE): <5, 4>(8, 60); the published permutation
+     * vector poseidonperm_x5_254_5 of [0, 1, 2, 3, 4], and a 6-element update + squeeze_and_reset */
+    imt_ctx* ctx5 = NULL;
+    st = imt_ctx_create_spec(0, IMT_FE_CANONICAL, 5, 4, 8, 60, &ctx5);
+    if (st != IMT_OK) {
+        fprintf(stderr, "imt_ctx_create_spec -> %d\n", (int)st);
+        return 1;
+    }
+    uint64_t in5[6 * 4] = {0}, out5[5 * 4], dg[4];
+    for (int i = 0; i < 5; ++i) in5[4 * i] = (uint64_t)i;
+    if (imt_poseidon_permute(ctx5, in5, 1, out5) != IMT_OK) return 1;
+    print_fe("perm5", out5);
+    for (int i = 0; i < 6; ++i) in5[4 * i] = (uint64_t)i + 1;
+    if (imt_poseidon_hash(ctx5, in5, 6, 1, dg) != IMT_OK) return 1;
+    print_fe("hash5_6", dg);
+    size_t fe_per_hash = 0;
+    if (imt_trace_fe_per_hash(ctx5, 6, &fe_per_hash) != IMT_OK) return 1;
+    printf("trace_fe %zu\n", fe_per_hash);
+    imt_ctx_destroy(ctx5);
     imt_ctx_destroy(ctx);
     return 0;
 }

@@ -54,3 +54,8 @@ def test_c_client_runs_the_reference_scenario():
     assert [str(fe(l)) for l in rounds[1::2]] == GOLD["scenario_roots"]
     assert [int(l.split()[3]) for l in rounds[0::2]] == [1, 0, 0, 0, 1, 0]      # is_new_leaf_largest per round (IMT:736-741)
     assert lines[16] == "non_inclusion low_idx 3 val 20 next 30 matched 1 largest 0"
+    assert lines[17] == "trace_ends_in_root 1"
+    assert lines[18] == "limbs nl_r 25 ll_r 30 llv_r 20 flags 111"
+    assert fe(lines[19]) == int(GOLD["spec"]["published_perm_x5_254_5_input_0_to_4"][0], 16)   # published Poseidon test vector
+    assert fe(lines[20]) == int(GOLD["spec"]["hashes"]["5,8,60"]["6"])
+    assert lines[21] == f"trace_fe {(6 // 4 + 1) * (1 + 8 + 60) * 5}"
