@@ -1,0 +1,190 @@
+// TEST: the native halves of the reference's own tests (/root/reference/src/indexed_merkle_tree.rs:360-810), written against
+// the C++ host mirror include/imt_b200.hpp with the reference's names and flow — the circuit halves (MockProver) are out of
+// scope. Built by tests/test_cpp_mirror.py with g++ and linked against libimt_b200.so (no CUDA headers).
+//   exit 0  every REQUIRE held; the printed values are compared with tests/golden/golden.json by the python test
+//   exit 3  no CUDA device: Poseidon::new_ threw NoDevice (the library has no CPU fallback)
+#include <cstdio>
+#include <cstdlib>
+
+#include "imt_b200.hpp"
+
+using namespace imt_b200;
+using IMTLeaf = IndexedMerkleTreeLeaf;   // the alias the reference's tests use (IMT:334)
+
+#define REQUIRE(cond)                                                        \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::fprintf(stderr, "%s:%d: REQUIRE(%s) failed\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                    \
+        }                                                                    \
+    } while (0)
+
+constexpr size_t T = 3, RATE = 2, R_F = 8, R_P = 57;   // IMT:362-365
+
+// test_hash_zero (IMT:805-810)
+static void test_hash_zero() {
+    auto native_hasher = Poseidon<T, RATE>::new_(R_F, R_P);
+    native_hasher.update({Fr::from(0), Fr::from(0), Fr::from(0)});
+    std::printf("test_hash_zero %s\n", native_hasher.squeeze_and_reset().hex().c_str());
+}
+
+// test_insert_leaf (IMT:360-596), native half; the unseeded thread_rng value (IMT:380-388) is a fixed 254-bit value < r here
+static void test_insert_leaf() {
+    const size_t tree_size = 8;
+    std::vector<Fr> leaves;
+    auto native_hasher = Poseidon<T, RATE>::new_(R_F, R_P);
+    for (size_t i = 0; i < tree_size; ++i) {   // filling leaves with default values
+        native_hasher.update({Fr::from(0), Fr::from(0), Fr::from(0)});
+        leaves.push_back(native_hasher.squeeze_and_reset());
+    }
+    auto tree = IndexedMerkleTree<T, RATE>::new_(native_hasher, leaves).unwrap();
+    Fr new_val;
+    new_val.l = {0x0123456789abcdefull, 0xfedcba9876543210ull, 0x0f1e2d3c4b5a6978ull, 0x2a3b4c5d6e7f8091ull};
+    const Fr next_val_gr = new_val;
+
+    Fr old_root = tree.get_root();
+    auto [low_leaf_proof, low_leaf_proof_helper] = tree.get_proof(0);
+    REQUIRE(tree.verify_proof(leaves[0], 0, tree.get_root(), low_leaf_proof));
+    REQUIRE(low_leaf_proof_helper[0] == Fr::one());   // leaf 0 is a LEFT child (utils.rs:70, 79)
+
+    IMTLeaf new_low_leaf{Fr::from(0), new_val, Fr::from(1)};
+    native_hasher.update({new_low_leaf.val, new_low_leaf.next_val, new_low_leaf.next_idx});
+    leaves[0] = native_hasher.squeeze_and_reset();
+    native_hasher.update({new_val, Fr::from(0), Fr::from(0)});
+    leaves[1] = native_hasher.squeeze_and_reset();
+    tree = IndexedMerkleTree<T, RATE>::new_(native_hasher, leaves).unwrap();
+    auto [new_leaf_proof, new_leaf_proof_helper] = tree.get_proof(1);
+    REQUIRE(tree.verify_proof(leaves[1], 1, tree.get_root(), new_leaf_proof));
+    REQUIRE(new_leaf_proof_helper[0] == Fr::zero());
+    REQUIRE(tree.get_root() != old_root);
+    std::printf("test_insert_leaf root1 %s\n", tree.get_root().hex().c_str());
+
+    // inserting a leaf less than the largest (IMT:493-536)
+    new_val = Fr::from(42);
+    new_low_leaf = IMTLeaf{Fr::from(0), new_val, Fr::from(2)};
+    native_hasher.update({new_low_leaf.val, new_low_leaf.next_val, new_low_leaf.next_idx});
+    leaves[0] = native_hasher.squeeze_and_reset();
+    native_hasher.update({new_val, next_val_gr, Fr::from(1)});
+    leaves[2] = native_hasher.squeeze_and_reset();
+    tree = IndexedMerkleTree<T, RATE>::new_(native_hasher, leaves).unwrap();
+    auto [proof2, helper2] = tree.get_proof(2);
+    REQUIRE(tree.verify_proof(leaves[2], 2, tree.get_root(), proof2));
+    Fr tampered = leaves[2];
+    tampered.l[0] ^= 1;
+    REQUIRE(!tree.verify_proof(tampered, 2, tree.get_root(), proof2));
+    std::printf("test_insert_leaf root2 %s\n", tree.get_root().hex().c_str());
+
+    // the same two inserts through the batched call: same roots, same witnesses
+    std::vector<IMTLeaf> empty(tree_size);
+    auto batched = IndexedMerkleTree<T, RATE>::from_preimages(native_hasher, empty).unwrap();
+    InsertWitness w = batched.insert_batch({next_val_gr, Fr::from(42)});
+    REQUIRE(w.new_roots[1] == tree.get_root() && batched.get_root() == tree.get_root());
+    REQUIRE(w.low_idx[0] == 0 && w.low_idx[1] == 0 && w.is_new_leaf_largest[0] && !w.is_new_leaf_largest[1]);
+    REQUIRE(w.new_proof[1] == proof2 && w.new_proof_helper[1] == helper2);
+}
+
+// test_insert_leaf_multiple_round (IMT:679-803), native half: per round the low-leaf scan, re-hash of ALL leaves and
+// rebuild of the WHOLE tree exactly as the reference does it — then the one-call batched replacement
+static void test_insert_leaf_multiple_round() {
+    auto native_hasher = Poseidon<T, RATE>::new_(R_F, R_P);
+    const std::vector<Fr> new_vals = {Fr::from(30), Fr::from(10), Fr::from(20), Fr::from(5), Fr::from(50), Fr::from(35)};   // IMT:683-690
+    const size_t tree_size = 8;
+    std::vector<IMTLeaf> nullifier_tree_preimages(tree_size);
+    std::vector<Fr> nullifier_tree_leaves = hash_nullifier_pre_images(native_hasher, nullifier_tree_preimages);
+    auto nullifier_tree = IndexedMerkleTree<T, RATE>::new_(native_hasher, nullifier_tree_leaves).unwrap();
+    std::printf("multiple_round empty_root %s\n", nullifier_tree.get_root().hex().c_str());
+    auto batched = IndexedMerkleTree<T, RATE>::from_preimages(native_hasher, nullifier_tree_preimages).unwrap();
+    InsertWitness w = batched.insert_batch(new_vals);
+
+    for (size_t round = 0; round < new_vals.size(); ++round) {
+        const Fr old_root = nullifier_tree.get_root();
+        auto [updated, low_leaf_idx] = update_idx_leaf(nullifier_tree_preimages, new_vals[round], round + 1);   // IMT:714-715
+        const IMTLeaf low_leaf = nullifier_tree_preimages[low_leaf_idx];
+        auto [low_leaf_proof, low_leaf_proof_helper] = nullifier_tree.get_proof(low_leaf_idx);                 // IMT:720-722
+        nullifier_tree_preimages = updated;
+        nullifier_tree_leaves = hash_nullifier_pre_images(native_hasher, nullifier_tree_preimages);             // IMT:724
+        nullifier_tree = IndexedMerkleTree<T, RATE>::new_(native_hasher, nullifier_tree_leaves).unwrap();      // IMT:726-730
+        const IMTLeaf new_leaf = nullifier_tree_preimages[round + 1];
+        auto [new_leaf_proof, new_leaf_proof_helper] = nullifier_tree.get_proof(round + 1);                    // IMT:734
+        const Fr new_root = nullifier_tree.get_root();
+        const bool is_new_leaf_largest = new_leaf.next_val.is_zero();                                          // IMT:736-741
+        std::printf("multiple_round %zu low_idx %zu largest %d root %s\n", round, low_leaf_idx, (int)is_new_leaf_largest, new_root.hex().c_str());
+        // the batched witness of the same round
+        REQUIRE(w.old_roots[round] == old_root && w.new_roots[round] == new_root && w.low_idx[round] == low_leaf_idx);
+        REQUIRE(w.low_leaves[round].val == low_leaf.val && w.low_leaves[round].next_val == low_leaf.next_val &&
+                w.low_leaves[round].next_idx == low_leaf.next_idx);
+        REQUIRE(w.new_leaves[round].val == new_leaf.val && w.new_leaves[round].next_val == new_leaf.next_val &&
+                w.new_leaves[round].next_idx == new_leaf.next_idx);
+        REQUIRE(w.low_proof[round] == low_leaf_proof && w.low_proof_helper[round] == low_leaf_proof_helper);
+        REQUIRE(w.new_proof[round] == new_leaf_proof && w.new_proof_helper[round] == new_leaf_proof_helper);
+        REQUIRE(w.is_new_leaf_largest[round] == is_new_leaf_largest);
+    }
+    REQUIRE(batched.get_root() == nullifier_tree.get_root());
+    const std::vector<IMTLeaf> fin = batched.preimages();
+    for (size_t i = 0; i < tree_size; ++i)
+        std::printf("multiple_round final %zu %llu %llu %llu\n", i, (unsigned long long)fin[i].val.l[0], (unsigned long long)fin[i].next_val.l[0],
+                    (unsigned long long)fin[i].next_idx.l[0]);
+}
+
+// IndexedMerkleTree::new error behaviour (utils.rs:24-36, 45, 76)
+static void test_new_errors() {
+    auto h = Poseidon<T, RATE>::new_(R_F, R_P);
+    auto e = IndexedMerkleTree<T, RATE>::new_(h, {});
+    REQUIRE(e.is_err());
+    std::printf("new_errors empty: %s\n", e.unwrap_err());
+    auto o = IndexedMerkleTree<T, RATE>::new_(h, {Fr::from(1), Fr::from(2), Fr::from(3)});
+    REQUIRE(o.is_err());
+    std::printf("new_errors odd: %s\n", o.unwrap_err());
+    auto single = IndexedMerkleTree<T, RATE>::new_(h, {Fr::from(7)}).unwrap();   // utils.rs:27-33: tree = [leaves], root = leaves[0]
+    REQUIRE(single.get_root() == Fr::from(7) && single.depth() == 0);
+    bool panicked = false;
+    try {
+        (void)IndexedMerkleTree<T, RATE>::new_(h, std::vector<Fr>(6, Fr::from(1)));   // even, not a power of two: utils.rs:45 panics
+    } catch (const std::out_of_range&) {
+        panicked = true;
+    }
+    REQUIRE(panicked);
+    auto t = IndexedMerkleTree<T, RATE>::new_(h, std::vector<Fr>(4, Fr::from(1))).unwrap();
+    panicked = false;
+    try {
+        (void)t.get_proof(4);   // utils.rs:76 panics
+    } catch (const std::out_of_range&) {
+        panicked = true;
+    }
+    REQUIRE(panicked);
+}
+
+// the generics of utils.rs:6, 19: another instance through the same classes
+static void test_other_instance() {
+    auto h = Poseidon<4, 3>::new_(8, 56);
+    h.update({Fr::from(1), Fr::from(2)});
+    h.update({Fr::from(3)});
+    std::printf("other_instance h3 %s\n", h.squeeze_and_reset().hex().c_str());
+    std::vector<Fr> leaves;
+    for (uint64_t i = 0; i < 8; ++i) leaves.push_back(Fr::from(i));
+    auto tree = IndexedMerkleTree<4, 3>::new_(h, leaves).unwrap();
+    auto [proof, helper] = tree.get_proof(5);
+    REQUIRE(tree.verify_proof(leaves[5], 5, tree.get_root(), proof) && proof.size() == 3 && helper[0] == Fr::zero());
+    bool rejected = false;
+    try {
+        (void)Poseidon<6, 5>::new_(8, 57);
+    } catch (const Error&) {
+        rejected = true;
+    }
+    REQUIRE(rejected);
+}
+
+int main() {
+    try {
+        test_hash_zero();
+    } catch (const NoDevice& e) {
+        std::printf("no-gpu: %s\n", e.what());
+        return 3;
+    }
+    test_insert_leaf();
+    test_insert_leaf_multiple_round();
+    test_new_errors();
+    test_other_instance();
+    std::printf("all reference tests passed\n");
+    return 0;
+}
