@@ -116,6 +116,14 @@ imt_status imt_poseidon_hash_dev(imt_ctx* ctx, const void* d_in, size_t arity, s
 /* imt_trace_hashes for any input length / instance: states = n x imt_trace_fe_per_hash(arity) FE (may be NULL). */
 imt_status imt_poseidon_trace(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* digests);
 imt_status imt_poseidon_trace_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_digests);
+/* EXTENDED witness trace (optional part): besides the per-round states, the three product cells the
+ * in-circuit S-box materialises (x^2, x^4, x^5 + c — halo2-base computes x^5 + c as mul, mul, mul_add) for EVERY S-box in
+ * execution order: per permutation r_f/2 full rounds x t lanes, r_p partial rounds x 1, r_f/2 full rounds x t lanes.
+ * sbox = n x imt_trace_sbox_fe_per_hash(arity) FE (486 = 2 x 81 x 3 for <3, 2>(8, 57)); may be NULL. The column layout of
+ * halo2-base itself is not reproduced (its source is not part of the reference). */
+imt_status imt_trace_sbox_fe_per_hash(const imt_ctx* ctx, size_t arity, size_t* fe);
+imt_status imt_poseidon_trace_ext(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* sbox, void* digests);
+imt_status imt_poseidon_trace_ext_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_sbox, void* d_digests);
 /* The bare permutation on n states of t FE each, in place semantics (in -> out): what the published Poseidon test
  * vectors (poseidonperm_x5_254_3 / _5) are stated on. Not used by the tree. */
 imt_status imt_poseidon_permute(imt_ctx* ctx, const void* in_states, size_t n, void* out_states);
@@ -179,6 +187,10 @@ imt_status imt_trace_merkle_proofs_dev(imt_ctx* ctx, const void* d_leaves, const
  * to imt_tree_get_proofs followed by imt_trace_merkle_proofs on the tree's leaf hashes. */
 imt_status imt_tree_trace_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* states);
 imt_status imt_tree_trace_proofs_dev(imt_tree* tree, const uint64_t* d_indices, size_t q, void* d_states);
+/* ... with the extended S-box trace (see imt_poseidon_trace_ext): sbox[q][depth][sbox fe per hash], may be NULL. The host
+ * variant sizes its device buffers for the whole batch. */
+imt_status imt_tree_trace_proofs_ext(imt_tree* tree, const uint64_t* indices, size_t q, void* states, void* sbox);
+imt_status imt_tree_trace_proofs_ext_dev(imt_tree* tree, const uint64_t* d_indices, size_t q, void* d_states, void* d_sbox);
 
 /* ---------------------------------------------------------------- indexed-leaf logic ------------------------- */
 /* Low-leaf (predecessor) lookup, the read-only half of update_idx_leaf (src/indexed_merkle_tree.rs:632-660):

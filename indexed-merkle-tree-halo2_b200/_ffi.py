@@ -90,6 +90,11 @@ SIGNATURES = {
     "imt_poseidon_hash_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "imt_poseidon_trace": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "imt_poseidon_trace_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "imt_trace_sbox_fe_per_hash": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
+    "imt_poseidon_trace_ext": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "imt_poseidon_trace_ext_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "imt_tree_trace_proofs_ext": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_tree_trace_proofs_ext_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "imt_poseidon_permute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "imt_spec_params_host": (c_int, [c_uint, c_uint, c_uint, c_uint, c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
     "imt_calibrate_imad": (c_int, [c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -373,42 +373,69 @@ extern "C" imt_status imt_poseidon_hash3(imt_ctx* ctx, const void* in, size_t n,
 extern "C" imt_status imt_poseidon_hash2_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<2>(ctx, in, n, out); }
 extern "C" imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<3>(ctx, in, n, out); }
 
-extern "C" imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests) {
+// n traced hashes on the compute stream: tuned kernels for this context's own instance and arity 2 / 3, any-width otherwise.
+// d_sbox (may be null) receives the extended S-box trace.
+static imt_status launch_trace_hashes(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_sbox, void* d_digests) {
+    if (ctx->generic || (arity != 2 && arity != 3))
+        return launch_spec_hash(ctx, arity, d_in, d_digests, n, ctx->fmt, ctx->fmt, d_states, ctx->stream, d_sbox);
+    if (arity == 2)
+        k_trace_hash<2><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states, (uint4*)d_digests, n,
+                                                                                  ctx->fmt, ctx->d_err, (uint4*)d_sbox);
+    else
+        k_trace_hash<3><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states, (uint4*)d_digests, n,
+                                                                                  ctx->fmt, ctx->d_err, (uint4*)d_sbox);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
+static imt_status trace_hashes_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_sbox, void* d_digests) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
-    if (ctx->generic || (arity != 2 && arity != 3)) return imt_poseidon_trace_dev(ctx, d_in, (size_t)arity, n, d_states, d_digests);
-    if (n && !d_in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n && ((arity && !d_in) || (d_sbox && !d_states))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     IMT_TRY(clear_err(ctx));
-    if (arity == 2)
-        k_trace_hash<2><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states,
-                                                                                  (uint4*)d_digests, n, ctx->fmt, ctx->d_err);
-    else
-        k_trace_hash<3><<<grid_for(n, kHashThreads), kHashThreads, 0, ctx->stream>>>((const uint4*)d_in, (uint4*)d_states,
-                                                                                  (uint4*)d_digests, n, ctx->fmt, ctx->d_err);
-    ++ctx->launches;
-    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    IMT_TRY(launch_trace_hashes(ctx, d_in, arity, n, d_states, d_sbox, d_digests));
     return finish(ctx);
 }
-extern "C" imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests) {
+static imt_status trace_hashes_host(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* sbox, void* digests) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
-    if (ctx->generic || (arity != 2 && arity != 3)) return imt_poseidon_trace(ctx, in, (size_t)arity, n, states, digests);
-    if (n && !in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n && ((arity && !in) || (sbox && !states))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t state_fe = trace_fe_per_hash(ctx, (size_t)arity);  // 132 x 3 for this instance
-    DevBuf din(ctx), dst(ctx), ddg(ctx);
+    const size_t state_fe = trace_fe_per_hash(ctx, arity), sbox_fe = sbox_fe_per_hash(ctx, arity);
+    DevBuf din(ctx), dst(ctx), dsb(ctx), ddg(ctx);
     IMT_TRY_CUDA(ctx, din.alloc(n * arity * sizeof(Fr)));
     if (states) IMT_TRY_CUDA(ctx, dst.alloc(n * state_fe * sizeof(Fr)));
+    if (sbox) IMT_TRY_CUDA(ctx, dsb.alloc(n * sbox_fe * sizeof(Fr)));
     if (digests) IMT_TRY_CUDA(ctx, ddg.alloc(n * sizeof(Fr)));
-    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * arity * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    IMT_TRY(imt_trace_hashes_dev(ctx, din.p, arity, n, states ? dst.p : nullptr, digests ? ddg.p : nullptr));
+    if (arity) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * arity * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(trace_hashes_dev(ctx, din.p, arity, n, states ? dst.p : nullptr, sbox ? dsb.p : nullptr, digests ? ddg.p : nullptr));
     if (states) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, n * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sbox) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(sbox, dsb.p, n * sbox_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (digests) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(digests, ddg.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
+}
+extern "C" imt_status imt_trace_hashes_dev(imt_ctx* ctx, const void* d_in, int arity, size_t n, void* d_states, void* d_digests) {
+    if (ctx && arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
+    return trace_hashes_dev(ctx, d_in, (size_t)arity, n, d_states, nullptr, d_digests);
+}
+extern "C" imt_status imt_trace_hashes(imt_ctx* ctx, const void* in, int arity, size_t n, void* states, void* digests) {
+    if (ctx && arity < 0) return fail(ctx, IMT_ERR_INVALID_ARG, "negative arity");
+    return trace_hashes_host(ctx, in, (size_t)arity, n, states, nullptr, digests);
+}
+extern "C" imt_status imt_poseidon_trace_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_digests) {
+    return trace_hashes_dev(ctx, d_in, arity, n, d_states, nullptr, d_digests);
+}
+extern "C" imt_status imt_poseidon_trace(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* digests) {
+    return trace_hashes_host(ctx, in, arity, n, states, nullptr, digests);
+}
+extern "C" imt_status imt_poseidon_trace_ext_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_sbox,
+                                                 void* d_digests) {
+    return trace_hashes_dev(ctx, d_in, arity, n, d_states, d_sbox, d_digests);
+}
+extern "C" imt_status imt_poseidon_trace_ext(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* sbox, void* digests) {
+    return trace_hashes_host(ctx, in, arity, n, states, sbox, digests);
 }
 
 // ------------------------------------------------------------------------------------------------- tree
@@ -712,15 +739,15 @@ extern "C" imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, 
 // Witness traces of verify_merkle_proof for leaves OF THIS TREE (indexed_merkle_tree.rs:65-96 with the paths of utils.rs:63-85):
 // all operands are stored levels, so the q x depth traced hashes run independently (k_trace_tree_paths) instead of as q
 // serial folds. states[q][depth][fe per hash]; identical bytes to imt_tree_get_proofs + imt_trace_merkle_proofs.
-static imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states) {
+static imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr) {
     imt_ctx* ctx = t->ctx;
     const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
     const unsigned depth = t->depth + cap_depth;
     if (q == 0 || depth == 0) return IMT_OK;
-    if (ctx->generic) return launch_spec_tree_trace(t, d_idx, q, d_states);
+    if (ctx->generic) return launch_spec_tree_trace(t, d_idx, q, d_states, d_sbox);
     k_trace_tree_paths<<<grid_for(q * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
         (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, d_idx, q, ctx->fmt,
-        (uint4*)d_states, ctx->d_err);
+        (uint4*)d_states, ctx->d_err, (uint4*)d_sbox);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
@@ -734,6 +761,37 @@ extern "C" imt_status imt_tree_trace_proofs_dev(imt_tree* t, const uint64_t* d_i
     IMT_TRY(clear_err(ctx));
     IMT_TRY(launch_tree_trace(t, d_indices, q, d_states));
     return finish(ctx);
+}
+extern "C" imt_status imt_tree_trace_proofs_ext_dev(imt_tree* t, const uint64_t* d_indices, size_t q, void* d_states, void* d_sbox) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!d_indices || !d_states)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_tree_trace(t, d_indices, q, d_states, d_sbox));
+    return finish(ctx);
+}
+// host buffers, extended: one launch into device buffers sized for the whole batch (the S-box trace adds 15 552 B per hash;
+// cut very large batches on the caller's side or use the _dev call)
+extern "C" imt_status imt_tree_trace_proofs_ext(imt_tree* t, const uint64_t* indices, size_t q, void* states, void* sbox) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    if (q && (!indices || !states)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    const unsigned depth = t->depth + (t->cap_valid ? t->cap_depth : 0);
+    if (q == 0 || depth == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t st_bytes = q * depth * trace_fe_per_hash(ctx, 2) * sizeof(Fr), sb_bytes = q * depth * sbox_fe_per_hash(ctx, 2) * sizeof(Fr);
+    DevBuf di(ctx), dst(ctx), dsb(ctx);
+    IMT_TRY_CUDA(ctx, di.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dst.alloc(st_bytes));
+    if (sbox) IMT_TRY_CUDA(ctx, dsb.alloc(sb_bytes));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(imt_tree_trace_proofs_ext_dev(t, di.as<uint64_t>(), q, dst.p, sbox ? dsb.p : nullptr));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sbox) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(sbox, dsb.p, sb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
 }
 extern "C" imt_status imt_tree_trace_proofs(imt_tree* t, const uint64_t* indices, size_t q, void* states) {
     if (!t) return IMT_ERR_INVALID_ARG;

@@ -174,13 +174,17 @@ inline size_t spec_perms(const imt_ctx* ctx, size_t arity) { return arity / (ctx
 inline size_t trace_fe_per_hash(const imt_ctx* ctx, size_t arity) {
     return spec_perms(ctx, arity) * ctx->spec.states_per_perm() * ctx->spec.t;
 }
+// FE per hash of the extended S-box trace: (x^2, x^4, x^5 + c) for each of the r_f t + r_p S-boxes of every permutation
+inline size_t sbox_fe_per_hash(const imt_ctx* ctx, size_t arity) {
+    return spec_perms(ctx, arity) * ((size_t)ctx->spec.r_f * ctx->spec.t + ctx->spec.r_p) * 3;
+}
 // derives + uploads ctx->d_spec if it is not there yet
 imt_status ensure_spec(imt_ctx* ctx);
 // out[i] = squeeze(update(in[arity*i ..])) with the context's instance; d_states may be null
 imt_status launch_spec_hash(imt_ctx* ctx, size_t arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, void* d_states,
-                            cudaStream_t s);
+                            cudaStream_t s, void* d_sbox = nullptr);
 // witness traces of the paths of a resident tree, one thread per (query, level), with the context's instance
-imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states);
+imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr);
 // batched verify_proof / compute_merkle_root (+ trace) with the context's instance
 imt_status launch_spec_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
                             unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);

@@ -24,22 +24,33 @@ namespace imt {
 
 struct SpecNoTrace {
     __device__ __forceinline__ void emit(const uint32_t (*)[8]) {}
+    __device__ __forceinline__ void emit_sbox(const uint32_t*, const uint32_t*, const uint32_t*) {}
 };
 // every traced state = T FE in the user format, hash after hash: perms x (1 + r_f + r_p) x T FE, contiguous per hash
+// `sbox` (may be null): the extended trace, (x^2, x^4, x^5 + c) of every S-box in execution order
 template <int T>
 struct SpecTraceSink {
     uint4* dst;
     int fmt;
+    uint4* sbox = nullptr;
+    __device__ __forceinline__ void put(uint4*& p, const uint32_t* x) {
+        uint32_t t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = x[i];
+        if (fmt == kFmtCanonical) from_mont(t, t);
+        else canonicalize(t);
+        store_fe(p, t);
+        p += 2;
+    }
     __device__ __forceinline__ void emit(const uint32_t (*s)[8]) {
 #pragma unroll
-        for (int j = 0; j < T; ++j) {
-            uint32_t t[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = s[j][i];
-            if (fmt == kFmtCanonical) from_mont(t, t);
-            else canonicalize(t);
-            store_fe(dst, t);
-            dst += 2;
+        for (int j = 0; j < T; ++j) put(dst, s[j]);
+    }
+    __device__ __forceinline__ void emit_sbox(const uint32_t* x2, const uint32_t* x4, const uint32_t* u) {
+        if (sbox) {
+            put(sbox, x2);
+            put(sbox, x4);
+            put(sbox, u);
         }
     }
 };
@@ -67,13 +78,14 @@ struct SpecPairLoad {
 template <int T>
 __global__ void __launch_bounds__(kHashThreads) k_spec_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, size_t arity,
                                                             const Fr* __restrict__ P, SpecLayout L, int in_fmt, int out_fmt,
-                                                            uint4* __restrict__ states, size_t state_fe, uint32_t* __restrict__ err) {
+                                                            uint4* __restrict__ states, size_t state_fe, uint32_t* __restrict__ err,
+                                                            uint4* __restrict__ sbox, size_t sbox_fe) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= n) return;
     SpecGlobalLoad load{in + 2 * arity * i, in_fmt, true};
     uint32_t d[8];
     if (states) {
-        SpecTraceSink<T> sink{states + 2 * state_fe * i, out_fmt};
+        SpecTraceSink<T> sink{states + 2 * state_fe * i, out_fmt, sbox ? sbox + 2 * sbox_fe * i : nullptr};
         spec_sponge<T>(d, arity, load, P, L, sink);
     } else {
         SpecNoTrace nt;
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(kHashThreads) k_spec_trace_tree_paths(const ui
                                                                         size_t n_local, unsigned depth_local, unsigned cap_depth, unsigned rank,
                                                                         const uint64_t* __restrict__ idx, size_t q, const Fr* __restrict__ P,
                                                                         SpecLayout L, int fmt, uint4* __restrict__ states, size_t state_fe,
-                                                                        uint32_t* __restrict__ err) {
+                                                                        uint32_t* __restrict__ err, uint4* __restrict__ sbox, size_t sbox_fe) {
     const unsigned depth = depth_local + cap_depth;
     const size_t t = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (t >= q * depth) return;
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(kHashThreads) k_spec_trace_tree_paths(const ui
     load_fe(lo, src);
     load_fe(hi, src + 2);
     SpecPairLoad load{lo, hi};
-    SpecTraceSink<T> sink{states + 2 * state_fe * t, fmt};
+    SpecTraceSink<T> sink{states + 2 * state_fe * t, fmt, sbox ? sbox + 2 * sbox_fe * t : nullptr};
     spec_sponge<T>(d, 2, load, P, L, sink);
 }
 
@@ -213,7 +225,7 @@ imt_status ensure_spec(imt_ctx* ctx) {
     }
 
 imt_status launch_spec_hash(imt_ctx* ctx, size_t arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, void* d_states,
-                            cudaStream_t s) {
+                            cudaStream_t s, void* d_sbox) {
     if (n == 0) return IMT_OK;
     IMT_TRY(ensure_spec(ctx));
     const SpecLayout L = ctx->spec;
@@ -226,7 +238,8 @@ imt_status launch_spec_hash(imt_ctx* ctx, size_t arity, const void* d_in, void* 
         IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
     }
     IMT_SPEC_DISPATCH(L.t, (k_spec_hash<T><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>(
-                               (const uint4*)d_in, (uint4*)d_out, n, arity, ctx->d_spec, L, in_fmt, out_fmt, (uint4*)d_states, state_fe, ctx->d_err)));
+                               (const uint4*)d_in, (uint4*)d_out, n, arity, ctx->d_spec, L, in_fmt, out_fmt, (uint4*)d_states, state_fe, ctx->d_err,
+                               (uint4*)d_sbox, sbox_fe_per_hash(ctx, arity))));
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     if (timed) {
@@ -251,7 +264,7 @@ imt_status launch_spec_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* 
     return IMT_OK;
 }
 
-imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states) {
+imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox) {
     imt_ctx* ctx = t->ctx;
     IMT_TRY(ensure_spec(ctx));
     const SpecLayout L = ctx->spec;
@@ -260,7 +273,8 @@ imt_status launch_spec_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, 
     const size_t state_fe = trace_fe_per_hash(ctx, 2);
     IMT_SPEC_DISPATCH(L.t, (k_spec_trace_tree_paths<T><<<grid_for(q * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
                                (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u,
-                               d_idx, q, ctx->d_spec, L, ctx->fmt, (uint4*)d_states, state_fe, ctx->d_err)));
+                               d_idx, q, ctx->d_spec, L, ctx->fmt, (uint4*)d_states, state_fe, ctx->d_err, (uint4*)d_sbox,
+                               sbox_fe_per_hash(ctx, 2))));
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
@@ -305,6 +319,11 @@ extern "C" imt_status imt_trace_fe_per_hash(const imt_ctx* ctx, size_t arity, si
     *fe = trace_fe_per_hash(ctx, arity);
     return IMT_OK;
 }
+extern "C" imt_status imt_trace_sbox_fe_per_hash(const imt_ctx* ctx, size_t arity, size_t* fe) {
+    if (!ctx || !fe) return IMT_ERR_INVALID_ARG;
+    *fe = sbox_fe_per_hash(ctx, arity);
+    return IMT_OK;
+}
 
 // host-only: the derived parameter array of an instance (no device work; CPU tests compare it with the oracle's)
 extern "C" imt_status imt_spec_params_host(unsigned t, unsigned rate, unsigned r_f, unsigned r_p, void* out, size_t capacity_fe, size_t* count_fe) {
@@ -346,34 +365,6 @@ extern "C" imt_status imt_poseidon_hash(imt_ctx* ctx, const void* in, size_t ari
     IMT_TRY(hash_any_launch(ctx, arity, din.p, dout.p, n, nullptr));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
-}
-
-extern "C" imt_status imt_poseidon_trace_dev(imt_ctx* ctx, const void* d_in, size_t arity, size_t n, void* d_states, void* d_digests) {
-    if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (n && arity && !d_in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
-    if (n == 0) return IMT_OK;
-    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    IMT_TRY(clear_err(ctx));
-    IMT_TRY(launch_spec_hash(ctx, arity, d_in, d_digests, n, ctx->fmt, ctx->fmt, d_states, ctx->stream));
-    return finish(ctx);
-}
-
-extern "C" imt_status imt_poseidon_trace(imt_ctx* ctx, const void* in, size_t arity, size_t n, void* states, void* digests) {
-    if (!ctx) return IMT_ERR_INVALID_ARG;
-    if (n && arity && !in) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
-    if (n == 0) return IMT_OK;
-    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t state_fe = trace_fe_per_hash(ctx, arity);
-    DevBuf din(ctx), dst(ctx), ddg(ctx);
-    IMT_TRY_CUDA(ctx, din.alloc(n * arity * sizeof(Fr)));
-    if (states) IMT_TRY_CUDA(ctx, dst.alloc(n * state_fe * sizeof(Fr)));
-    if (digests) IMT_TRY_CUDA(ctx, ddg.alloc(n * sizeof(Fr)));
-    if (arity) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * arity * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    IMT_TRY(imt_poseidon_trace_dev(ctx, din.p, arity, n, states ? dst.p : nullptr, digests ? ddg.p : nullptr));
-    if (states) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(states, dst.p, n * state_fe * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-    if (digests) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(digests, ddg.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return IMT_OK;
 }
 
 extern "C" imt_status imt_poseidon_permute(imt_ctx* ctx, const void* in_states, size_t n, void* out_states) {

@@ -30,9 +30,28 @@ __global__ void __launch_bounds__(kHashThreads) k_hash(const uint4* __restrict__
 }
 
 // Writes every traced state as 3 FE in the user format. One thread owns one hash: 132 x 96 contiguous bytes.
+// `sbox` (may be null) receives the extended trace: (x^2, x^4, x^5 + c) of every S-box in execution order —
+// kSboxPerHash x 3 FE per hash, contiguous.
 struct TraceSink {
     uint4* dst;
     int fmt;
+    uint4* sbox = nullptr;
+    __device__ __forceinline__ void put(uint4*& p, const uint32_t* x) {
+        uint32_t t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = x[i];
+        if (fmt == kFmtCanonical) from_mont(t, t);
+        else canonicalize(t);
+        store_fe(p, t);
+        p += 2;
+    }
+    __device__ __forceinline__ void emit_sbox(const uint32_t* x2, const uint32_t* x4, const uint32_t* u) {
+        if (sbox) {
+            put(sbox, x2);
+            put(sbox, x4);
+            put(sbox, u);
+        }
+    }
     __device__ __forceinline__ void emit(const uint32_t (*s)[8]) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -50,7 +69,7 @@ struct TraceSink {
 template <int ARITY>
 __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __restrict__ in, uint4* __restrict__ states,
                                                              uint4* __restrict__ digests, size_t n, int fmt,
-                                                             uint32_t* __restrict__ err) {
+                                                             uint32_t* __restrict__ err, uint4* __restrict__ sbox) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= n) return;
     uint32_t x[ARITY][8], d[8];
@@ -62,7 +81,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __rest
     }
     if (!ok) atomicOr(err, kErrNonCanonical);
     if (states) {
-        TraceSink sink{states + i * (size_t)(kStatesPerHash * 3 * 2), fmt};
+        TraceSink sink{states + i * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + i * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
         hash_fixed<ARITY>(d, x, c_params, sink);
     } else {
         NoTrace nt;
@@ -176,7 +195,8 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
 __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* __restrict__ levels, const uint4* __restrict__ cap,
                                                                    size_t n_local, unsigned depth_local, unsigned cap_depth, unsigned rank,
                                                                    const uint64_t* __restrict__ idx, size_t q, int fmt,
-                                                                   uint4* __restrict__ states, uint32_t* __restrict__ err) {
+                                                                   uint4* __restrict__ states, uint32_t* __restrict__ err,
+                                                                   uint4* __restrict__ sbox) {
     const unsigned depth = depth_local + cap_depth;
     const size_t t = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (t >= q * depth) return;
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* 
     uint32_t x[2][8], d[8];
     load_fe(x[0], src);      // tree levels are Montgomery, canonical
     load_fe(x[1], src + 2);
-    TraceSink sink{states + t * (size_t)(kStatesPerHash * 3 * 2), fmt};
+    TraceSink sink{states + t * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + t * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
     hash_fixed<2>(d, x, c_params, sink);
 }
 

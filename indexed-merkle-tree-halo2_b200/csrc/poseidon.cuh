@@ -18,6 +18,8 @@ constexpr int kRP = 57;
 constexpr int kHalfF = kRF / 2;
 constexpr int kStatesPerPerm = 1 + kRF + kRP;     // 66: after the pre-add, then after every round's linear layer
 constexpr int kStatesPerHash = 2 * kStatesPerPerm;  // 132: every fixed-length hash of <= 3 inputs is 2 permutations
+constexpr int kSboxPerPerm = kRF * kT + kRP;        // 81 S-boxes per permutation: 3 per full round, 1 per partial round
+constexpr int kSboxPerHash = 2 * kSboxPerPerm;      // 162, each traced as (x^2, x^4, x^5 + c)
 
 struct PartialRound {
     Fr c;        // optimized partial-round constant (added to s0 after the S-box)
@@ -36,12 +38,16 @@ struct PoseidonParams {
     Fr one;               // 1: the padding element
 };
 
+// A trace sink sees the state after the pre-add and after every round's linear layer (emit) and, for the optional extended
+// trace of SURVEY 8a row 9, the three product cells of every S-box the chip materialises (emit_sbox: x^2, x^4, x^5 + c).
 struct NoTrace {
     IMT_HD void emit(const uint32_t (*)[8]) {}
+    IMT_HD void emit_sbox(const uint32_t*, const uint32_t*, const uint32_t*) {}
 };
 
 // u = x^5 + c   (x semi-reduced, c canonical constant; u semi-reduced)
-IMT_HD void sbox_add(uint32_t* u, const uint32_t* x, const uint32_t* c) {
+template <class Sink>
+IMT_HD void sbox_add(uint32_t* u, const uint32_t* x, const uint32_t* c, Sink& sink) {
     uint32_t x2[8], x4[8];
     mont_sqr(x2, x);
     mont_sqr(x4, x2);
@@ -51,6 +57,11 @@ IMT_HD void sbox_add(uint32_t* u, const uint32_t* x, const uint32_t* c) {
     add_hi(w, c);
     redc(u, w);       // < 4p^2/2^256 + p + p < 2.76 p
     cond_sub_2p(u);
+    sink.emit_sbox(x2, x4, u);
+}
+IMT_HD void sbox_add(uint32_t* u, const uint32_t* x, const uint32_t* c) {
+    NoTrace nt;
+    sbox_add(u, x, c, nt);
 }
 IMT_HD void sbox(uint32_t* u, const uint32_t* x) {
     uint32_t x2[8], x4[8];
@@ -83,9 +94,9 @@ IMT_HD void mul_add(uint32_t* r, const uint32_t* u, const uint32_t* m, const uin
 template <class Sink>
 IMT_HD void full_round(uint32_t (*s)[8], const Fr* c, const Fr (*m)[3], Sink& sink) {
     uint32_t u0[8], u1[8], u2[8];
-    sbox_add(u0, s[0], c[0].l);
-    sbox_add(u1, s[1], c[1].l);
-    sbox_add(u2, s[2], c[2].l);
+    sbox_add(u0, s[0], c[0].l, sink);
+    sbox_add(u1, s[1], c[1].l, sink);
+    sbox_add(u2, s[2], c[2].l, sink);
     dot3(s[0], u0, u1, u2, m[0][0].l, m[0][1].l, m[0][2].l);
     dot3(s[1], u0, u1, u2, m[1][0].l, m[1][1].l, m[1][2].l);
     dot3(s[2], u0, u1, u2, m[2][0].l, m[2][1].l, m[2][2].l);
@@ -95,7 +106,7 @@ IMT_HD void full_round(uint32_t (*s)[8], const Fr* c, const Fr (*m)[3], Sink& si
 template <class Sink>
 IMT_HD void partial_round(uint32_t (*s)[8], const PartialRound& pr, Sink& sink) {
     uint32_t u[8], n0[8];
-    sbox_add(u, s[0], pr.c.l);
+    sbox_add(u, s[0], pr.c.l, sink);
     dot3(n0, u, s[1], s[2], pr.row[0].l, pr.row[1].l, pr.row[2].l);
     mul_add(s[1], u, pr.col[0].l, s[1]);
     mul_add(s[2], u, pr.col[1].l, s[2]);
@@ -152,7 +163,7 @@ IMT_HD void permute(uint32_t (*s)[8], const PoseidonParams& P, Sink& sink) {
 #pragma unroll 1
         for (int j = 0; j < lanes; ++j) {
             const uint32_t* c = full ? P.full[fr][j].l : P.partial[pk].c.l;
-            sbox_add(s[0], s[0], c);
+            sbox_add(s[0], s[0], c, sink);
             if (full) rotate3(s);  // three rotations bring the lanes back in order
         }
         // ---- linear layer: dense 3x3 (full rounds) or sparse (row . s ; s_i + col_i * s0)

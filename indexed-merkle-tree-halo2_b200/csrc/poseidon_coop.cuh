@@ -27,6 +27,7 @@ __device__ __forceinline__ void shfl_fe(uint32_t* d, const uint32_t* s, int src_
 struct NoCoopTrace {
     __device__ __forceinline__ void emit(const uint32_t*, int) {}
 };
+// (the extended S-box trace is produced by the one-thread-per-hash kernels only)
 // Witness-trace sink of the cooperative kernels: lane r writes element r of every traced state (3 x 32 contiguous bytes
 // per state from the three lanes of a quad).
 struct CoopTraceSink {

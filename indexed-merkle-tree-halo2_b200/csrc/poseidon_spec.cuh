@@ -46,7 +46,8 @@ __device__ __forceinline__ void spec_load_const(uint32_t* x, const Fr* p) {
 }
 
 // u = x^5 + c
-__device__ __forceinline__ void spec_sbox_add(uint32_t* u, const uint32_t* x, const Fr* c) {
+template <class Sink>
+__device__ __forceinline__ void spec_sbox_add(uint32_t* u, const uint32_t* x, const Fr* c, Sink& sink) {
     uint32_t x2[8], x4[8], cc_[8];
     spec_load_const(cc_, c);
     mont_sqr(x2, x);
@@ -57,6 +58,7 @@ __device__ __forceinline__ void spec_sbox_add(uint32_t* u, const uint32_t* x, co
     add_hi(w, cc_);
     redc(u, w);
     cond_sub_2p(u);
+    sink.emit_sbox(x2, x4, u);
 }
 
 // r = sum_k row[k] * s[k], one reduction (row canonical constants, s semi-reduced): < 2 T p^2 / 2^256 + p < 4p for T <= 7
@@ -122,7 +124,7 @@ __device__ __forceinline__ void spec_permute(uint32_t (*s)[8], const Fr* __restr
         const unsigned lanes = full ? T : 1;
 #pragma unroll 1
         for (unsigned j = 0; j < lanes; ++j) {
-            spec_sbox_add(s[0], s[0], full ? P + L.full(fr, j) : P + L.partial_c(pk));
+            spec_sbox_add(s[0], s[0], full ? P + L.full(fr, j) : P + L.partial_c(pk), sink);
             if (full) spec_rotate<T>(s);  // T rotations bring the lanes back in order
         }
         // ---- linear layer: dense T x T (full rounds) or sparse (row . s ; s_j + col_j * s0)

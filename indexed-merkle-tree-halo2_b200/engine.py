@@ -181,6 +181,20 @@ class Engine:
         self._check(self._lib.imt_trace_hashes(self._h, _ptr(a), arity, n, _ptr(states), _ptr(digests)))
         return digests, states
 
+    def sbox_cells_per_hash(self, arity):
+        """S-boxes of one hash of `arity` inputs (each traced as 3 FE: x^2, x^4, x^5 + c) in the extended trace"""
+        return (arity // self.rate + 1) * (self.r_f * self.t + self.r_p)
+
+    def trace_hashes_ext(self, inputs, arity):
+        """trace_hashes + the extended S-box trace: (digests, states, sbox[n, S-boxes per hash, 3, 4])"""
+        a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, arity, 4)
+        n = a.shape[0]
+        states = np.empty((n, self.states_per_hash(arity), self.t, 4), np.uint64)
+        sbox = np.empty((n, self.sbox_cells_per_hash(arity), 3, 4), np.uint64)
+        digests = np.empty((n, 4), np.uint64)
+        self._check(self._lib.imt_poseidon_trace_ext(self._h, _ptr(a), arity, n, _ptr(states), _ptr(sbox), _ptr(digests)))
+        return digests, states, sbox
+
     def trace_hashes_dev(self, d_in, arity, n, d_states, d_digests):
         self._check(self._lib.imt_trace_hashes_dev(self._h, _dev_ptr(d_in), arity, n,
                                                    _dev_ptr(d_states) if d_states is not None else None,
@@ -435,6 +449,15 @@ class Tree:
         states = out_states if out_states is not None else np.empty(shape, np.uint64)
         self.engine._check(self._lib.imt_tree_trace_proofs(self._h, _ptr(idx), q, _ptr(states)))
         return states
+
+    def trace_proofs_ext(self, indices):
+        """trace_proofs + the extended S-box trace: (states, sbox[q, depth, S-boxes per hash, 3, 4])"""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q, e = idx.shape[0], self.engine
+        states = np.empty((q, self.depth, e.states_per_hash(2), e.t, 4), np.uint64)
+        sbox = np.empty((q, self.depth, e.sbox_cells_per_hash(2), 3, 4), np.uint64)
+        e._check(self._lib.imt_tree_trace_proofs_ext(self._h, _ptr(idx), q, _ptr(states), _ptr(sbox)))
+        return states, sbox
 
     def trace_proofs_dev(self, d_indices, q, d_states):
         self.engine._check(self._lib.imt_tree_trace_proofs_dev(self._h, _dev_ptr(d_indices), q, _dev_ptr(d_states)))

@@ -195,33 +195,43 @@ def permute_naive(state, sp=None):
     return s
 
 
-def permute_trace(state, sp=None):
+def permute_trace(state, sp=None, sbox_out=None):
     """Optimized schedule (pse-poseidon permutation.rs, same as halo2-base's in-circuit hasher).
 
     Returns (final_state, states) where states is the 66-entry witness trace of SURVEY §8a row 9:
-    [after the pre-constant add] + [after the linear layer of each of the 4+57+4 rounds]."""
+    [after the pre-constant add] + [after the linear layer of each of the 4+57+4 rounds].
+    sbox_out (optional list) receives the extended trace: (x^2, x^4, x^5 + c) of every S-box in execution order."""
     sp = sp or spec()
     half = sp.r_f // 2
+
+    def sb(x, c):
+        x2 = x * x % P
+        x4 = x2 * x2 % P
+        u = (x4 * x + c) % P
+        if sbox_out is not None:
+            sbox_out.append((x2, x4, u))
+        return u
+
     s = [(x + c) % P for x, c in zip(state, sp.start[0])]
     out = [list(s)]
     for i in range(1, half):
-        s = [(sbox(x) + c) % P for x, c in zip(s, sp.start[i])]
+        s = [sb(x, c) for x, c in zip(s, sp.start[i])]
         s = mat_vec(sp.mds, s)
         out.append(list(s))
-    s = [(sbox(x) + c) % P for x, c in zip(s, sp.start[half])]
+    s = [sb(x, c) for x, c in zip(s, sp.start[half])]
     s = mat_vec(sp.pre_sparse, s)
     out.append(list(s))
     for k in range(sp.r_p):
         row, col_hat = sp.sparse[k]
-        s0 = (sbox(s[0]) + sp.partial[k]) % P
+        s0 = sb(s[0], sp.partial[k])
         v = [s0] + s[1:]
         s = [sum(r * x for r, x in zip(row, v)) % P] + [(col_hat[i - 1] * s0 + v[i]) % P for i in range(1, sp.t)]
         out.append(list(s))
     for i in range(half - 1):
-        s = [(sbox(x) + c) % P for x, c in zip(s, sp.end[i])]
+        s = [sb(x, c) for x, c in zip(s, sp.end[i])]
         s = mat_vec(sp.mds, s)
         out.append(list(s))
-    s = [sbox(x) for x in s]
+    s = [sb(x, 0) for x in s]
     s = mat_vec(sp.mds, s)
     out.append(list(s))
     return s, out
@@ -275,8 +285,9 @@ def hash_n(inputs, sp=None):
     return h.squeeze_and_reset()
 
 
-def hash_trace_n(inputs, sp=None):
-    """digest + every traced state ((len // rate + 1) x (1 + r_f + r_p) states of t values) of one hash, any instance"""
+def hash_trace_n(inputs, sp=None, sbox_out=None):
+    """digest + every traced state ((len // rate + 1) x (1 + r_f + r_p) states of t values) of one hash, any instance;
+    sbox_out (optional list) receives the extended S-box trace of all permutations"""
     sp = sp or spec()
     rate = sp.t - 1
     s = [1 << 64] + [0] * rate
@@ -289,7 +300,7 @@ def hash_trace_n(inputs, sp=None):
             chunk = chunk + [1]
         for j, e in enumerate(chunk):
             s[1 + j] = (s[1 + j] + e) % P
-        s, tr = permute_trace(s, sp)
+        s, tr = permute_trace(s, sp, sbox_out)
         states += tr
         if last:
             return s[1], states

@@ -107,6 +107,55 @@ def test_witness_trace_matches_the_oracle(t, r_f, r_p):
             assert ints(st[i]) == [v for stt in ws for v in stt]
 
 
+def _flat_sbox(cells):
+    return [v for c in cells for v in c]
+
+
+def test_extended_sbox_trace_matches_the_oracle():
+    """SURVEY 8a row 9, optional part: (x^2, x^4, x^5 + c) of every S-box, tuned kernels (arity 2 / 3, both formats), the
+    any-width kernels (other arities, other instances) and the tree-path trace"""
+    tuned = imt_b200.Engine(0, "canonical")
+    mont = imt_b200.Engine(0, "montgomery")
+    R256 = 1 << 256
+    for arity in (2, 3, 5):
+        x = synth.field_elements(arity * 3, seed=40 + arity).reshape(3, arity, 4)
+        dg, st, sb = tuned.trace_hashes_ext(x, arity)
+        assert sb.shape == (3, (arity // 2 + 1) * 81, 3, 4)
+        xm = imt_b200.fes_from_ints([v * R256 % P for v in ints(x)]).reshape(3, arity, 4)
+        dgm, stm, sbm = mont.trace_hashes_ext(xm, arity)
+        for i in range(3):
+            cells = []
+            wd, ws = R.hash_trace_n(ints(x[i]), None, cells)
+            assert imt_b200.fe_to_int(dg[i]) == wd and ints(st[i]) == [v for s_ in ws for v in s_]
+            assert ints(sb[i]) == _flat_sbox(cells), arity
+            assert ints(sbm[i]) == [v * R256 % P for v in _flat_sbox(cells)]
+        d0, s0 = tuned.trace_hashes(x, arity)                      # the plain trace is unchanged by the extension
+        assert np.array_equal(d0, dg) and np.array_equal(s0, st)
+    g = engine(4, 8, 56)
+    sp = spec(4, 8, 56)
+    x = synth.field_elements(6, seed=3).reshape(2, 3, 4)
+    dg, st, sb = g.trace_hashes_ext(x, 3)
+    assert sb.shape == (2, 8 * 4 + 56, 3, 4)
+    for i in range(2):
+        cells = []
+        wd, ws = R.hash_trace_n(ints(x[i]), sp, cells)
+        assert imt_b200.fe_to_int(dg[i]) == wd and ints(sb[i]) == _flat_sbox(cells)
+    # tree paths: every (query, level) hash with its S-box cells
+    n = 16
+    leaves = synth.field_elements(n, seed=9)
+    for e, sp_ in ((tuned, None), (g, sp)):
+        t = e.build_from_hashes(leaves)
+        idx = np.array([0, 5, 15], np.uint64)
+        st, sb = t.trace_proofs_ext(idx)
+        assert np.array_equal(st, t.trace_proofs(idx))
+        for k, i in enumerate(idx):
+            for lvl in range(4):
+                pair = ints(t.level(lvl, n >> lvl)[(int(i) >> lvl) & ~1:][:2])
+                cells = []
+                R.hash_trace_n(pair, sp_, cells)
+                assert ints(sb[k, lvl]) == _flat_sbox(cells), (k, lvl)
+
+
 @pytest.mark.parametrize("t,r_f,r_p", [(2, 8, 56), (4, 8, 56), (5, 8, 60)])
 def test_tree_paths_folds_and_inserts_with_another_instance(t, r_f, r_p):
     """the whole tree API on an any-width context: the mirror of the reference's test_insert_leaf_multiple_round
