@@ -24,10 +24,10 @@ __device__ __forceinline__ void shfl_fe(uint32_t* d, const uint32_t* s, int src_
     for (int i = 0; i < 8; ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
 }
 
+// (the extended S-box trace is produced by the one-thread-per-hash kernels only)
 struct NoCoopTrace {
     __device__ __forceinline__ void emit(const uint32_t*, int) {}
 };
-// (the extended S-box trace is produced by the one-thread-per-hash kernels only)
 // Witness-trace sink of the cooperative kernels: lane r writes element r of every traced state (3 x 32 contiguous bytes
 // per state from the three lanes of a quad).
 struct CoopTraceSink {
