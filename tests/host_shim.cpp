@@ -46,6 +46,7 @@ void shim_mul_wide_merged(uint32_t* out16, const uint32_t* a, const uint32_t* b)
 }
 struct Collect {
     uint32_t* dst;
+    uint32_t* sbox = nullptr;  // optional: the extended S-box trace, (x^2, x^4, x^5 + c) per S-box
     void emit(const uint32_t (*s)[8]) {
         for (int i = 0; i < 3; ++i) {
             uint32_t t[8];
@@ -54,16 +55,29 @@ struct Collect {
             dst += 8;
         }
     }
+    void emit_sbox(const uint32_t* x2, const uint32_t* x4, const uint32_t* u) {
+        if (!sbox) return;
+        const uint32_t* v[3] = {x2, x4, u};
+        for (int i = 0; i < 3; ++i) {
+            uint32_t t[8];
+            for (int j = 0; j < 8; ++j) t[j] = v[i][j];
+            from_mont(sbox, t);
+            sbox += 8;
+        }
+    }
 };
-// canonical in (arity x 8 words) -> canonical digest; states (132 x 3 x 8 words, canonical) optional
-void shim_hash(uint32_t* out, const uint32_t* in, int arity, uint32_t* states) {
+// canonical in (arity x 8 words) -> canonical digest; states (132 x 3 x 8 words, canonical) optional;
+// sbox (162 x 3 x 8 words, canonical) optional, only with states
+void shim_hash_ext(uint32_t* out, const uint32_t* in, int arity, uint32_t* states, uint32_t* sbox);
+void shim_hash(uint32_t* out, const uint32_t* in, int arity, uint32_t* states) { shim_hash_ext(out, in, arity, states, nullptr); }
+void shim_hash_ext(uint32_t* out, const uint32_t* in, int arity, uint32_t* states, uint32_t* sbox) {
     uint32_t m[3][8], d[8];
     for (int i = 0; i < arity; ++i) {
         to_mont(m[i], in + 8 * i);
         cond_sub_p(m[i]);
     }
     if (states) {
-        Collect c{states};
+        Collect c{states, sbox};
         if (arity == 3) hash_fixed<3>(d, m, params(), c); else hash_fixed<2>(d, m, params(), c);
     } else {
         NoTrace n;

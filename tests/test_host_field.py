@@ -152,6 +152,11 @@ def test_hash_and_trace(shim):
         assert [iv(st[8 * i:8 * i + 8]) for i in range(396)] == [v for s_ in tr for v in s_]
         shim.shim_hash(p_(out), p_(I), ar, None)
         assert iv(out) == d
+        sb = np.zeros(162 * 3 * 8, np.uint32)                    # extended trace: (x^2, x^4, x^5 + c) of all 162 S-boxes
+        shim.shim_hash_ext(p_(out), p_(I), ar, p_(st), p_(sb))
+        cells = []
+        R.hash_trace_n(x, None, cells)
+        assert iv(out) == d and [iv(sb[8 * i:8 * i + 8]) for i in range(486)] == [v for c in cells for v in c]
     I = np.concatenate([w(0)] * 3)
     shim.shim_hash(p_(out), p_(I), 3, None)
     assert iv(out) == R.KAT_H3_ZERO  # /root/reference/src/indexed_merkle_tree.rs:247-251
