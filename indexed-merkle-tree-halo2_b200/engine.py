@@ -512,15 +512,31 @@ class Tree:
                                                              _ptr(o["is_largest"])))
         return o
 
-    def insert_batch(self, new_vals, first_idx=None):
+    @staticmethod
+    def insert_buffers(b, depth, pinned=False):
+        """output buffers of insert_batch for b inserts (see non_inclusion_buffers for `pinned`)"""
+        shapes = dict(old_roots=((b, 4), np.uint64), low_idx=((b,), np.uint64), low_leaves=((b, 3, 4), np.uint64),
+                      low_siblings=((b, depth, 4), np.uint64), low_helpers=((b, depth), np.uint8), new_roots=((b, 4), np.uint64),
+                      new_leaves=((b, 3, 4), np.uint64), new_siblings=((b, depth, 4), np.uint64), new_helpers=((b, depth), np.uint8),
+                      is_largest=((b,), np.uint8))
+        if not pinned:
+            return {k: np.empty(sh, dt) for k, (sh, dt) in shapes.items()}
+        import torch
+        keep = {k: torch.empty(sh, dtype=torch.int64 if dt == np.uint64 else torch.uint8, pin_memory=True) for k, (sh, dt) in shapes.items()}
+        out = {k: (t.numpy().view(np.uint64) if shapes[k][1] == np.uint64 else t.numpy()) for k, t in keep.items()}
+        out["_pinned"] = keep
+        return out
+
+    def insert_batch(self, new_vals, first_idx=None, out=None):
+        """imt_insert_batch: the tree advances by the whole batch; returns every per-insert witness insert_leaf loads
+        (IMT:444-489). out: buffers from insert_buffers() to fill instead of allocating new arrays."""
         v = _fe_array(new_vals, ())
         if first_idx is None:
             first_idx = self.occupied
         b, d = v.shape[0], self.depth
-        o = dict(old_roots=np.empty((b, 4), np.uint64), low_idx=np.empty(b, np.uint64), low_leaves=np.empty((b, 3, 4), np.uint64),
-                 low_siblings=np.empty((b, d, 4), np.uint64), low_helpers=np.empty((b, d), np.uint8),
-                 new_roots=np.empty((b, 4), np.uint64), new_leaves=np.empty((b, 3, 4), np.uint64),
-                 new_siblings=np.empty((b, d, 4), np.uint64), new_helpers=np.empty((b, d), np.uint8), is_largest=np.empty(b, np.uint8))
+        o = out if out is not None else self.insert_buffers(b, d)
+        if o["low_siblings"].shape != (b, d, 4):
+            raise ValueError("out buffers were made for another batch size / depth")
         w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
         self.engine._check(self._lib.imt_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
         return o
