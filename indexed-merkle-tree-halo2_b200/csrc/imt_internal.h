@@ -72,7 +72,10 @@ namespace imt {
 
 constexpr int kFmtCanonical = 0;
 constexpr int kFmtMontgomery = 1;
-constexpr int kHashThreads = 128;
+#ifndef IMT_HASH_THREADS
+#define IMT_HASH_THREADS 128  // swept 64 / 128 / 256
+#endif
+constexpr int kHashThreads = IMT_HASH_THREADS;
 
 // bits of imt_ctx::d_err
 constexpr uint32_t kErrNonCanonical = 1u;   // an input FE >= p

@@ -10,8 +10,14 @@ namespace imt {
 
 // out[i] = H(in[ARITY*i .. ARITY*i + ARITY)). in_fmt/out_fmt select canonical <-> Montgomery conversion at the
 // edges; tree levels are Montgomery on both sides.
+// Occupancy hint of the throughput kernels: 7 blocks of 128 threads per SM = 72 registers per thread and 7 warps per
+// scheduler (with 48-96 bytes of spill) instead of the 92 registers / 5 warps ptxas picks on its own. Swept on the depth-24
+// build: 1 -> 62.0, 6 -> 62.4, 7 -> 62.8, 8 -> 61.9 M hashes/s; 64-thread blocks x 14 -> 62.7.
+#ifndef IMT_HASH_MIN_BLOCKS
+#define IMT_HASH_MIN_BLOCKS 7
+#endif
 template <int ARITY>
-__global__ void __launch_bounds__(kHashThreads) k_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
+__global__ void __launch_bounds__(kHashThreads, IMT_HASH_MIN_BLOCKS) k_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
                                                        int in_fmt, int out_fmt, uint32_t* __restrict__ err) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= n) return;
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
     }
 }
 
+// (no occupancy hint here: with 7 / 6 blocks per SM the trace sink spills and the kernel drops from 60.6 to 58.1 / 60.0 M hashes/s)
 // Witness traces of verify_merkle_proof (indexed_merkle_tree.rs:65-96) for paths of a tree that is resident on the device:
 // hash l of the fold for leaf index g is H(level[l][2k], level[l][2k+1]) with k = g >> (l + 1), and both operands are already
 // stored — so the q x depth hashes are INDEPENDENT. One thread per (query, level): a 2^16-path batch runs 1.5 M threads at
