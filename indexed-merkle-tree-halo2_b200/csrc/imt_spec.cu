@@ -75,8 +75,12 @@ struct SpecPairLoad {
 };
 
 // out[i] = H(in[arity*i .. arity*i + arity)); `states` (optional) receives the witness trace of every hash
+// occupancy hint per width (same reasoning as k_hash, kernels.cuh): blocks of 128 threads per SM
+#ifndef IMT_SPEC_MIN_BLOCKS
+#define IMT_SPEC_MIN_BLOCKS(T) ((T) <= 2 ? 7 : (T) == 3 ? 6 : (T) == 4 ? 5 : 4)
+#endif
 template <int T>
-__global__ void __launch_bounds__(kHashThreads) k_spec_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, size_t arity,
+__global__ void __launch_bounds__(kHashThreads, IMT_SPEC_MIN_BLOCKS(T)) k_spec_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, size_t arity,
                                                             const Fr* __restrict__ P, SpecLayout L, int in_fmt, int out_fmt,
                                                             uint4* __restrict__ states, size_t state_fe, uint32_t* __restrict__ err,
                                                             uint4* __restrict__ sbox, size_t sbox_fe) {
