@@ -138,12 +138,13 @@ imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
 // Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed.
 imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
     imt_ctx* ctx = t->ctx;
-    const size_t chunk = (size_t)1 << 19;  // 512 Ki leaves = 48 MiB per copy
+    const size_t max_chunk = (size_t)1 << 19;  // 512 Ki leaves = 48 MiB per copy
+    size_t chunk = (size_t)1 << 16;            // the first copy is the only exposed one: start small (6 MiB), double up to 48 MiB
     const char* src = static_cast<const char*>(preimages);
     Event copied;  // re-recorded per chunk: cudaStreamWaitEvent captures the record that precedes it
     IMT_TRY_CUDA(ctx, copied.create());
     imt_status st = IMT_OK;
-    for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk) {
+    for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk, chunk = chunk < max_chunk ? 2 * chunk : max_chunk) {
         const size_t cnt = (t->n - off < chunk) ? t->n - off : chunk;
         cudaError_t e = cudaMemcpyAsync(t->d_pre + 3 * off, src + 3 * off * sizeof(Fr), 3 * cnt * sizeof(Fr),
                                         cudaMemcpyHostToDevice, ctx->copy_stream);
