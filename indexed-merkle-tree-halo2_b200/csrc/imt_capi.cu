@@ -135,30 +135,48 @@ imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
     return IMT_OK;
 }
 
-// Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed.
+// Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed. The chunk kernels alternate between
+// the compute stream and the auxiliary one: on a single stream every chunk boundary drains the GPU (the last blocks of chunk
+// k run alone for up to one block time before chunk k+1 may start), ~0.25 ms x 32 chunks at depth 24.
 imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
     imt_ctx* ctx = t->ctx;
     const size_t max_chunk = (size_t)1 << 19;  // 512 Ki leaves = 48 MiB per copy
     size_t chunk = (size_t)1 << 16;            // the first copy is the only exposed one: start small (6 MiB), double up to 48 MiB
     const char* src = static_cast<const char*>(preimages);
-    Event copied;  // re-recorded per chunk: cudaStreamWaitEvent captures the record that precedes it
+    Event copied, forked, joined;  // `copied` is re-recorded per chunk: cudaStreamWaitEvent captures the record that precedes it
     IMT_TRY_CUDA(ctx, copied.create());
+    IMT_TRY_CUDA(ctx, forked.create());
+    IMT_TRY_CUDA(ctx, joined.create());
+    IMT_TRY_CUDA(ctx, cudaEventRecord(forked, ctx->stream));  // the auxiliary stream starts after whatever precedes this call
+    IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, forked, 0));
+    cudaStream_t lanes[2] = {ctx->stream, ctx->aux_stream};
     imt_status st = IMT_OK;
-    for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk, chunk = chunk < max_chunk ? 2 * chunk : max_chunk) {
+    size_t k = 0;
+    for (size_t off = 0; off < t->n && st == IMT_OK; off += chunk, chunk = chunk < max_chunk ? 2 * chunk : max_chunk, ++k) {
         const size_t cnt = (t->n - off < chunk) ? t->n - off : chunk;
+        cudaStream_t lane = lanes[k & 1];
         cudaError_t e = cudaMemcpyAsync(t->d_pre + 3 * off, src + 3 * off * sizeof(Fr), 3 * cnt * sizeof(Fr),
                                         cudaMemcpyHostToDevice, ctx->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(copied, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, copied, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(lane, copied, 0);
         if (e != cudaSuccess) {
             ctx->last_error = std::string("leaf staging: ") + cudaGetErrorString(e);
             st = IMT_ERR_CUDA;
             break;
         }
-        st = launch_hash_t<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, ctx->stream);
+        st = launch_hash_t<3>(ctx, t->d_pre + 3 * off, t->d_levels + off, cnt, ctx->fmt, kFmtMontgomery, lane);
+    }
+    cudaError_t e = cudaEventRecord(joined, ctx->aux_stream);  // the levels above (compute stream) need every chunk
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, joined, 0);
+    if (e != cudaSuccess && st == IMT_OK) {
+        ctx->last_error = std::string("leaf staging: ") + cudaGetErrorString(e);
+        st = IMT_ERR_CUDA;
     }
     cudaStreamSynchronize(ctx->copy_stream);  // the caller's buffer is free again when this returns
-    if (st != IMT_OK) cudaStreamSynchronize(ctx->stream);
+    if (st != IMT_OK) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
     return st;
 }
 
@@ -267,6 +285,7 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_err, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_params, sizeof(PoseidonParams));
@@ -288,6 +307,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     drain_timing(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_spec) cudaFree(ctx->d_spec);

@@ -21,6 +21,8 @@ struct imt_ctx {
     cudaStream_t stream = nullptr;       // compute (own_stream unless the caller supplied one)
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
+    cudaStream_t aux_stream = nullptr;   // second compute stream: consecutive chunk kernels of a pipelined call alternate between
+                                         // `stream` and this one so that chunk k+1 fills the SMs while chunk k drains
     uint32_t* d_err = nullptr;           // device error bits, see kErr*
     uint32_t* h_err = nullptr;           // pinned mirror
     imt::PoseidonParams* d_params = nullptr;  // global-memory copy of the parameters (lane-dependent reads of the cooperative kernel)
