@@ -28,7 +28,11 @@ using namespace imt_host;
 
 namespace {
 
-constexpr size_t kInsertChunk = 4096;  // inserts resolved together (the pairwise scans below are O(chunk^2))
+// Inserts resolved together. Every level of a chunk is ONE launch of 2 x chunk hashes, so larger chunks amortise the hash
+// latency of the `depth` dependent levels better (32768 inserts at depth 24: 357 k inserts/s with chunks of 4096, 434 k with
+// 8192, 488 k with 16384) until the O(chunk^2) sibling-link scan takes over. IMT_INSERT_CHUNK overrides it (tests, A/B).
+constexpr size_t kInsertChunk = 16384;
+constexpr size_t kShardInsertRound = 4096;  // inserts per round of the sharded insert calls (host-side plan arrays)
 
 __device__ __forceinline__ int cmp256(const uint32_t* a, const uint32_t* b) {
 #pragma unroll
@@ -858,7 +862,9 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
 
     lap("validate");
     // ---- per-chunk scratch
-    const size_t C = std::min(b, kInsertChunk), W = 2 * C, L = depth + 1;
+    const char* chunk_env = std::getenv("IMT_INSERT_CHUNK");  // read per call: tests force small chunks to cross chunk boundaries
+    const size_t chunk_override = chunk_env ? (size_t)std::strtoull(chunk_env, nullptr, 10) : 0;
+    const size_t C = std::min(b, chunk_override ? chunk_override : kInsertChunk), W = 2 * C, L = depth + 1;
     DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx), pairs(ctx);
     IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
@@ -1078,7 +1084,7 @@ extern "C" imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leav
 }
 
 // ------------------------------------------------------------------------------------------------- sharded inserts
-// An insert batch over a subtree-sharded tree (one process per GPU), at most kInsertChunk inserts per round of calls:
+// An insert batch over a subtree-sharded tree (one process per GPU), at most kShardInsertRound inserts per round of calls:
 //   1. every rank   imt_shard_insert_neighbors   neighbours of each value in the rank's own sorted index
 //   2. all-gather of the five arrays; every rank  imt_shard_insert_plan  -> the replicated plan: write slots x[2b]
 //      (GLOBAL), the preimages every write stores (upd), the low leaves before, is_largest
@@ -1125,7 +1131,7 @@ extern "C" imt_status imt_shard_insert_plan(imt_ctx* ctx, const void* values, si
     if (!ctx) return IMT_ERR_INVALID_ARG;
     if (b && (!values || !pred_keys || !pred_slots || !succ_keys || !succ_slots || !flags || !x || !upd || !low_old || !is_largest))
         return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
-    if (b > kInsertChunk || world == 0) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (b > kShardInsertRound || world == 0) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
     if (b == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t g = (size_t)world * b;
@@ -1167,7 +1173,7 @@ extern "C" imt_status imt_shard_insert_apply(imt_tree* t, const uint64_t* x, con
     if (!t) return IMT_ERR_INVALID_ARG;
     imt_ctx* ctx = t->ctx;
     if (b && (!x || !upd || !sub_roots || !sib_local)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
-    if (b > kInsertChunk) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (b > kShardInsertRound) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
     if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
     IMT_TRY(ensure_index(t));
     const unsigned depth = t->depth;
@@ -1253,7 +1259,7 @@ extern "C" imt_status imt_shard_insert_cap(imt_tree* t, const uint64_t* x, const
     if (!t) return IMT_ERR_INVALID_ARG;
     imt_ctx* ctx = t->ctx;
     if (b && (!x || !sub_roots || !roots)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
-    if (b > kInsertChunk) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
+    if (b > kShardInsertRound) return fail(ctx, IMT_ERR_INVALID_ARG, "at most 4096 inserts per round of sharded insert calls");
     if (!t->cap_valid) return fail(ctx, IMT_ERR_INVALID_ARG, "no cap attached: exchange the subtree roots first");
     if (b == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -142,10 +142,13 @@ def test_non_inclusion_witnesses(eng):
     assert ok.all()
 
 
-@pytest.mark.parametrize("depth,m,b", [(6, 10, 40), (10, 512, 300), (13, 3000, 4200)])
-def test_insert_batch_matches_sequential_oracle(eng, depth, m, b):
-    """b inserts in one call (b > 4096 crosses the internal chunking) against the oracle advancing one insert at a
-    time; then the device state (preimages, every level, index) against the oracle's final state."""
+@pytest.mark.parametrize("depth,m,b,chunk", [(6, 10, 40, None), (10, 512, 300, 128), (13, 3000, 4200, None), (13, 3000, 4200, 4096)])
+def test_insert_batch_matches_sequential_oracle(eng, depth, m, b, chunk, monkeypatch):
+    """b inserts in one call against the oracle advancing one insert at a time; then the device state (preimages, every
+    level, index) against the oracle's final state. `chunk` forces the internal chunking (default 16384 inserts) so that
+    the batch crosses chunk boundaries."""
+    if chunk:
+        monkeypatch.setenv("IMT_INSERT_CHUNK", str(chunk))
     n = 1 << depth
     pre = synth.indexed_preimages(n, m, seed=depth)
     tree = eng.build_from_leaves(pre)
@@ -248,6 +251,35 @@ def test_non_inclusion_limbs_edge_values(eng, eng_mont):
         bad[0, 3] = np.uint64(0xFFFFFFFFFFFFFFFF)                                # >= p
         eng.non_inclusion_limbs(low, bad)
     assert ex.value.status == _ffi.ERR_NON_CANONICAL
+
+
+def test_insert_batch_is_independent_of_the_chunking(eng, monkeypatch):
+    """the same 9000 inserts with chunks of 16384 (one chunk), 4096 and 1000: identical witnesses and final state"""
+    depth, m, b = 15, 20000, 9000
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, m, seed=61)
+    vals = synth.field_elements(b, seed=62)
+    results = []
+    for chunk in (None, 4096, 1000):
+        if chunk:
+            monkeypatch.setenv("IMT_INSERT_CHUNK", str(chunk))
+        else:
+            monkeypatch.delenv("IMT_INSERT_CHUNK", raising=False)
+        tree = eng.build_from_leaves(pre)
+        w = tree.insert_batch(vals, m)
+        results.append((w, tree.root().copy(), tree.preimages(n)))
+        tree.close()
+    w0, r0, p0 = results[0]
+    for w, r, p in results[1:]:
+        assert np.array_equal(r, r0) and np.array_equal(p, p0)
+        for k in w0:
+            assert np.array_equal(np.asarray(w[k]), np.asarray(w0[k])), k
+    st = O.InsertState(pre, threads=8)                       # and against the oracle, one insert at a time
+    for k in range(b):
+        want = st.insert(vals[k], m + k, incremental=True)
+        if k % 251 == 0 or k == b - 1:
+            assert_witness_equal(w0, k, want)
+    assert np.array_equal(r0, st.root())
 
 
 def test_insert_errors_leave_the_tree_untouched(eng):
@@ -436,8 +468,10 @@ def test_insert_batch_adversarial_orders(eng, pattern):
     assert np.array_equal(tree.preimages(n), st.pre) and np.array_equal(tree.root(), st.root())
 
 
-def test_insert_batch_chunk_boundary_and_single_inserts(eng):
-    """4097 inserts = one full internal chunk + 1; then single-insert calls; then the tree filled to the last slot."""
+def test_insert_batch_chunk_boundary_and_single_inserts(eng, monkeypatch):
+    """4097 inserts = one full internal chunk + 1 (chunks forced to 4096); then single-insert calls; then the tree filled to
+    the last slot."""
+    monkeypatch.setenv("IMT_INSERT_CHUNK", "4096")
     depth = 13
     n = 1 << depth
     m = n - 4097 - 3
