@@ -11,6 +11,7 @@
 // a batch costs `depth` launches instead of B full rebuilds, and yields the same roots and paths as the reference's
 // sequence of rebuilds (checked against the oracle's restatement of that sequence).
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -29,9 +30,10 @@ using namespace imt_host;
 namespace {
 
 // Inserts resolved together. Every level of a chunk is ONE launch of 2 x chunk hashes, so larger chunks amortise the hash
-// latency of the `depth` dependent levels better (32768 inserts at depth 24: 357 k inserts/s with chunks of 4096, 434 k with
-// 8192, 488 k with 16384) until the O(chunk^2) sibling-link scan takes over. IMT_INSERT_CHUNK overrides it (tests, A/B).
-constexpr size_t kInsertChunk = 16384;
+// latency of the `depth` dependent levels better (depth 24, 131072 inserts: 381 k inserts/s with chunks of 4096, 775 k with
+// 16384, 858 k with 32768, see DESIGN.md for 65536); scratch is 25 x 2 x chunk field elements (105 MB at 65536).
+// IMT_INSERT_CHUNK overrides it (tests, A/B).
+constexpr size_t kInsertChunk = 65536;
 constexpr size_t kShardInsertRound = 4096;  // inserts per round of the sharded insert calls (host-side plan arrays)
 
 __device__ __forceinline__ int cmp256(const uint32_t* a, const uint32_t* b) {
@@ -492,31 +494,49 @@ __global__ void __launch_bounds__(256) k_export_versions(const uint4* __restrict
     store_fe(out + 2 * (size_t)t, r);
 }
 
-// For write t and level l (l fastest): prev = latest earlier write whose level-l node is the SIBLING of t's node
-// (-1: none, take the stored tree); last = no later write touches t's own level-l node (t's version is the final one).
-__global__ void __launch_bounds__(256) k_ins_links(const uint64_t* __restrict__ x, unsigned writes, unsigned depth, int* __restrict__ prev,
-                                                   uint8_t* __restrict__ last) {
-    const unsigned levels = depth + 1;
-    const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (id >= (size_t)writes * levels) return;
-    const unsigned t = (unsigned)(id / levels), l = (unsigned)(id % levels);
-    const uint64_t node = x[t] >> l;
-    int p = -1;
-    for (int u = (int)t - 1; u >= 0; --u) {
-        if (((x[u] >> l) ^ 1) == node) {
-            p = u;
-            break;
-        }
+// For write t and level l: prev = latest earlier write whose level-l node is the SIBLING of t's node (-1: none, take the
+// stored tree); last = no later write touches t's own level-l node (t's version is the final one).
+// Computed level by level over the writes kept sorted by (level-l node, time): in that order the writes of a node form a
+// segment sorted by time, the sibling's segment is adjacent, and
+//     rank r of t among the sibling's times   =>   prev = the sibling segment's element r - 1
+//     position of t in the PARENT's segment   =   start of the even child's segment + (index in own segment) + r
+// i.e. one step of a bottom-up merge sort per level: O(writes x log) per level instead of the pairwise O(writes^2) scan
+// (0.9 ms per level-set at 8192 writes, 14 ms at 32768). Keys pack (slot << 20 | time): at most 2^20 writes per chunk, slots < 2^32.
+constexpr unsigned kLinkTimeBits = 20;
+__global__ void __launch_bounds__(256) k_ins_link_keys(const uint64_t* __restrict__ x, unsigned writes, uint64_t* __restrict__ keys) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < writes) keys[t] = (x[t] << kLinkTimeBits) | t;
+}
+// first position whose level-l node is >= v
+__device__ __forceinline__ unsigned link_lower_bound(const uint64_t* __restrict__ a, unsigned writes, unsigned shift, uint64_t v) {
+    unsigned lo = 0, hi = writes;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if ((a[mid] >> shift) < v) lo = mid + 1;
+        else hi = mid;
     }
-    bool fin = true;
-    for (unsigned u = t + 1; u < writes; ++u) {
-        if ((x[u] >> l) == node) {
-            fin = false;
-            break;
-        }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_ins_links_level(const uint64_t* __restrict__ a, uint64_t* __restrict__ a_next, unsigned writes,
+                                                         unsigned depth, unsigned l, int* __restrict__ prev, uint8_t* __restrict__ last) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= writes) return;
+    const unsigned shift = kLinkTimeBits + l;
+    const uint64_t key = a[i], v = key >> shift;
+    const unsigned t = (unsigned)(key & ((1u << kLinkTimeBits) - 1));
+    const unsigned own = link_lower_bound(a, writes, shift, v);
+    const unsigned sb = link_lower_bound(a, writes, shift, v ^ 1), se = link_lower_bound(a, writes, shift, (v ^ 1) + 1);
+    unsigned lo = sb, hi = se;  // rank of t among the sibling segment's times (the segment is sorted by time)
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if ((unsigned)(a[mid] & ((1u << kLinkTimeBits) - 1)) < t) lo = mid + 1;
+        else hi = mid;
     }
-    prev[id] = p;
-    last[id] = fin ? 1 : 0;
+    const unsigned r = lo - sb;
+    const size_t id = (size_t)t * (depth + 1) + l;
+    prev[id] = r ? (int)(a[sb + r - 1] & ((1u << kLinkTimeBits) - 1)) : -1;
+    last[id] = (i + 1 == writes || (a[i + 1] >> shift) != v) ? 1 : 0;
+    if (l < depth) a_next[((v & 1) ? sb : own) + (i - own) + r] = key;  // merged by time into the parent's segment
 }
 
 // One level of all writes, operand half: pairs[t] = (left, right) children of write t's level-(l+1) node — its own
@@ -634,10 +654,27 @@ __global__ void k_iota_slots(uint32_t* s, size_t b, uint64_t first) {
 // ver[0 .. writes): links, then per level the operand gather + one level launch. ver holds (depth+1) x writes FE.
 imt_status versioned_levels(imt_ctx* ctx, const Fr* tree_levels, size_t n, unsigned depth, const uint64_t* d_x, unsigned writes, Fr* d_ver,
                             int* d_prev, uint8_t* d_last, Fr* d_pairs, uint4* sib_low, uint4* sib_new, uint4* sib_all) {
-    const size_t L = depth + 1;
-    k_ins_links<<<grid_for((size_t)writes * L, 256), 256, 0, ctx->stream>>>(d_x, writes, depth, d_prev, d_last);
-    ++ctx->launches;
-    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    if (writes > (1u << kLinkTimeBits)) return fail(ctx, IMT_ERR_INVALID_ARG, "more than 2^20 writes in one insert chunk");
+    {  // links of every (write, level): sort the writes by (slot, time) once, then one merge step per level
+        DevBuf keys_a(ctx), keys_b(ctx), temp(ctx);
+        IMT_TRY_CUDA(ctx, keys_a.alloc(writes * sizeof(uint64_t)));
+        IMT_TRY_CUDA(ctx, keys_b.alloc(writes * sizeof(uint64_t)));
+        k_ins_link_keys<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(d_x, writes, keys_a.as<uint64_t>());
+        size_t temp_bytes = 0;
+        IMT_TRY_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), (int)writes, 0, 64,
+                                                         ctx->stream));
+        IMT_TRY_CUDA(ctx, temp.alloc(temp_bytes));
+        IMT_TRY_CUDA(ctx, cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), (int)writes, 0, 64,
+                                                         ctx->stream));
+        uint64_t* cur = keys_b.as<uint64_t>();
+        uint64_t* nxt = keys_a.as<uint64_t>();
+        for (unsigned l = 0; l <= depth; ++l) {
+            k_ins_links_level<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(cur, nxt, writes, depth, l, d_prev, d_last);
+            std::swap(cur, nxt);
+        }
+        ctx->launches += depth + 4;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+    }  // the scratch is freed in stream order
     for (unsigned l = 0; l < depth; ++l) {
         k_ins_pairs<<<grid_for(writes, 256), 256, 0, ctx->stream>>>((const uint4*)d_ver + 2 * ((size_t)l * writes), (const uint4*)tree_levels, n, l,
                                                                     d_x, d_prev, writes, depth, ctx->fmt, (uint4*)d_pairs, sib_low, sib_new, sib_all);
@@ -864,7 +901,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     // ---- per-chunk scratch
     const char* chunk_env = std::getenv("IMT_INSERT_CHUNK");  // read per call: tests force small chunks to cross chunk boundaries
     const size_t chunk_override = chunk_env ? (size_t)std::strtoull(chunk_env, nullptr, 10) : 0;
-    const size_t C = std::min(b, chunk_override ? chunk_override : kInsertChunk), W = 2 * C, L = depth + 1;
+    const size_t C = std::min(b, chunk_override ? std::min(chunk_override, (size_t)1 << (kLinkTimeBits - 1)) : kInsertChunk), W = 2 * C, L = depth + 1;
     DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx), pairs(ctx);
     IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
