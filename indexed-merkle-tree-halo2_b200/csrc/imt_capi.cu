@@ -102,16 +102,44 @@ size_t coop_max_nodes() {
 }
 
 // one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
-imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes) {
-    return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes, cudaStream_t s = nullptr, bool on_stream = false) {
+    return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, on_stream ? s : ctx->stream);
 }
 
-// all levels above level 0 (which must already hold the Montgomery leaf hashes)
+// all levels above level 0 (which must already hold the Montgomery leaf hashes).
+// Level-synchronous launches on ONE stream drain the GPU at every boundary: the last blocks of level l run alone for ~0.3 ms
+// (half a hash latency) before level l + 1 may start — 7 to 10 such boundaries per build. From depth 16 on the two HALVES of
+// the tree (independent subtrees) are therefore built on two streams, launches interleaved level by level: the block
+// dispatcher serves the kernels in launch order, so each half's next level fills the other half's drain. The small levels of
+// the two halves (latency-bound, a few warps each) simply run side by side. The root is hashed after the join.
+constexpr unsigned kTwoLaneMinDepth = 16;
 imt_status build_upper_levels(imt_tree* t) {
     imt_ctx* ctx = t->ctx;
-    for (unsigned l = 0; l < t->depth; ++l)
-        IMT_TRY(launch_level_impl(ctx, t->d_levels + level_offset(t->n, l), t->d_levels + level_offset(t->n, l + 1), t->n >> (l + 1)));
-    return IMT_OK;
+    if (t->depth < kTwoLaneMinDepth || std::getenv("IMT_SINGLE_LANE")) {  // IMT_SINGLE_LANE: A/B measurements only
+        for (unsigned l = 0; l < t->depth; ++l)
+            IMT_TRY(launch_level_impl(ctx, t->d_levels + level_offset(t->n, l), t->d_levels + level_offset(t->n, l + 1), t->n >> (l + 1)));
+        return IMT_OK;
+    }
+    Event forked, joined;
+    IMT_TRY_CUDA(ctx, forked.create());
+    IMT_TRY_CUDA(ctx, joined.create());
+    IMT_TRY_CUDA(ctx, cudaEventRecord(forked, ctx->stream));  // level 0 is complete on the compute stream
+    IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, forked, 0));
+    cudaStream_t lanes[2] = {ctx->stream, ctx->aux_stream};
+    imt_status st = IMT_OK;
+    for (unsigned l = 0; l + 1 < t->depth && st == IMT_OK; ++l) {
+        const size_t in_half = t->n >> (l + 1), out_half = t->n >> (l + 2);  // nodes of one half at level l / l + 1
+        for (size_t h = 0; h < 2 && st == IMT_OK; ++h)
+            st = launch_level_impl(ctx, t->d_levels + level_offset(t->n, l) + h * in_half, t->d_levels + level_offset(t->n, l + 1) + h * out_half,
+                                   out_half, lanes[h], true);
+    }
+    if (st != IMT_OK) {  // do not leave work behind on the auxiliary stream
+        cudaStreamSynchronize(ctx->aux_stream);
+        return st;
+    }
+    IMT_TRY_CUDA(ctx, cudaEventRecord(joined, ctx->aux_stream));
+    IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, joined, 0));
+    return launch_level_impl(ctx, t->d_levels + level_offset(t->n, t->depth - 1), t->d_levels + level_offset(t->n, t->depth), 1);
 }
 
 imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
