@@ -37,17 +37,21 @@ struct SpecLayout {
     IMT_HD unsigned states_per_perm() const { return 1 + r_f + r_p; }
 };
 
-#ifdef __CUDACC__
-
-__device__ __forceinline__ void spec_load_const(uint32_t* x, const Fr* p) {
+// Everything below also compiles for the HOST (fr.cuh's emulated carry flag): tests/host_shim.cpp runs exactly this
+// source on the CPU against the oracle (tests/test_host_field.py). Test-only; the library has no CPU compute path.
+IMT_HD void spec_load_const(uint32_t* x, const Fr* p) {
+#ifdef __CUDA_ARCH__
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
     x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w;
     x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+#else
+    for (int i = 0; i < 8; ++i) x[i] = p->l[i];
+#endif
 }
 
 // u = x^5 + c
 template <class Sink>
-__device__ __forceinline__ void spec_sbox_add(uint32_t* u, const uint32_t* x, const Fr* c, Sink& sink) {
+IMT_HD void spec_sbox_add(uint32_t* u, const uint32_t* x, const Fr* c, Sink& sink) {
     uint32_t x2[8], x4[8], cc_[8];
     spec_load_const(cc_, c);
     mont_sqr(x2, x);
@@ -63,7 +67,7 @@ __device__ __forceinline__ void spec_sbox_add(uint32_t* u, const uint32_t* x, co
 
 // r = sum_k row[k] * s[k], one reduction (row canonical constants, s semi-reduced): < 2 T p^2 / 2^256 + p < 4p for T <= 7
 template <int T>
-__device__ __forceinline__ void spec_dot(uint32_t* r, const uint32_t (*s)[8], const Fr* row) {
+IMT_HD void spec_dot(uint32_t* r, const uint32_t (*s)[8], const Fr* row) {
     Wide w;
     wide_zero(w);
     uint32_t m[8];
@@ -79,7 +83,7 @@ __device__ __forceinline__ void spec_dot(uint32_t* r, const uint32_t (*s)[8], co
 }
 
 // r = m * u + a
-__device__ __forceinline__ void spec_mul_add(uint32_t* r, const uint32_t* u, const Fr* m, const uint32_t* a) {
+IMT_HD void spec_mul_add(uint32_t* r, const uint32_t* u, const Fr* m, const uint32_t* a) {
     uint32_t mm[8];
     spec_load_const(mm, m);
     Wide w;
@@ -92,7 +96,7 @@ __device__ __forceinline__ void spec_mul_add(uint32_t* r, const uint32_t* u, con
 
 // (s0, ..., sT-1) <- (s1, ..., sT-1, s0)
 template <int T>
-__device__ __forceinline__ void spec_rotate(uint32_t (*s)[8]) {
+IMT_HD void spec_rotate(uint32_t (*s)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const uint32_t t0 = s[0][i];
@@ -104,7 +108,7 @@ __device__ __forceinline__ void spec_rotate(uint32_t (*s)[8]) {
 
 // One permutation, in place. Sink::emit(s) sees the state after the pre-add and after every round's linear layer.
 template <int T, class Sink>
-__device__ __forceinline__ void spec_permute(uint32_t (*s)[8], const Fr* __restrict__ P, const SpecLayout L, Sink& sink) {
+IMT_HD void spec_permute(uint32_t (*s)[8], const Fr* __restrict__ P, const SpecLayout L, Sink& sink) {
     {
         uint32_t c[8];
 #pragma unroll
@@ -165,7 +169,7 @@ __device__ __forceinline__ void spec_permute(uint32_t (*s)[8], const Fr* __restr
 // followed by the padding element 1 is added and permuted once more; the digest is state[1].
 // `load(j, x)` yields input j in Montgomery form (semi-reduced). arity / RATE + 1 permutations, ONE call site.
 template <int T, class Load, class Sink>
-__device__ __forceinline__ void spec_sponge(uint32_t* digest, size_t arity, Load& load, const Fr* __restrict__ P, const SpecLayout L,
+IMT_HD void spec_sponge(uint32_t* digest, size_t arity, Load& load, const Fr* __restrict__ P, const SpecLayout L,
                                             Sink& sink) {
     constexpr int RATE = T - 1;
     uint32_t s[T][8];
@@ -197,7 +201,5 @@ __device__ __forceinline__ void spec_sponge(uint32_t* digest, size_t arity, Load
 #pragma unroll
     for (int i = 0; i < 8; ++i) digest[i] = s[1][i];
 }
-
-#endif  // __CUDACC__
 
 }  // namespace imt

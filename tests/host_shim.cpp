@@ -85,4 +85,49 @@ void shim_hash_ext(uint32_t* out, const uint32_t* in, int arity, uint32_t* state
     }
     from_mont(out, d);
 }
+}  // extern "C"
+
+// any-width instance <t, t-1>(r_f, r_p): canonical in (arity x 8 words) -> canonical digest; states optional
+// ((arity / (t-1) + 1) x (1 + r_f + r_p) x t x 8 words, canonical). Returns 0, or 1 for an unsupported instance.
+template <int T>
+struct CollectT {
+    uint32_t* dst;
+    void emit(const uint32_t (*s)[8]) {
+        if (!dst) return;
+        for (int i = 0; i < T; ++i) {
+            uint32_t t[8];
+            for (int j = 0; j < 8; ++j) t[j] = s[i][j];
+            from_mont(dst, t);
+            dst += 8;
+        }
+    }
+    void emit_sbox(const uint32_t*, const uint32_t*, const uint32_t*) {}
+};
+struct HostLoad {
+    const uint32_t* in;
+    void operator()(size_t j, uint32_t* x) {
+        to_mont(x, in + 8 * j);
+        cond_sub_p(x);
+    }
+};
+template <int T>
+static void spec_hash_t(uint32_t* out, const uint32_t* in, size_t arity, const Fr* P, SpecLayout L, uint32_t* states) {
+    uint32_t d[8];
+    HostLoad load{in};
+    CollectT<T> sink{states};
+    spec_sponge<T>(d, arity, load, P, L, sink);
+    from_mont(out, d);
+}
+extern "C" int shim_spec_hash(unsigned t, unsigned r_f, unsigned r_p, const uint32_t* in, size_t arity, uint32_t* out, uint32_t* states) {
+    if (t < kSpecMinT || t > kSpecMaxT) return 1;
+    const SpecLayout L{t, r_f, r_p};
+    static Fr params[4096];
+    if (L.total() > 4096 || !poseidon_spec_generate(t, r_f, r_p, params)) return 1;
+    switch (t) {
+        case 2: spec_hash_t<2>(out, in, arity, params, L, states); break;
+        case 3: spec_hash_t<3>(out, in, arity, params, L, states); break;
+        case 4: spec_hash_t<4>(out, in, arity, params, L, states); break;
+        default: spec_hash_t<5>(out, in, arity, params, L, states); break;
+    }
+    return 0;
 }

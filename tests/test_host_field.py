@@ -25,7 +25,7 @@ def shim():
     out = os.path.join(ROOT, "tests", "_build", "libhost_shim.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     srcs = [os.path.join(ROOT, "tests", "host_shim.cpp"), os.path.join(CSRC, "poseidon_params.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("fr.cuh", "poseidon.cuh", "poseidon_params.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("fr.cuh", "poseidon.cuh", "poseidon_spec.cuh", "poseidon_params.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, "-x", "c++", *srcs, "-o", out], check=True)
     return ctypes.CDLL(out)
@@ -160,3 +160,24 @@ def test_hash_and_trace(shim):
     I = np.concatenate([w(0)] * 3)
     shim.shim_hash(p_(out), p_(I), 3, None)
     assert iv(out) == R.KAT_H3_ZERO  # /root/reference/src/indexed_merkle_tree.rs:247-251
+
+
+@pytest.mark.parametrize("t,r_f,r_p", [(2, 8, 56), (3, 8, 57), (4, 8, 56), (5, 8, 60), (3, 6, 10), (4, 2, 0)])
+def test_any_width_sponge_source_on_the_host(shim, t, r_f, r_p):
+    """csrc/poseidon_spec.cuh (the any-width permutation + sponge the GPU kernels run) compiled for the host with the emulated
+    carry flag: digests and per-round traces for every input length 0 .. 2t + 1 against the Python oracle"""
+    sp = R.Spec(r_f, r_p, t)
+    rng = random.Random(t * 100 + r_p)
+    per_perm = (1 + r_f + r_p) * t
+    for arity in range(0, 2 * t + 2):
+        x = [rng.randrange(P) for _ in range(arity)]
+        I = np.concatenate([w(v) for v in x]) if arity else np.zeros(8, np.uint32)
+        perms = arity // (t - 1) + 1
+        out = np.zeros(8, np.uint32)
+        st = np.zeros(perms * per_perm * 8, np.uint32)
+        assert shim.shim_spec_hash(t, r_f, r_p, p_(I), ctypes.c_size_t(arity), p_(out), p_(st)) == 0
+        d, tr = R.hash_trace_n(x, sp)
+        assert iv(out) == d, (t, arity)
+        assert [iv(st[8 * i:8 * i + 8]) for i in range(perms * per_perm)] == [v for s_ in tr for v in s_]
+        assert shim.shim_spec_hash(t, r_f, r_p, p_(I), ctypes.c_size_t(arity), p_(out), None) == 0 and iv(out) == d
+    assert shim.shim_spec_hash(6, 8, 57, p_(out), ctypes.c_size_t(0), p_(out), None) == 1
