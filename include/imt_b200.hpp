@@ -221,6 +221,34 @@ class IndexedMerkleTree {
         detail::check(ctx_, imt_tree_preimages(tree_.get(), out.data()));
         return out;
     }
+    // witnesses of verify_non_inclusion (IMT:127-137) for many values at once: low leaf, its path, is_new_leaf_largest,
+    // and the 128-bit limb splits the chip assigns (IMT:143-172, 206-222) with the outcome of its two comparisons
+    struct NonInclusion {
+        std::vector<uint64_t> low_idx;
+        std::vector<IndexedMerkleTreeLeaf> low_leaves;
+        std::vector<std::vector<Fr>> low_proof, low_proof_helper;
+        std::vector<bool> is_new_leaf_largest, valid;            // valid: passes the chip's prover-side assertions (IMT:190, 226-228)
+        std::vector<std::array<Fr, 6>> limbs;                    // nl_q, nl_r, ll_q, ll_r, llv_q, llv_r
+    };
+    NonInclusion non_inclusion_paths(const std::vector<Fr>& values) const {
+        const size_t q = values.size(), d = depth();
+        NonInclusion o;
+        o.low_idx.resize(q), o.low_leaves.resize(q), o.limbs.resize(q);
+        std::vector<uint8_t> matched(q), hel(q * d), lg(q), flags(3 * q);
+        std::vector<Fr> sib(q * d);
+        detail::check(ctx_, imt_non_inclusion_paths(tree_.get(), values.data(), q, o.low_idx.data(), matched.data(), o.low_leaves.data(), sib.data(),
+                                                    hel.data(), lg.data()));
+        detail::check(ctx_, imt_non_inclusion_limbs(ctx_, o.low_leaves.data(), values.data(), q, o.limbs.data(), flags.data()));
+        for (size_t i = 0; i < q; ++i) {
+            o.low_proof.emplace_back(sib.begin() + i * d, sib.begin() + (i + 1) * d);
+            std::vector<Fr> h(d);
+            for (size_t k = 0; k < d; ++k) h[k] = Fr::from(hel[i * d + k]);
+            o.low_proof_helper.push_back(std::move(h));
+            o.is_new_leaf_largest.push_back(lg[i] != 0);
+            o.valid.push_back(matched[i] != 0 && flags[3 * i + 2] != 0);
+        }
+        return o;
+    }
     // IMT:710-741 for a whole batch with O(depth) hashes per insert: the tree advances in place and every per-insert
     // witness comes back — bit-identical to re-hashing and rebuilding per insert as the reference does (IMT:724-730)
     InsertWitness insert_batch(const std::vector<Fr>& new_vals) {

@@ -120,6 +120,19 @@ static void test_insert_leaf_multiple_round() {
         REQUIRE(w.is_new_leaf_largest[round] == is_new_leaf_largest);
     }
     REQUIRE(batched.get_root() == nullifier_tree.get_root());
+    // verify_non_inclusion's witnesses for two absent values and one present one, from the final tree
+    auto ni = batched.non_inclusion_paths({Fr::from(25), Fr::from(60), Fr::from(20)});
+    REQUIRE(ni.low_idx[0] == 3 && ni.low_leaves[0].val == Fr::from(20) && ni.low_leaves[0].next_val == Fr::from(30) && !ni.is_new_leaf_largest[0]);
+    REQUIRE(ni.low_idx[1] == 5 && ni.low_leaves[1].val == Fr::from(50) && ni.is_new_leaf_largest[1] && ni.valid[0] && ni.valid[1]);
+    // 20 IS in the tree: the reference's scan (IMT:632-660) then falls through to the first empty slot {0, 0, 0} (SURVEY 8a.10:
+    // a quirk to document, not to fix) — same answer here
+    REQUIRE(ni.low_idx[2] == 7 && ni.low_leaves[2].val.is_zero() && ni.low_leaves[2].next_val.is_zero());
+    REQUIRE(ni.limbs[0][1] == Fr::from(25) && ni.limbs[0][3] == Fr::from(30) && ni.limbs[0][5] == Fr::from(20) && ni.limbs[0][0].is_zero());
+    {
+        Poseidon<T, RATE>& h = native_hasher;
+        h.update({ni.low_leaves[0].val, ni.low_leaves[0].next_val, ni.low_leaves[0].next_idx});
+        REQUIRE(batched.verify_proof(h.squeeze_and_reset(), ni.low_idx[0], batched.get_root(), ni.low_proof[0]));
+    }
     const std::vector<IMTLeaf> fin = batched.preimages();
     for (size_t i = 0; i < tree_size; ++i)
         std::printf("multiple_round final %zu %llu %llu %llu\n", i, (unsigned long long)fin[i].val.l[0], (unsigned long long)fin[i].next_val.l[0],
