@@ -129,6 +129,26 @@ def cpu_build_rate(depth_hint_seconds, threads=None):
     return hashes / dt, th, f"depth-{d} build ({hashes} hashes) in {dt:.2f}s, {th} threads", d, dt
 
 
+def cpu_single_thread_rate(seconds=2.0):
+    """The same port on ONE thread — the reference itself is strictly sequential (its hasher is a `&mut` borrow,
+    utils.rs:21, 43-47). Returns (hashes/s, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from imt_b200 import synth
+    d = 10
+    pre = synth.random_preimages(1 << d)
+    t0 = time.perf_counter()
+    O.build_from_preimages(pre, 1)
+    rate = (2 * (1 << d) - 1) / (time.perf_counter() - t0)
+    d = max(10, min(18, int(rate * seconds / 2).bit_length() - 1))
+    pre = synth.random_preimages(1 << d)
+    t0 = time.perf_counter()
+    O.build_from_preimages(pre, 1)
+    dt = time.perf_counter() - t0
+    hashes = 2 * (1 << d) - 1
+    return hashes / dt, f"depth-{d} build ({hashes} hashes) in {dt:.2f}s, 1 thread"
+
+
 def run_reference(a):
     """--impl reference: the reference's own CPU implementation of the path. The Rust crate cannot be built here
     (no cargo/rustc, un-vendored git deps), so this is the oracle PORT of it, with all host threads."""
@@ -160,7 +180,8 @@ def run_reference(a):
                                         "depth": a.depth, "leaves": 1 << a.depth, "hashes_per_step": 2 * (1 << a.depth) - 1,
                                         "sharding": "host threads", "seed": synth.DEFAULT_SEED, "fe_format": "canonical",
                                         "sample_depth": S, "sample_hashes_per_step": hashes},
-        "cpu_baseline": {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample,
+                         "single_thread": dict(zip(("value", "sample"), cpu_single_thread_rate()))},
         "e2e": {"value": v, "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C port of the reference's Rust CPU path (oracle/imt_oracle.c): the crate itself is unbuildable here",
     }), flush=True)
@@ -553,7 +574,8 @@ def main():
     }
     if rank == 0 and not a.no_cpu_baseline:
         v, th, sample, _, _ = cpu_build_rate(a.cpu_seconds)
-        out["cpu_baseline"] = {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample}
+        out["cpu_baseline"] = {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample,
+                               "single_thread": dict(zip(("value", "sample"), cpu_single_thread_rate()))}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -26,6 +26,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["config"]["depth"] == 24 and "workload" in line["config"]
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] > 1000 and "sample" in cb
+    assert cb["single_thread"]["value"] > 1000 and "1 thread" in cb["single_thread"]["sample"]   # the reference is sequential (utils.rs:21)
     assert line["e2e"] == {"value": line["value"], "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
