@@ -8,7 +8,7 @@ PKG     := indexed-merkle-tree-halo2_b200
 CSRC    := $(PKG)/csrc
 OBJDIR  := $(PKG)/build
 LIB     := $(PKG)/libimt_b200.so
-UNITS   := imt_capi.cu imt_indexed.cu imt_spec.cu poseidon_params.cpp
+UNITS   := imt_capi.cu imt_indexed.cu imt_spec.cu imt_comm.cu poseidon_params.cpp
 OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(basename $(UNITS))))
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 550 -Iinclude -I$(CSRC)
 HEADERS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/imt_b200.h
@@ -24,7 +24,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HEADERS)
 	env -u CC -u CXX $(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	env -u CC -u CXX $(NVCC) -gencode arch=compute_100a,code=sm_100a -shared $(OBJS) -o $@
+	env -u CC -u CXX $(NVCC) -gencode arch=compute_100a,code=sm_100a -shared $(OBJS) -ldl -o $@
 
 clients: $(LIB)
 	@mkdir -p tests/_build

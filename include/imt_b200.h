@@ -260,6 +260,8 @@ imt_status imt_tree_attach_cap_dev(imt_tree* tree, unsigned rank, unsigned world
  *      (head_next_zero = imt_tree_head_next_zero of rank 0: the reference's first-insert branch, IMT:640)
  *   4. the owner of each low_idx serves its preimage (imt_tree_leaves) and path (imt_tree_get_proofs), global indices. */
 imt_status imt_tree_set_shard(imt_tree* tree, unsigned rank, unsigned world);
+/* rank / world of a shard (0 / 1 for an unsharded tree) and the leaves this rank holds; any pointer may be NULL */
+imt_status imt_tree_shard_info(const imt_tree* tree, unsigned* rank, unsigned* world, size_t* n_local);
 imt_status imt_tree_head_next_zero(imt_tree* tree, int* flag);
 imt_status imt_low_leaf_candidates(imt_tree* tree, const void* values, size_t q, void* cand_keys, uint64_t* cand_slots, uint8_t* flags);
 imt_status imt_low_leaf_merge(imt_ctx* ctx, const void* values, const void* cand_keys, const uint64_t* cand_slots, const uint8_t* flags,
@@ -287,6 +289,87 @@ imt_status imt_shard_insert_cap(imt_tree* tree, const uint64_t* x, const void* s
 /* Preimages (3 FE each, context format) of the given slots and is_largest = (next_val == 0). Global indices inside this
  * rank's range for a shard. Either output may be NULL. */
 imt_status imt_tree_leaves(imt_tree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest);
+
+/* ---------------------------------------------------------------- multi-GPU inside the library (NCCL) --------- */
+/* The calls above leave the exchange of the subtree roots to the caller. The calls below do it INSIDE the library with NCCL
+ * (bound at run time: libnccl.so.2 is only needed once a communicator is made), so that the reference's single entry point
+ * `IndexedMerkleTree::new(&mut hasher, leaves)` (src/utils.rs:20-57) maps to ONE call on a multi-GPU box:
+ *     N local subtree builds  ->  one ncclAllGather of N x 32 bytes over NVLink  ->  log2 N cap levels on every rank.
+ * Results are bit-identical to the single-GPU tree (and to the reference). Two ways to form the group of ranks:
+ *
+ * (1) ONE PROCESS PER GPU (torchrun / MPI layout). Rank 0 calls imt_comm_unique_id and passes the IMT_COMM_ID_BYTES bytes
+ *     to every rank by any means (file, socket, MPI_Bcast, a torch.distributed store); every rank attaches a communicator
+ *     to its own context. world must be a power of two. The imt_sharded_* calls are collective: every rank calls them
+ *     with the same arguments (query arrays are replicated inputs, results are replicated outputs). */
+#define IMT_COMM_ID_BYTES 128
+imt_status imt_comm_unique_id(void* id);
+imt_status imt_comm_create(imt_ctx* ctx, unsigned rank, unsigned world, const void* id);
+imt_status imt_comm_destroy(imt_ctx* ctx); /* before imt_ctx_destroy; trees of the context first */
+/* rank / world of the context's group (0 / 1 without one) and the NCCL version in use (any pointer may be NULL) */
+imt_status imt_comm_info(const imt_ctx* ctx, unsigned* rank, unsigned* world, int* nccl_version);
+/* Exchange after a local (re)build made with the single-GPU calls: all-gathers the subtree roots straight out of / into
+ * the trees' device buffers on the context's stream and builds the cap; afterwards root / depth / get_proofs refer to the
+ * GLOBAL tree (as after imt_tree_attach_cap). */
+imt_status imt_tree_exchange_roots(imt_tree* tree);
+/* IndexedMerkleTree::new for this rank's contiguous slice of the leaves (n_local = n / world), exchange included. */
+imt_status imt_sharded_build_from_leaves(imt_ctx* ctx, const void* local_preimages, size_t n_local, imt_tree** out);
+imt_status imt_sharded_build_from_leaves_dev(imt_ctx* ctx, const void* d_local_preimages, size_t n_local, imt_tree** out);
+imt_status imt_sharded_rebuild_from_leaves(imt_tree* tree, const void* local_preimages);
+imt_status imt_sharded_rebuild_from_leaves_dev(imt_tree* tree, const void* d_local_preimages);
+/* get_proof (src/utils.rs:63-85) for GLOBAL indices: the owner of each leaf serves its path, one all-reduce assembles the
+ * replicated result. Same outputs as imt_tree_get_proofs on the unsharded tree. */
+imt_status imt_sharded_get_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers);
+/* imt_tree_leaves for GLOBAL indices, replicated. */
+imt_status imt_sharded_leaves(imt_tree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest);
+/* update_idx_leaf's scan (src/indexed_merkle_tree.rs:632-660) over the sharded tree: per-rank predecessor candidates, one
+ * all-gather on the device, the same decision as imt_low_leaf_lookup. occupied_total may be NULL. */
+imt_status imt_sharded_low_leaf_lookup(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched);
+imt_status imt_sharded_occupied(imt_tree* tree, uint64_t* occupied_total);
+/* imt_non_inclusion_paths over the sharded tree (any output pointer may be NULL). */
+imt_status imt_sharded_non_inclusion_paths(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                           void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest);
+/* imt_insert_batch over the sharded tree: same witnesses, same final state as on one GPU — the reference's sequence of
+ * rebuilds (src/indexed_merkle_tree.rs:710-741). Insert i goes to GLOBAL slot first_idx + i; first_idx must equal the total
+ * number of occupied slots (imt_sharded_occupied). */
+imt_status imt_sharded_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w);
+/* Witness traces of verify_merkle_proof (imt_tree_trace_proofs) sharded by leaf OWNER with no exchange: this rank traces the
+ * queries whose leaves it owns. positions[j] (capacity q) = index into `indices` of the j-th traced query, *n_mine = how
+ * many; states[j] = its trace. The traces stay on the rank that produced them (19.9 GB for 2^16 depth-24 paths). */
+imt_status imt_sharded_trace_proofs(imt_tree* tree, const uint64_t* indices, size_t q, uint64_t* positions, size_t* n_mine, void* states);
+
+/* (2) ONE PROCESS DRIVES N GPUs — the natural shape for the Rust host, whose `IndexedMerkleTree::new` is one call on one
+ *     thread. imt_multi_create makes one context per listed device (a power of two of them) and their communicators
+ *     (ncclCommInitAll); an imt_mtree is the sharded tree: shard i (leaves [i n/N, (i+1) n/N)) lives on devices[i].
+ *     Host arrays are whole-tree arrays; every call fans out to the devices and returns the assembled result. A device may be
+ *     listed more than once (one-GPU test boxes): NCCL refuses duplicate devices, so such a group exchanges by
+ *     device-to-device copies instead — everything else is the same code. */
+typedef struct imt_multi imt_multi;
+typedef struct imt_mtree imt_mtree;
+imt_status imt_multi_create(const int* devices, unsigned n_dev, imt_fe_format format, imt_multi** out);
+void imt_multi_destroy(imt_multi* m); /* destroy its trees first */
+unsigned imt_multi_size(const imt_multi* m);
+imt_ctx* imt_multi_ctx(imt_multi* m, unsigned i); /* context of device i: batched hashing, folds, traces, timing, ... */
+const char* imt_multi_last_error(const imt_multi* m);
+int imt_multi_uses_nccl(const imt_multi* m); /* the NCCL version code in use, 0 = copy transport */
+/* IndexedMerkleTree::new (src/utils.rs:20-57) + leaf hashing (src/indexed_merkle_tree.rs:662-671) over all devices: the N
+ * host->device pipelines, leaf kernels and level launches are queued on all devices before anything is waited for. */
+imt_status imt_multi_build_from_leaves(imt_multi* m, const void* preimages, size_t n, imt_mtree** out);
+imt_status imt_mtree_rebuild_from_leaves(imt_mtree* tree, const void* preimages);
+void imt_mtree_destroy(imt_mtree* tree);
+imt_tree* imt_mtree_shard(imt_mtree* tree, unsigned i); /* shard i as an imt_tree (levels, preimages, device-pointer calls) */
+size_t imt_mtree_num_leaves(const imt_mtree* tree);
+unsigned imt_mtree_depth(const imt_mtree* tree);
+imt_status imt_mtree_root(imt_mtree* tree, void* out_fe);
+imt_status imt_mtree_get_proofs(imt_mtree* tree, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers);
+imt_status imt_mtree_leaves(imt_mtree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest);
+imt_status imt_mtree_low_leaf_lookup(imt_mtree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched);
+imt_status imt_mtree_occupied(imt_mtree* tree, uint64_t* occupied_total);
+imt_status imt_mtree_non_inclusion_paths(imt_mtree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                         void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest);
+imt_status imt_mtree_insert_batch(imt_mtree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w);
+/* imt_tree_trace_proofs for GLOBAL indices: every device traces the queries it owns and drains them over its own PCIe link
+ * into states[q][depth][fe per hash] (caller order). */
+imt_status imt_mtree_trace_proofs(imt_mtree* tree, const uint64_t* indices, size_t q, void* states);
 
 /* ---------------------------------------------------------------- calibration -------------------------------- */
 /* Integer-multiply roofline calibration: saturates every SM with IMAD.WIDE.U32.X carry chains (the instruction the

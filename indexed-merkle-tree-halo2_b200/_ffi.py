@@ -73,6 +73,7 @@ SIGNATURES = {
     "imt_tree_attach_cap": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),
     "imt_tree_attach_cap_dev": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),
     "imt_tree_set_shard": (c_int, [c_void_p, c_uint, c_uint]),
+    "imt_tree_shard_info": (c_int, [c_void_p, ctypes.POINTER(c_uint), ctypes.POINTER(c_uint), ctypes.POINTER(c_size_t)]),
     "imt_tree_head_next_zero": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "imt_low_leaf_candidates": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "imt_low_leaf_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint, c_size_t, c_u64, c_u64, c_int, c_void_p, c_void_p]),
@@ -98,6 +99,43 @@ SIGNATURES = {
     "imt_poseidon_permute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "imt_spec_params_host": (c_int, [c_uint, c_uint, c_uint, c_uint, c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
     "imt_calibrate_imad": (c_int, [c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    # ---- multi-GPU inside the library (NCCL)
+    "imt_comm_unique_id": (c_int, [c_void_p]),
+    "imt_comm_create": (c_int, [c_void_p, c_uint, c_uint, c_void_p]),
+    "imt_comm_destroy": (c_int, [c_void_p]),
+    "imt_comm_info": (c_int, [c_void_p, ctypes.POINTER(c_uint), ctypes.POINTER(c_uint), ctypes.POINTER(c_int)]),
+    "imt_tree_exchange_roots": (c_int, [c_void_p]),
+    "imt_sharded_build_from_leaves": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "imt_sharded_build_from_leaves_dev": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "imt_sharded_rebuild_from_leaves": (c_int, [c_void_p, c_void_p]),
+    "imt_sharded_rebuild_from_leaves_dev": (c_int, [c_void_p, c_void_p]),
+    "imt_sharded_get_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_sharded_leaves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_sharded_low_leaf_lookup": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_sharded_occupied": (c_int, [c_void_p, c_u64p]),
+    "imt_sharded_non_inclusion_paths": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "imt_sharded_insert_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, ctypes.POINTER(InsertWitness)]),
+    "imt_sharded_trace_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, ctypes.POINTER(c_size_t), c_void_p]),
+    "imt_multi_create": (c_int, [ctypes.POINTER(c_int), c_uint, c_int, ctypes.POINTER(c_void_p)]),
+    "imt_multi_destroy": (None, [c_void_p]),
+    "imt_multi_size": (c_uint, [c_void_p]),
+    "imt_multi_ctx": (c_void_p, [c_void_p, c_uint]),
+    "imt_multi_last_error": (ctypes.c_char_p, [c_void_p]),
+    "imt_multi_uses_nccl": (c_int, [c_void_p]),
+    "imt_multi_build_from_leaves": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "imt_mtree_rebuild_from_leaves": (c_int, [c_void_p, c_void_p]),
+    "imt_mtree_destroy": (None, [c_void_p]),
+    "imt_mtree_shard": (c_void_p, [c_void_p, c_uint]),
+    "imt_mtree_num_leaves": (c_size_t, [c_void_p]),
+    "imt_mtree_depth": (c_uint, [c_void_p]),
+    "imt_mtree_root": (c_int, [c_void_p, c_void_p]),
+    "imt_mtree_get_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_mtree_leaves": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_mtree_low_leaf_lookup": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "imt_mtree_occupied": (c_int, [c_void_p, c_u64p]),
+    "imt_mtree_non_inclusion_paths": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "imt_mtree_insert_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, ctypes.POINTER(InsertWitness)]),
+    "imt_mtree_trace_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
-SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "poseidon_params.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
+SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "imt_comm.cu", "poseidon_params.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "poseidon_quad.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
 OBJ_DIR = os.path.join(HERE, "build")
 
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-o", LIB], check=True, env=env)
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-ldl", "-o", LIB], check=True, env=env)
     return LIB
 
 

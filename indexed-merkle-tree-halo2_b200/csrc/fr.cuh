@@ -172,6 +172,24 @@ IMT_HD void madwc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
     flag() = (uint32_t)(t >> 32);
 #endif
 }
+// First MAC of a chain. Default: it consumes the (provably zero) carry the previous chain left behind, which strings every
+// chain of a thread into program order (see INVARIANT above) — right for the throughput kernels. A chain whose head does NOT
+// read the flag is independent of what precedes it, so ptxas may overlap it with the previous chain (one more carry predicate
+// live): the latency kernels (a lone warp per scheduler, poseidon_coop.cuh) gain from that. IMT_FREE_MASK selects which heads
+// are free — bit 0 / 1: the even / odd accumulator chain of a product row, bit 2 / 3: of a reduction row, bit 4: squaring rows;
+// IMT_FREE_CHAINS = all of them. Measured per combination by tools/latency_lab.cu.
+#if defined(IMT_FREE_CHAINS) && !defined(IMT_FREE_MASK)
+#define IMT_FREE_MASK 31
+#endif
+#ifndef IMT_FREE_MASK
+#define IMT_FREE_MASK 0
+#endif
+template <int KIND>
+IMT_HD void madw_head(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    if constexpr (((IMT_FREE_MASK) >> KIND) & 1) madw_cc(lo, hi, a, b);
+    else madwc_cc(lo, hi, a, b);
+}
+constexpr int kHeadProdE = 0, kHeadProdO = 1, kHeadRedE = 2, kHeadRedO = 3, kHeadSqr = 4;
 }  // namespace cc
 
 // ------------------------------------------------------------------------------------------ wide accumulator
@@ -211,23 +229,23 @@ IMT_HD void chain_top(Wide& w, int pos) {
 template <bool FRESH, int I>
 IMT_HD void mac_row(Wide& w, const uint32_t* a, uint32_t s) {
     if constexpr ((I & 1) == 0) {
-        cc::madwc_cc(w.e[I], w.e[I + 1], a[0], s);
+        cc::madw_head<cc::kHeadProdE>(w.e[I], w.e[I + 1], a[0], s);
         cc::madwc_cc(w.e[I + 2], w.e[I + 3], a[2], s);
         cc::madwc_cc(w.e[I + 4], w.e[I + 5], a[4], s);
         cc::madwc_cc(w.e[I + 6], w.e[I + 7], a[6], s);
         chain_top<FRESH, true>(w, I + 8);
-        cc::madwc_cc(w.o[I], w.o[I + 1], a[1], s);
+        cc::madw_head<cc::kHeadProdO>(w.o[I], w.o[I + 1], a[1], s);
         cc::madwc_cc(w.o[I + 2], w.o[I + 3], a[3], s);
         cc::madwc_cc(w.o[I + 4], w.o[I + 5], a[5], s);
         cc::madwc_cc(w.o[I + 6], w.o[I + 7], a[7], s);
         chain_top<FRESH, false>(w, I + 9);
     } else {
-        cc::madwc_cc(w.o[I - 1], w.o[I], a[0], s);
+        cc::madw_head<cc::kHeadProdO>(w.o[I - 1], w.o[I], a[0], s);
         cc::madwc_cc(w.o[I + 1], w.o[I + 2], a[2], s);
         cc::madwc_cc(w.o[I + 3], w.o[I + 4], a[4], s);
         cc::madwc_cc(w.o[I + 5], w.o[I + 6], a[6], s);
         chain_top<FRESH, false>(w, I + 8);
-        cc::madwc_cc(w.e[I + 1], w.e[I + 2], a[1], s);
+        cc::madw_head<cc::kHeadProdE>(w.e[I + 1], w.e[I + 2], a[1], s);
         cc::madwc_cc(w.e[I + 3], w.e[I + 4], a[3], s);
         cc::madwc_cc(w.e[I + 5], w.e[I + 6], a[5], s);
         cc::madwc_cc(w.e[I + 7], w.e[I + 8], a[7], s);
@@ -270,52 +288,52 @@ IMT_HD void add_hi(Wide& w, const uint32_t* c) {
 IMT_HD void sqr_wide(Wide& w, const uint32_t* a) {
     // ---- off-diagonal a_i * a_j, i < j, landing at limb position i + j
     // row 0
-    cc::madwc_cc(w.o[0], w.o[1], a[0], a[1]);
+    cc::madw_head<cc::kHeadSqr>(w.o[0], w.o[1], a[0], a[1]);
     cc::madwc_cc(w.o[2], w.o[3], a[0], a[3]);
     cc::madwc_cc(w.o[4], w.o[5], a[0], a[5]);
     cc::madwc_cc(w.o[6], w.o[7], a[0], a[7]);
     w.o[8] = cc::addc_cc(w.o[8], 0);
-    cc::madwc_cc(w.e[2], w.e[3], a[0], a[2]);
+    cc::madw_head<cc::kHeadSqr>(w.e[2], w.e[3], a[0], a[2]);
     cc::madwc_cc(w.e[4], w.e[5], a[0], a[4]);
     cc::madwc_cc(w.e[6], w.e[7], a[0], a[6]);
     w.e[8] = cc::addc_cc(w.e[8], 0);
     // row 1
-    cc::madwc_cc(w.o[2], w.o[3], a[1], a[2]);
+    cc::madw_head<cc::kHeadSqr>(w.o[2], w.o[3], a[1], a[2]);
     cc::madwc_cc(w.o[4], w.o[5], a[1], a[4]);
     cc::madwc_cc(w.o[6], w.o[7], a[1], a[6]);
     w.o[8] = cc::addc_cc(w.o[8], 0);
-    cc::madwc_cc(w.e[4], w.e[5], a[1], a[3]);
+    cc::madw_head<cc::kHeadSqr>(w.e[4], w.e[5], a[1], a[3]);
     cc::madwc_cc(w.e[6], w.e[7], a[1], a[5]);
     cc::madwc_cc(w.e[8], w.e[9], a[1], a[7]);
     w.e[10] = cc::addc_cc(w.e[10], 0);
     // row 2
-    cc::madwc_cc(w.o[4], w.o[5], a[2], a[3]);
+    cc::madw_head<cc::kHeadSqr>(w.o[4], w.o[5], a[2], a[3]);
     cc::madwc_cc(w.o[6], w.o[7], a[2], a[5]);
     cc::madwc_cc(w.o[8], w.o[9], a[2], a[7]);
     w.o[10] = cc::addc_cc(w.o[10], 0);
-    cc::madwc_cc(w.e[6], w.e[7], a[2], a[4]);
+    cc::madw_head<cc::kHeadSqr>(w.e[6], w.e[7], a[2], a[4]);
     cc::madwc_cc(w.e[8], w.e[9], a[2], a[6]);
     w.e[10] = cc::addc_cc(w.e[10], 0);
     // row 3
-    cc::madwc_cc(w.o[6], w.o[7], a[3], a[4]);
+    cc::madw_head<cc::kHeadSqr>(w.o[6], w.o[7], a[3], a[4]);
     cc::madwc_cc(w.o[8], w.o[9], a[3], a[6]);
     w.o[10] = cc::addc_cc(w.o[10], 0);
-    cc::madwc_cc(w.e[8], w.e[9], a[3], a[5]);
+    cc::madw_head<cc::kHeadSqr>(w.e[8], w.e[9], a[3], a[5]);
     cc::madwc_cc(w.e[10], w.e[11], a[3], a[7]);
     w.e[12] = cc::addc_cc(w.e[12], 0);
     // row 4
-    cc::madwc_cc(w.o[8], w.o[9], a[4], a[5]);
+    cc::madw_head<cc::kHeadSqr>(w.o[8], w.o[9], a[4], a[5]);
     cc::madwc_cc(w.o[10], w.o[11], a[4], a[7]);
     w.o[12] = cc::addc_cc(w.o[12], 0);
-    cc::madwc_cc(w.e[10], w.e[11], a[4], a[6]);
+    cc::madw_head<cc::kHeadSqr>(w.e[10], w.e[11], a[4], a[6]);
     w.e[12] = cc::addc_cc(w.e[12], 0);
     // row 5
-    cc::madwc_cc(w.o[10], w.o[11], a[5], a[6]);
+    cc::madw_head<cc::kHeadSqr>(w.o[10], w.o[11], a[5], a[6]);
     w.o[12] = cc::addc_cc(w.o[12], 0);
-    cc::madwc_cc(w.e[12], w.e[13], a[5], a[7]);
+    cc::madw_head<cc::kHeadSqr>(w.e[12], w.e[13], a[5], a[7]);
     w.e[14] = cc::addc_cc(w.e[14], 0);
     // row 6
-    cc::madwc_cc(w.o[12], w.o[13], a[6], a[7]);
+    cc::madw_head<cc::kHeadSqr>(w.o[12], w.o[13], a[6], a[7]);
     w.o[14] = cc::addc_cc(w.o[14], 0);
     // ---- merge: e[pos] += o[pos-1]  (e[0] = e[1]'s pair is still zero; position 0 holds nothing)
     w.e[1] = cc::add_cc(w.e[1], w.o[0]);
@@ -326,7 +344,7 @@ IMT_HD void sqr_wide(Wide& w, const uint32_t* a) {
 #pragma unroll
     for (int pos = 2; pos < 16; ++pos) w.e[pos] = cc::addc_cc(w.e[pos], w.e[pos]);
     // ---- diagonal a_i^2 at position 2i: one chain over aligned pairs
-    cc::madwc_cc(w.e[0], w.e[1], a[0], a[0]);
+    cc::madw_head<cc::kHeadSqr>(w.e[0], w.e[1], a[0], a[0]);
     cc::madwc_cc(w.e[2], w.e[3], a[1], a[1]);
     cc::madwc_cc(w.e[4], w.e[5], a[2], a[2]);
     cc::madwc_cc(w.e[6], w.e[7], a[3], a[3]);
@@ -355,12 +373,12 @@ IMT_HD void redc_row(Wide& w, uint32_t& cin) {
         w.e[I] = t;
         cin = c1;
         m = t * IMT_INV32;
-        cc::madwc_cc(w.e[I], w.e[I + 1], m, IMT_P0);
+        cc::madw_head<cc::kHeadRedE>(w.e[I], w.e[I + 1], m, IMT_P0);
         cc::madwc_cc(w.e[I + 2], w.e[I + 3], m, IMT_P2);
         cc::madwc_cc(w.e[I + 4], w.e[I + 5], m, IMT_P4);
         cc::madwc_cc(w.e[I + 6], w.e[I + 7], m, IMT_P6);
         chain_top<false, true>(w, I + 8);
-        cc::madwc_cc(w.o[I], w.o[I + 1], m, IMT_P1);
+        cc::madw_head<cc::kHeadRedO>(w.o[I], w.o[I + 1], m, IMT_P1);
         cc::madwc_cc(w.o[I + 2], w.o[I + 3], m, IMT_P3);
         cc::madwc_cc(w.o[I + 4], w.o[I + 5], m, IMT_P5);
         cc::madwc_cc(w.o[I + 6], w.o[I + 7], m, IMT_P7);
@@ -374,12 +392,12 @@ IMT_HD void redc_row(Wide& w, uint32_t& cin) {
         w.o[I - 1] = t;
         cin = c1;
         m = t * IMT_INV32;
-        cc::madwc_cc(w.o[I - 1], w.o[I], m, IMT_P0);
+        cc::madw_head<cc::kHeadRedO>(w.o[I - 1], w.o[I], m, IMT_P0);
         cc::madwc_cc(w.o[I + 1], w.o[I + 2], m, IMT_P2);
         cc::madwc_cc(w.o[I + 3], w.o[I + 4], m, IMT_P4);
         cc::madwc_cc(w.o[I + 5], w.o[I + 6], m, IMT_P6);
         chain_top<false, false>(w, I + 8);
-        cc::madwc_cc(w.e[I + 1], w.e[I + 2], m, IMT_P1);
+        cc::madw_head<cc::kHeadRedE>(w.e[I + 1], w.e[I + 2], m, IMT_P1);
         cc::madwc_cc(w.e[I + 3], w.e[I + 4], m, IMT_P3);
         cc::madwc_cc(w.e[I + 5], w.e[I + 6], m, IMT_P5);
         cc::madwc_cc(w.e[I + 7], w.e[I + 8], m, IMT_P7);

@@ -53,8 +53,7 @@ imt_status finish(imt_ctx* ctx) {
 }  // namespace imt_host
 using namespace imt_host;
 
-namespace {
-
+namespace imt_host {
 imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
     if (n == 0) return fail(ctx, IMT_ERR_EMPTY, imt_status_string(IMT_ERR_EMPTY));
     if (n == 1) return IMT_OK;
@@ -62,6 +61,9 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n) {
     if (n & (n - 1)) return fail(ctx, IMT_ERR_NOT_POW2, imt_status_string(IMT_ERR_NOT_POW2));
     return IMT_OK;
 }
+}  // namespace imt_host
+
+namespace {
 
 // Batches (tree levels, insert levels, API calls) with at most this many hashes cannot fill the GPU with one thread per
 // hash and cost one full hash latency each: they go to the 3-lanes-per-hash kernels (poseidon_coop.cuh), which trade
@@ -142,7 +144,8 @@ imt_status build_upper_levels(imt_tree* t) {
     return launch_level_impl(ctx, t->d_levels + level_offset(t->n, t->depth - 1), t->d_levels + level_offset(t->n, t->depth), 1);
 }
 
-imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
+}  // namespace
+imt_status imt_host::tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
     imt_tree* t = new (std::nothrow) imt_tree();
     if (!t) return fail(ctx, IMT_ERR_CUDA, "out of host memory");
     t->ctx = ctx;
@@ -162,6 +165,7 @@ imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out) {
     *out = t;
     return IMT_OK;
 }
+namespace {
 
 // Leaf hashing of host preimages, pipelined: chunk k+1 is copied while chunk k is hashed. The chunk kernels alternate between
 // the compute stream and the auxiliary one: on a single stream every chunk boundary drains the GPU (the last blocks of chunk
@@ -200,15 +204,17 @@ imt_status hash_leaves_from_host(imt_tree* t, const void* preimages) {
         ctx->last_error = std::string("leaf staging: ") + cudaGetErrorString(e);
         st = IMT_ERR_CUDA;
     }
-    cudaStreamSynchronize(ctx->copy_stream);  // the caller's buffer is free again when this returns
-    if (st != IMT_OK) {
+    if (st != IMT_OK) {  // (on success the caller waits for the copies: imt_host::wait_staging)
+        cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamSynchronize(ctx->stream);
     }
     return st;
 }
 
-imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
+}  // namespace
+// Everything of a (re)build queued on the context's streams; returns without waiting (see imt_internal.h).
+imt_status imt_host::enqueue_rebuild(imt_tree* t, const void* preimages, bool device_src) {
     imt_ctx* ctx = t->ctx;
     if (!preimages) return fail(ctx, IMT_ERR_INVALID_ARG, "null preimages");
     if (!t->d_pre && !device_src) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
@@ -224,7 +230,23 @@ imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
     } else {
         IMT_TRY(hash_leaves_from_host(t, preimages));
     }
-    IMT_TRY(build_upper_levels(t));
+    return build_upper_levels(t);
+}
+// the caller's HOST buffer of a queued build has been consumed when this returns
+imt_status imt_host::wait_staging(imt_ctx* ctx) {
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return IMT_OK;
+}
+namespace {
+imt_status rebuild(imt_tree* t, const void* preimages, bool device_src) {
+    imt_ctx* ctx = t->ctx;
+    imt_status st = enqueue_rebuild(t, preimages, device_src);
+    if (st == IMT_OK && !device_src) st = wait_staging(ctx);
+    if (st != IMT_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return st;
+    }
     return finish(ctx);
 }
 
@@ -260,14 +282,15 @@ imt_status launch_convert(imt_ctx* ctx, const void* d_in, void* d_out, size_t n,
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
 }
-imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe) {
+imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe,
+                                bool select) {
     imt_ctx* ctx = t->ctx;
     const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
     const unsigned depth = t->depth + cap_depth;
     if (q == 0 || depth == 0) return IMT_OK;
     k_gather_proofs<<<grid_for(q * depth, 256), 256, 0, ctx->stream>>>(
         (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, d_idx, q, ctx->fmt,
-        (uint4*)d_siblings, d_helpers, (uint4*)d_helpers_fe, ctx->d_err);
+        (uint4*)d_siblings, d_helpers, (uint4*)d_helpers_fe, ctx->d_err, select ? (uint64_t)t->n * t->world : 0);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
@@ -788,7 +811,7 @@ extern "C" imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, 
 // Witness traces of verify_merkle_proof for leaves OF THIS TREE (indexed_merkle_tree.rs:65-96 with the paths of utils.rs:63-85):
 // all operands are stored levels, so the q x depth traced hashes run independently (k_trace_tree_paths) instead of as q
 // serial folds. states[q][depth][fe per hash]; identical bytes to imt_tree_get_proofs + imt_trace_merkle_proofs.
-static imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr) {
+imt_status imt_host::launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox) {
     imt_ctx* ctx = t->ctx;
     const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
     const unsigned depth = t->depth + cap_depth;
@@ -864,6 +887,13 @@ extern "C" imt_status imt_tree_trace_proofs(imt_tree* t, const uint64_t* indices
 }
 
 // ------------------------------------------------------------------------------------------------- sharding
+extern "C" imt_status imt_tree_shard_info(const imt_tree* t, unsigned* rank, unsigned* world, size_t* n_local) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    if (rank) *rank = t->rank;
+    if (world) *world = t->world;
+    if (n_local) *n_local = t->n;
+    return IMT_OK;
+}
 extern "C" imt_status imt_tree_subtree_root_dev(imt_tree* t, const void** d_subtree_root) {
     if (!t || !d_subtree_root) return IMT_ERR_INVALID_ARG;
     imt_ctx* ctx = t->ctx;

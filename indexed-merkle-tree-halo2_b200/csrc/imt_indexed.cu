@@ -258,12 +258,22 @@ __global__ void __launch_bounds__(256) k_is_zero(const uint4* __restrict__ value
     out[i] = zero256(v) ? 1 : 0;
 }
 
+// n_total_select != 0: an index owned by another rank writes zeros instead of raising kErrIndexOob (see k_gather_proofs)
 __global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__ pre, size_t n, uint64_t base,
                                                        const uint64_t* __restrict__ idx, size_t q, uint4* __restrict__ leaves,
-                                                       uint8_t* __restrict__ is_largest, uint32_t* __restrict__ err) {
+                                                       uint8_t* __restrict__ is_largest, uint32_t* __restrict__ err,
+                                                       uint64_t n_total_select = 0) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= q) return;
     if (idx[i] < base || idx[i] - base >= n) {
+        if (n_total_select && idx[i] < n_total_select) {
+            if (leaves) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) leaves[6 * i + k] = make_uint4(0, 0, 0, 0);
+            }
+            if (is_largest) is_largest[i] = 0;
+            return;
+        }
         atomicOr(err, kErrIndexOob);
         return;
     }
@@ -697,7 +707,8 @@ imt_status sort_pairs(imt_ctx* ctx, Fr* d_keys, uint32_t* d_slots, size_t count)
     return IMT_OK;
 }
 
-imt_status ensure_index(imt_tree* t) {
+}  // namespace
+imt_status imt_host::ensure_index(imt_tree* t) {
     imt_ctx* ctx = t->ctx;
     if (t->index_valid) return IMT_OK;
     if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves: no preimages to index");
@@ -740,6 +751,7 @@ imt_status ensure_index(imt_tree* t) {
     t->index_valid = true;
     return IMT_OK;
 }
+namespace {
 
 imt_status lookup_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low, uint8_t* d_matched) {
     imt_ctx* ctx = t->ctx;
@@ -1332,4 +1344,636 @@ extern "C" imt_status imt_shard_insert_cap(imt_tree* t, const uint64_t* x, const
     if (sib_cap && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(sib_cap, sib.p, (size_t)writes * depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- sharded calls (NCCL inside)
+// The same sharded algorithms the piecewise calls above expose to a caller-driven exchange, with the exchange done here through
+// the group's transport (imt_comm.cu). `Parts` = the shards of one tree this process drives: one in process-per-GPU mode, all
+// of them in single-process mode. Per-rank phases run on one host thread per local shard (a context is single-threaded, two
+// contexts are independent); collectives are issued by the calling thread between the phases.
+#include <thread>
+
+namespace {
+
+struct Parts {
+    imt_group* g = nullptr;
+    std::vector<imt_tree*> t;  // local shards, ascending rank
+    size_t n_total() const { return t[0]->n * (size_t)group_world(g); }
+};
+
+imt_status parts_of_tree(imt_tree* tree, Parts* p) {
+    if (!tree) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = tree->ctx;
+    if (!ctx->group) return fail(ctx, IMT_ERR_INVALID_ARG, "the context has no communicator: call imt_comm_create first");
+    if (group_local_count(ctx->group) != 1) return fail(ctx, IMT_ERR_INVALID_ARG, "this tree is a shard of an imt_mtree: use the imt_mtree_* calls");
+    if (!tree->cap_valid) return fail(ctx, IMT_ERR_INVALID_ARG, "no cap attached: exchange the subtree roots first");
+    p->g = ctx->group;
+    p->t = {tree};
+    return IMT_OK;
+}
+imt_status parts_of_mtree(imt_mtree* mt, Parts* p) {
+    IMT_TRY(mtree_parts(mt, &p->g, &p->t));
+    for (imt_tree* t : p->t)
+        if (!t->cap_valid) return fail(t->ctx, IMT_ERR_INVALID_ARG, "no cap attached");
+    return IMT_OK;
+}
+
+// fn(slot) on every local shard, concurrently when there are several; returns the first failure
+template <class Fn>
+imt_status for_each_part(const Parts& p, Fn fn) {
+    const size_t n = p.t.size();
+    if (n == 1) return fn((size_t)0);
+    std::vector<imt_status> st(n, IMT_OK);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (size_t i = 0; i < n; ++i) th.emplace_back([&, i] { st[i] = fn(i); });
+    for (auto& x : th) x.join();
+    for (size_t i = 0; i < n; ++i)
+        if (st[i] != IMT_OK) {
+            if (i) p.t[0]->ctx->last_error = p.t[i]->ctx->last_error;
+            return st[i];
+        }
+    return IMT_OK;
+}
+
+// ---- low-leaf lookups: per-rank candidates packed as [header 32 B][keys q x 32][slots q x 8][flags q], one all-gather, merge
+constexpr size_t kCandHeader = 32;
+size_t cand_bytes(size_t q) { return (kCandHeader + q * 41 + 15) & ~(size_t)15; }
+__global__ void k_cand_header(unsigned long long* hdr, unsigned long long occupied, unsigned long long head_next_zero) {
+    hdr[0] = occupied, hdr[1] = head_next_zero, hdr[2] = 0, hdr[3] = 0;
+}
+__global__ void __launch_bounds__(256) k_low_leaf_merge_packed(const uint8_t* __restrict__ gathered, size_t stride, unsigned world, size_t q,
+                                                               uint64_t n_total, const uint4* __restrict__ values,
+                                                               uint64_t* __restrict__ low_idx, uint8_t* __restrict__ matched,
+                                                               unsigned long long* __restrict__ occupied_out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    uint64_t occupied = 0;
+    for (unsigned r = 0; r < world; ++r) occupied += reinterpret_cast<const unsigned long long*>(gathered + (size_t)r * stride)[0];
+    const bool head_next_zero = reinterpret_cast<const unsigned long long*>(gathered)[1] != 0;  // rank 0 owns slot 0
+    if (i == 0 && occupied_out) *occupied_out = occupied;
+    if (i >= q) return;
+    uint32_t best[8], v[8];
+    bool have = false, present = false;
+    uint64_t slot = 0;
+    for (unsigned r = 0; r < world; ++r) {
+        const uint8_t* blk = gathered + (size_t)r * stride + kCandHeader;
+        const uint8_t f = blk[q * 40 + i];
+        present |= (f & 2) != 0;
+        if (f & 1) {
+            uint32_t k[8];
+            load_fe(k, reinterpret_cast<const uint4*>(blk) + 2 * i);
+            if (!have || cmp256(k, best) > 0) copy256(best, k), slot = reinterpret_cast<const uint64_t*>(blk + q * 32)[i], have = true;
+        }
+    }
+    load_fe(v, values + 2 * i);
+    uint64_t low = 0;
+    uint8_t hit = 0;
+    if (head_next_zero) hit = 1;
+    else if (have && !present) low = slot, hit = 1;
+    else if (!zero256(v) && occupied < n_total) low = occupied, hit = 1;
+    low_idx[i] = low;
+    if (matched) matched[i] = hit;
+}
+
+// Device buffers of one local shard for a batch of q replicated queries
+struct PartBufs {
+    DevBuf values, low, matched, pack, gathered, occupied;
+    explicit PartBufs(imt_ctx* c) : values(c), low(c), matched(c), pack(c), gathered(c), occupied(c) {}
+};
+
+// every local shard: values already on the device -> d_low / d_matched (replicated). occupied_total (optional) on the host.
+imt_status sharded_lookup_dev(const Parts& p, std::vector<PartBufs*>& b, size_t q, uint64_t* occupied_total) {
+    const unsigned world = group_world(p.g);
+    const size_t stride = cand_bytes(q);
+    IMT_TRY(for_each_part(p, [&](size_t i) -> imt_status {
+        imt_tree* t = p.t[i];
+        imt_ctx* ctx = t->ctx;
+        IMT_TRY(ensure_index(t));
+        IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+        IMT_TRY_CUDA(ctx, b[i]->pack.alloc(stride));
+        IMT_TRY_CUDA(ctx, b[i]->gathered.alloc(stride * world));
+        IMT_TRY_CUDA(ctx, b[i]->low.alloc(q * sizeof(uint64_t)));
+        IMT_TRY_CUDA(ctx, b[i]->matched.alloc(q));
+        IMT_TRY_CUDA(ctx, b[i]->occupied.alloc(sizeof(unsigned long long)));
+        IMT_TRY(clear_err(ctx));
+        uint8_t* pk = b[i]->pack.as<uint8_t>();
+        k_cand_header<<<1, 1, 0, ctx->stream>>>((unsigned long long*)pk, t->occupied, (t->rank == 0 && t->head_next_zero) ? 1ull : 0ull);
+        if (q)
+            k_low_leaf_candidates<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied,
+                                                                             (uint64_t)t->rank * t->n, b[i]->values.as<uint4>(), q, ctx->fmt,
+                                                                             (uint4*)(pk + kCandHeader), (uint64_t*)(pk + kCandHeader + q * 32),
+                                                                             pk + kCandHeader + q * 40, ctx->d_err);
+        ctx->launches += 2;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        return IMT_OK;
+    }));
+    std::vector<const void*> send(p.t.size());
+    std::vector<void*> recv(p.t.size());
+    for (size_t i = 0; i < p.t.size(); ++i) send[i] = b[i]->pack.p, recv[i] = b[i]->gathered.p;
+    IMT_TRY(group_all_gather(p.g, send, recv, stride));
+    return for_each_part(p, [&](size_t i) -> imt_status {
+        imt_tree* t = p.t[i];
+        imt_ctx* ctx = t->ctx;
+        IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+        k_low_leaf_merge_packed<<<grid_for(q ? q : 1, 256), 256, 0, ctx->stream>>>(b[i]->gathered.as<uint8_t>(), stride, world, q, p.n_total(),
+                                                                                   b[i]->values.as<uint4>(), b[i]->low.as<uint64_t>(),
+                                                                                   b[i]->matched.as<uint8_t>(), b[i]->occupied.as<unsigned long long>());
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        if (i == 0 && occupied_total) {
+            unsigned long long occ = 0;
+            IMT_TRY_CUDA(ctx, cudaMemcpyAsync(&occ, b[i]->occupied.p, sizeof(occ), cudaMemcpyDeviceToHost, ctx->stream));
+            IMT_TRY(finish(ctx));
+            *occupied_total = occ;
+            return IMT_OK;
+        }
+        return finish(ctx);
+    });
+}
+
+// every local shard: d_idx (replicated, GLOBAL) -> the owner's rows, zeros elsewhere -> sum over ranks: replicated paths / leaves
+imt_status sharded_gather_dev(const Parts& p, const std::vector<const uint64_t*>& d_idx, size_t q, const std::vector<void*>& d_sib,
+                              const std::vector<uint8_t*>& d_hel, const std::vector<void*>& d_leaves, const std::vector<uint8_t*>& d_largest) {
+    const unsigned depth = p.t[0]->depth + p.t[0]->cap_depth;
+    const bool paths = !d_sib.empty() && depth, hel = !d_hel.empty() && depth, leaves = !d_leaves.empty(), largest = !d_largest.empty();
+    IMT_TRY(for_each_part(p, [&](size_t i) -> imt_status {
+        imt_tree* t = p.t[i];
+        imt_ctx* ctx = t->ctx;
+        IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+        IMT_TRY(clear_err(ctx));
+        if (paths) IMT_TRY(launch_gather_proofs(t, d_idx[i], q, d_sib[i], hel ? d_hel[i] : nullptr, nullptr, true));
+        if (leaves || largest) {
+            if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+            k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, (uint64_t)t->rank * t->n, d_idx[i], q,
+                                                                       leaves ? (uint4*)d_leaves[i] : nullptr, largest ? d_largest[i] : nullptr,
+                                                                       ctx->d_err, p.n_total());
+            ++ctx->launches;
+            IMT_TRY_CUDA(ctx, cudaGetLastError());
+        }
+        return finish(ctx);  // index errors surface before the collective (every rank sees the same indices: all fail alike)
+    }));
+    auto reduce = [&](auto& bufs, size_t count, bool bytes8) -> imt_status {
+        std::vector<void*> v(bufs.size());
+        for (size_t i = 0; i < bufs.size(); ++i) v[i] = (void*)bufs[i];
+        return group_all_reduce_sum(p.g, v, count, bytes8);
+    };
+    if (paths) IMT_TRY(reduce(d_sib, q * depth * 4, false));
+    if (paths && hel) IMT_TRY(reduce(d_hel, q * depth, true));
+    if (leaves) IMT_TRY(reduce(d_leaves, q * 12, false));
+    if (largest) IMT_TRY(reduce(d_largest, q, true));
+    return IMT_OK;
+}
+
+imt_status sync_all(const Parts& p) {
+    for (imt_tree* t : p.t) {
+        IMT_TRY_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+        IMT_TRY_CUDA(t->ctx, cudaStreamSynchronize(t->ctx->stream));
+    }
+    return IMT_OK;
+}
+
+// ---- host-facing: lookups / non-inclusion witnesses (replicated inputs; outputs read from the first local shard)
+imt_status sharded_non_inclusion(const Parts& p, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched, void* low_leaves,
+                                 void* siblings, uint8_t* helpers, uint8_t* is_largest, uint64_t* occupied_total) {
+    imt_ctx* c0 = p.t[0]->ctx;
+    if (q && !values) return fail(c0, IMT_ERR_INVALID_ARG, "null buffer");
+    const unsigned depth = p.t[0]->depth + p.t[0]->cap_depth;
+    const size_t nl = p.t.size();
+    std::vector<PartBufs*> b(nl, nullptr);
+    std::vector<DevBuf*> dlv(nl, nullptr), dsib(nl, nullptr), dhel(nl, nullptr), dlg(nl, nullptr);
+    auto cleanup = [&] {
+        for (size_t i = 0; i < nl; ++i) {
+            cudaSetDevice(p.t[i]->ctx->device);
+            delete b[i], delete dlv[i], delete dsib[i], delete dhel[i], delete dlg[i];
+        }
+    };
+    imt_status st = IMT_OK;
+    for (size_t i = 0; i < nl && st == IMT_OK; ++i) {
+        imt_ctx* ctx = p.t[i]->ctx;
+        cudaSetDevice(ctx->device);
+        b[i] = new PartBufs(ctx);
+        dlv[i] = new DevBuf(ctx), dsib[i] = new DevBuf(ctx), dhel[i] = new DevBuf(ctx), dlg[i] = new DevBuf(ctx);
+        cudaError_t e = b[i]->values.alloc(q * sizeof(Fr));
+        if (e == cudaSuccess && q) e = cudaMemcpyAsync(b[i]->values.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && low_leaves) e = dlv[i]->alloc(q * 3 * sizeof(Fr));
+        if (e == cudaSuccess && (siblings || helpers)) e = dsib[i]->alloc(q * (size_t)depth * sizeof(Fr));
+        if (e == cudaSuccess && helpers) e = dhel[i]->alloc(q * (size_t)depth);
+        if (e == cudaSuccess && is_largest) e = dlg[i]->alloc(q);
+        if (e != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (st == IMT_OK) st = sharded_lookup_dev(p, b, q, occupied_total);
+    if (st == IMT_OK && q && (low_leaves || siblings || helpers || is_largest)) {
+        std::vector<const uint64_t*> idx(nl);
+        std::vector<void*> vs, vl;
+        std::vector<uint8_t*> vh, vg;
+        for (size_t i = 0; i < nl; ++i) {
+            idx[i] = b[i]->low.as<uint64_t>();
+            if (siblings || helpers) vs.push_back(dsib[i]->p);
+            if (helpers) vh.push_back(dhel[i]->as<uint8_t>());
+            if (low_leaves) vl.push_back(dlv[i]->p);
+            if (is_largest) vg.push_back(dlg[i]->as<uint8_t>());
+        }
+        st = sharded_gather_dev(p, idx, q, vs, vh, vl, vg);
+    }
+    if (st == IMT_OK && q) {
+        imt_ctx* ctx = c0;
+        cudaSetDevice(ctx->device);
+        cudaError_t e = cudaSuccess;
+        auto d2h = [&](void* host, const void* dev, size_t bytes) {
+            if (host && bytes && e == cudaSuccess) e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        };
+        d2h(low_idx, b[0]->low.p, q * sizeof(uint64_t));
+        d2h(matched, b[0]->matched.p, q);
+        d2h(low_leaves, dlv[0]->p, q * 3 * sizeof(Fr));
+        d2h(siblings, dsib[0]->p, q * (size_t)depth * sizeof(Fr));
+        d2h(helpers, dhel[0]->p, q * (size_t)depth);
+        d2h(is_largest, dlg[0]->p, q);
+        if (e != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    const imt_status s2 = sync_all(p);
+    cleanup();
+    return st != IMT_OK ? st : s2;
+}
+
+imt_status sharded_gather_host(const Parts& p, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers, void* leaves,
+                               uint8_t* is_largest) {
+    imt_ctx* c0 = p.t[0]->ctx;
+    if (q && !indices) return fail(c0, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    const unsigned depth = p.t[0]->depth + p.t[0]->cap_depth;
+    const size_t nl = p.t.size();
+    std::vector<DevBuf*> di(nl, nullptr), dlv(nl, nullptr), dsib(nl, nullptr), dhel(nl, nullptr), dlg(nl, nullptr);
+    imt_status st = IMT_OK;
+    for (size_t i = 0; i < nl && st == IMT_OK; ++i) {
+        imt_ctx* ctx = p.t[i]->ctx;
+        cudaSetDevice(ctx->device);
+        di[i] = new DevBuf(ctx), dlv[i] = new DevBuf(ctx), dsib[i] = new DevBuf(ctx), dhel[i] = new DevBuf(ctx), dlg[i] = new DevBuf(ctx);
+        cudaError_t e = di[i]->alloc(q * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(di[i]->p, indices, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && leaves) e = dlv[i]->alloc(q * 3 * sizeof(Fr));
+        if (e == cudaSuccess && (siblings || helpers)) e = dsib[i]->alloc(q * (size_t)depth * sizeof(Fr));
+        if (e == cudaSuccess && helpers) e = dhel[i]->alloc(q * (size_t)depth);
+        if (e == cudaSuccess && is_largest) e = dlg[i]->alloc(q);
+        if (e != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (st == IMT_OK) {
+        std::vector<const uint64_t*> idx(nl);
+        std::vector<void*> vs, vl;
+        std::vector<uint8_t*> vh, vg;
+        for (size_t i = 0; i < nl; ++i) {
+            idx[i] = di[i]->as<uint64_t>();
+            if (siblings || helpers) vs.push_back(dsib[i]->p);
+            if (helpers) vh.push_back(dhel[i]->as<uint8_t>());
+            if (leaves) vl.push_back(dlv[i]->p);
+            if (is_largest) vg.push_back(dlg[i]->as<uint8_t>());
+        }
+        st = sharded_gather_dev(p, idx, q, vs, vh, vl, vg);
+    }
+    if (st == IMT_OK) {
+        cudaSetDevice(c0->device);
+        cudaError_t e = cudaSuccess;
+        auto d2h = [&](void* host, const void* dev, size_t bytes) {
+            if (host && bytes && e == cudaSuccess) e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c0->stream);
+        };
+        d2h(siblings, dsib[0]->p, q * (size_t)depth * sizeof(Fr));
+        d2h(helpers, dhel[0]->p, q * (size_t)depth);
+        d2h(leaves, dlv[0]->p, q * 3 * sizeof(Fr));
+        d2h(is_largest, dlg[0]->p, q);
+        if (e != cudaSuccess) st = fail(c0, IMT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    const imt_status s2 = sync_all(p);
+    for (size_t i = 0; i < nl; ++i) {
+        cudaSetDevice(p.t[i]->ctx->device);
+        delete di[i], delete dlv[i], delete dsib[i], delete dhel[i], delete dlg[i];
+    }
+    return st != IMT_OK ? st : s2;
+}
+
+// ---- host-staged collectives for the (small) plan arrays of an insert round
+imt_status host_all_gather(const Parts& p, const std::vector<const void*>& h_send, size_t bytes, std::vector<uint8_t>* h_recv) {
+    const size_t nl = p.t.size();
+    const unsigned world = group_world(p.g);
+    std::vector<DevBuf*> s(nl, nullptr), r(nl, nullptr);
+    std::vector<const void*> send(nl);
+    std::vector<void*> recv(nl);
+    imt_status st = IMT_OK;
+    for (size_t i = 0; i < nl && st == IMT_OK; ++i) {
+        imt_ctx* ctx = p.t[i]->ctx;
+        cudaSetDevice(ctx->device);
+        s[i] = new DevBuf(ctx), r[i] = new DevBuf(ctx);
+        cudaError_t e = s[i]->alloc(bytes);
+        if (e == cudaSuccess) e = r[i]->alloc(bytes * world);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s[i]->p, h_send[i], bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, cudaGetErrorString(e));
+        send[i] = s[i]->p, recv[i] = r[i]->p;
+    }
+    if (st == IMT_OK) st = group_all_gather(p.g, send, recv, bytes);
+    if (st == IMT_OK) {
+        imt_ctx* ctx = p.t[0]->ctx;
+        cudaSetDevice(ctx->device);
+        h_recv->resize(bytes * world);
+        if (cudaMemcpyAsync(h_recv->data(), r[0]->p, bytes * world, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            st = fail(ctx, IMT_ERR_CUDA, "all-gather read back failed");
+    }
+    const imt_status s2 = sync_all(p);
+    for (size_t i = 0; i < nl; ++i) {
+        cudaSetDevice(p.t[i]->ctx->device);
+        delete s[i], delete r[i];
+    }
+    return st != IMT_OK ? st : s2;
+}
+// in place on the host arrays of every local shard: element-wise sum over ranks (one owner per element); result in h[0]
+imt_status host_all_reduce_u64(const Parts& p, const std::vector<void*>& h, size_t count) {
+    const size_t nl = p.t.size(), bytes = count * 8;
+    std::vector<DevBuf*> d(nl, nullptr);
+    std::vector<void*> v(nl);
+    imt_status st = IMT_OK;
+    for (size_t i = 0; i < nl && st == IMT_OK; ++i) {
+        imt_ctx* ctx = p.t[i]->ctx;
+        cudaSetDevice(ctx->device);
+        d[i] = new DevBuf(ctx);
+        cudaError_t e = d[i]->alloc(bytes);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d[i]->p, h[i], bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, cudaGetErrorString(e));
+        v[i] = d[i]->p;
+    }
+    if (st == IMT_OK) st = group_all_reduce_sum(p.g, v, count, false);
+    if (st == IMT_OK) {
+        imt_ctx* ctx = p.t[0]->ctx;
+        cudaSetDevice(ctx->device);
+        if (cudaMemcpyAsync(h[0], d[0]->p, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = fail(ctx, IMT_ERR_CUDA, "all-reduce read back failed");
+    }
+    const imt_status s2 = sync_all(p);
+    for (size_t i = 0; i < nl; ++i) {
+        cudaSetDevice(p.t[i]->ctx->device);
+        delete d[i];
+    }
+    return st != IMT_OK ? st : s2;
+}
+
+// ---- inserts: the rounds of imt_shard_insert_* with the exchanges done here
+imt_status sharded_insert(const Parts& p, const void* new_vals, size_t b_total, uint64_t first_idx, imt_insert_witness* w) {
+    imt_ctx* c0 = p.t[0]->ctx;
+    if (b_total && !new_vals) return fail(c0, IMT_ERR_INVALID_ARG, "null buffer");
+    for (imt_tree* t : p.t)
+        if (!t->d_pre) return fail(c0, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    const unsigned world = group_world(p.g), d_local = p.t[0]->depth, d_cap = p.t[0]->cap_depth, depth = d_local + d_cap;
+    const size_t nl = p.t.size(), n_total = p.n_total();
+    // total occupancy: the lookup machinery with zero queries carries the per-rank counts
+    uint64_t occupied = 0;
+    {
+        std::vector<PartBufs*> pb(nl, nullptr);
+        imt_status st = IMT_OK;
+        for (size_t i = 0; i < nl && st == IMT_OK; ++i) {
+            cudaSetDevice(p.t[i]->ctx->device);
+            pb[i] = new PartBufs(p.t[i]->ctx);
+            if (pb[i]->values.alloc(16) != cudaSuccess) st = fail(p.t[i]->ctx, IMT_ERR_CUDA, "alloc");
+        }
+        if (st == IMT_OK) st = sharded_lookup_dev(p, pb, 0, &occupied);
+        const imt_status s2 = sync_all(p);
+        for (size_t i = 0; i < nl; ++i) {
+            cudaSetDevice(p.t[i]->ctx->device);
+            delete pb[i];
+        }
+        IMT_TRY(st);
+        IMT_TRY(s2);
+    }
+    if (first_idx != occupied) return fail(c0, IMT_ERR_INVALID_ARG, "first_idx must be the next free slot (the total number of occupied slots)");
+    if (b_total > n_total - occupied) return fail(c0, IMT_ERR_TREE_FULL, imt_status_string(IMT_ERR_TREE_FULL));
+    const imt_insert_witness none = {};
+    const imt_insert_witness out = w ? *w : none;
+    const Fr* vals_all = static_cast<const Fr*>(new_vals);
+    for (size_t off = 0; off < b_total; off += kShardInsertRound) {
+        const size_t b = std::min(kShardInsertRound, b_total - off), W = 2 * b;
+        const Fr* vals = vals_all + off;
+        Fr root_before;
+        IMT_TRY(imt_tree_root(p.t[0], &root_before));
+        // 1. neighbours of every value in each rank's own index, packed [pred keys][succ keys][pred slots][succ slots][flags]
+        const size_t nb = b * (32 + 32 + 8 + 8 + 1);
+        std::vector<std::vector<uint8_t>> packs(nl, std::vector<uint8_t>(nb));
+        IMT_TRY(for_each_part(p, [&](size_t i) -> imt_status {
+            uint8_t* pk = packs[i].data();
+            return imt_shard_insert_neighbors(p.t[i], vals, b, pk, (uint64_t*)(pk + b * 64), pk + b * 32, (uint64_t*)(pk + b * 72), pk + b * 80);
+        }));
+        std::vector<const void*> hs(nl);
+        for (size_t i = 0; i < nl; ++i) hs[i] = packs[i].data();
+        std::vector<uint8_t> gathered;
+        IMT_TRY(host_all_gather(p, hs, nb, &gathered));
+        // 2. the replicated plan (identical on every rank: computed once per process)
+        std::vector<Fr> pk_all((size_t)world * b), sk_all((size_t)world * b);
+        std::vector<uint64_t> ps_all((size_t)world * b), ss_all((size_t)world * b);
+        std::vector<uint8_t> fl_all((size_t)world * b);
+        for (unsigned r = 0; r < world; ++r) {
+            const uint8_t* blk = gathered.data() + (size_t)r * nb;
+            std::memcpy(&pk_all[(size_t)r * b], blk, b * 32);
+            std::memcpy(&sk_all[(size_t)r * b], blk + b * 32, b * 32);
+            std::memcpy(&ps_all[(size_t)r * b], blk + b * 64, b * 8);
+            std::memcpy(&ss_all[(size_t)r * b], blk + b * 72, b * 8);
+            std::memcpy(&fl_all[(size_t)r * b], blk + b * 80, b);
+        }
+        std::vector<uint64_t> x(W);
+        std::vector<Fr> upd(W * 3), low_old(b * 3);
+        std::vector<uint8_t> largest(b);
+        IMT_TRY(imt_shard_insert_plan(c0, vals, b, first_idx + off, world, pk_all.data(), ps_all.data(), sk_all.data(), ss_all.data(), fl_all.data(),
+                                      x.data(), upd.data(), low_old.data(), largest.data()));
+        // 3. every rank applies its own writes to its subtree
+        std::vector<std::vector<Fr>> sub(nl, std::vector<Fr>(W)), sibl(nl, std::vector<Fr>(W * (size_t)(d_local ? d_local : 1)));
+        IMT_TRY(for_each_part(p, [&](size_t i) -> imt_status {
+            return imt_shard_insert_apply(p.t[i], x.data(), upd.data(), b, sub[i].data(), sibl[i].data());
+        }));
+        // 4. each write has one owner: a sum over ranks assembles the subtree-root versions and the local paths
+        {
+            std::vector<void*> v(nl);
+            for (size_t i = 0; i < nl; ++i) v[i] = sub[i].data();
+            IMT_TRY(host_all_reduce_u64(p, v, W * 4));
+            if (d_local) {
+                for (size_t i = 0; i < nl; ++i) v[i] = sibl[i].data();
+                IMT_TRY(host_all_reduce_u64(p, v, W * (size_t)d_local * 4));
+            }
+        }
+        // 5. all writes on the replicated cap
+        std::vector<std::vector<Fr>> roots(nl, std::vector<Fr>(W)), sibc(nl, std::vector<Fr>(W * (size_t)(d_cap ? d_cap : 1)));
+        IMT_TRY(for_each_part(p, [&](size_t i) -> imt_status {
+            return imt_shard_insert_cap(p.t[i], x.data(), sub[0].data(), b, roots[i].data(), d_cap ? sibc[i].data() : nullptr);
+        }));
+        // 6. witnesses of this round (IMT:444-489), from the first local shard's replicated copies
+        const Fr* rt = roots[0].data();
+        for (size_t k = 0; k < b; ++k) {
+            const size_t o = off + k;
+            if (out.old_roots) static_cast<Fr*>(out.old_roots)[o] = k ? rt[2 * k - 1] : root_before;
+            if (out.new_roots) static_cast<Fr*>(out.new_roots)[o] = rt[2 * k + 1];
+            if (out.low_idx) out.low_idx[o] = x[2 * k];
+            if (out.is_largest) out.is_largest[o] = largest[k];
+            if (out.low_leaves) std::memcpy(static_cast<Fr*>(out.low_leaves) + 3 * o, &low_old[3 * k], 3 * sizeof(Fr));
+            if (out.new_leaves) std::memcpy(static_cast<Fr*>(out.new_leaves) + 3 * o, &upd[3 * (2 * k + 1)], 3 * sizeof(Fr));
+            for (int side = 0; side < 2; ++side) {
+                const size_t t = 2 * k + side;
+                Fr* sib_out = static_cast<Fr*>(side ? out.new_siblings : out.low_siblings);
+                uint8_t* hel_out = side ? out.new_helpers : out.low_helpers;
+                if (sib_out) {
+                    if (d_local) std::memcpy(sib_out + o * depth, &sibl[0][t * d_local], d_local * sizeof(Fr));
+                    if (d_cap) std::memcpy(sib_out + o * depth + d_local, &sibc[0][t * d_cap], d_cap * sizeof(Fr));
+                }
+                if (hel_out)
+                    for (unsigned l = 0; l < depth; ++l) hel_out[o * depth + l] = ((x[t] >> l) & 1) == 0;  // 1 = current node is LEFT (utils.rs:70)
+            }
+        }
+    }
+    return IMT_OK;
+}
+
+// owner-sharded witness traces: the positions (into `indices`) of the queries whose leaves shard t owns
+std::vector<uint64_t> owned_positions(const imt_tree* t, const uint64_t* indices, size_t q, uint64_t n_total, bool* oob) {
+    std::vector<uint64_t> pos;
+    const uint64_t base = (uint64_t)t->rank * t->n;
+    for (size_t i = 0; i < q; ++i) {
+        if (indices[i] >= n_total) *oob = true;
+        else if (indices[i] >= base && indices[i] - base < t->n) pos.push_back(i);
+    }
+    return pos;
+}
+
+}  // namespace
+
+// ---- one process per GPU
+extern "C" imt_status imt_sharded_get_proofs(imt_tree* tree, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    if (q && !siblings) return fail(tree->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_gather_host(p, indices, q, siblings, helpers, nullptr, nullptr);
+}
+extern "C" imt_status imt_sharded_leaves(imt_tree* tree, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    return sharded_gather_host(p, indices, q, nullptr, nullptr, leaves, is_largest);
+}
+extern "C" imt_status imt_sharded_low_leaf_lookup(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    if (q && !low_idx) return fail(tree->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_non_inclusion(p, values, q, low_idx, matched, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+extern "C" imt_status imt_sharded_occupied(imt_tree* tree, uint64_t* occupied_total) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    if (!occupied_total) return fail(tree->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_non_inclusion(p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, occupied_total);
+}
+extern "C" imt_status imt_sharded_non_inclusion_paths(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                                      void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    return sharded_non_inclusion(p, values, q, low_idx, matched, low_leaves, siblings, helpers, is_largest, nullptr);
+}
+extern "C" imt_status imt_sharded_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w) {
+    Parts p;
+    IMT_TRY(parts_of_tree(tree, &p));
+    return sharded_insert(p, new_vals, b, first_idx, w);
+}
+extern "C" imt_status imt_sharded_trace_proofs(imt_tree* tree, const uint64_t* indices, size_t q, uint64_t* positions, size_t* n_mine, void* states) {
+    if (!tree) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = tree->ctx;
+    if (!n_mine || (q && (!indices || !positions))) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    *n_mine = 0;
+    if (!tree->cap_valid && tree->world > 1) return fail(ctx, IMT_ERR_INVALID_ARG, "no cap attached: exchange the subtree roots first");
+    bool oob = false;
+    const std::vector<uint64_t> pos = owned_positions(tree, indices, q, (uint64_t)tree->n * tree->world, &oob);
+    if (oob) return fail(ctx, IMT_ERR_INDEX_OOB, "index out of bounds");
+    std::vector<uint64_t> mine(pos.size());
+    for (size_t j = 0; j < pos.size(); ++j) mine[j] = indices[pos[j]], positions[j] = pos[j];
+    *n_mine = pos.size();
+    if (pos.empty()) return IMT_OK;
+    if (!states) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return imt_tree_trace_proofs(tree, mine.data(), mine.size(), states);
+}
+
+// ---- one process, N GPUs
+extern "C" imt_status imt_mtree_get_proofs(imt_mtree* mt, const uint64_t* indices, size_t q, void* siblings, uint8_t* helpers) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    if (q && !siblings) return fail(p.t[0]->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_gather_host(p, indices, q, siblings, helpers, nullptr, nullptr);
+}
+extern "C" imt_status imt_mtree_leaves(imt_mtree* mt, const uint64_t* indices, size_t q, void* leaves, uint8_t* is_largest) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    return sharded_gather_host(p, indices, q, nullptr, nullptr, leaves, is_largest);
+}
+extern "C" imt_status imt_mtree_low_leaf_lookup(imt_mtree* mt, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    if (q && !low_idx) return fail(p.t[0]->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_non_inclusion(p, values, q, low_idx, matched, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+extern "C" imt_status imt_mtree_occupied(imt_mtree* mt, uint64_t* occupied_total) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    if (!occupied_total) return fail(p.t[0]->ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    return sharded_non_inclusion(p, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, occupied_total);
+}
+extern "C" imt_status imt_mtree_non_inclusion_paths(imt_mtree* mt, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched,
+                                                    void* low_leaves, void* siblings, uint8_t* helpers, uint8_t* is_largest) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    return sharded_non_inclusion(p, values, q, low_idx, matched, low_leaves, siblings, helpers, is_largest, nullptr);
+}
+extern "C" imt_status imt_mtree_insert_batch(imt_mtree* mt, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    return sharded_insert(p, new_vals, b, first_idx, w);
+}
+// Every device traces the queries it owns — each traced hash reads stored nodes of that device's subtree or of the replicated
+// cap — and drains them over its own PCIe link straight to their place in the caller's array (one copy per query: a depth-24
+// path is 304 KB of trace, large enough for the link).
+extern "C" imt_status imt_mtree_trace_proofs(imt_mtree* mt, const uint64_t* indices, size_t q, void* states) {
+    Parts p;
+    IMT_TRY(parts_of_mtree(mt, &p));
+    imt_ctx* c0 = p.t[0]->ctx;
+    if (q && (!indices || !states)) return fail(c0, IMT_ERR_INVALID_ARG, "null buffer");
+    if (q == 0) return IMT_OK;
+    const uint64_t n_total = p.n_total();
+    const unsigned depth = p.t[0]->depth + p.t[0]->cap_depth;
+    const size_t per_query = (size_t)depth * trace_fe_per_hash(c0, 2) * sizeof(Fr);
+    for (size_t i = 0; i < q; ++i)
+        if (indices[i] >= n_total) return fail(c0, IMT_ERR_INDEX_OOB, "index out of bounds");
+    return for_each_part(p, [&](size_t s) -> imt_status {
+        imt_tree* t = p.t[s];
+        imt_ctx* ctx = t->ctx;
+        bool oob = false;
+        const std::vector<uint64_t> pos = owned_positions(t, indices, q, n_total, &oob);
+        if (pos.empty()) return IMT_OK;
+        IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+        std::vector<uint64_t> mine(pos.size());
+        for (size_t j = 0; j < pos.size(); ++j) mine[j] = indices[pos[j]];
+        size_t chunk = 4096;
+        while (chunk > 64 && chunk * per_query > ((size_t)2 << 30)) chunk >>= 1;
+        chunk = std::min(chunk, pos.size());
+        DevBuf di(ctx), buf0(ctx), buf1(ctx);
+        IMT_TRY_CUDA(ctx, di.alloc(mine.size() * sizeof(uint64_t)));
+        IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
+        if (pos.size() > chunk) IMT_TRY_CUDA(ctx, buf1.alloc(chunk * per_query));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(di.p, mine.data(), mine.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        IMT_TRY(clear_err(ctx));
+        void* bufs[2] = {buf0.p, buf1.p};
+        Event produced[2], drained[2];
+        for (int k = 0; k < 2; ++k) {
+            IMT_TRY_CUDA(ctx, produced[k].create());
+            IMT_TRY_CUDA(ctx, drained[k].create());
+        }
+        size_t c = 0;
+        for (size_t off = 0; off < pos.size(); off += chunk, ++c) {
+            const size_t cq = std::min(chunk, pos.size() - off);
+            const int bsel = (int)(c & 1);
+            if (c >= 2) IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, drained[bsel], 0));
+            IMT_TRY(launch_tree_trace(t, di.as<uint64_t>() + off, cq, bufs[bsel]));
+            IMT_TRY_CUDA(ctx, cudaEventRecord(produced[bsel], ctx->stream));
+            IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, produced[bsel], 0));
+            for (size_t j = 0; j < cq; ++j)
+                IMT_TRY_CUDA(ctx, cudaMemcpyAsync((char*)states + pos[off + j] * per_query, (const char*)bufs[bsel] + j * per_query, per_query,
+                                                  cudaMemcpyDeviceToHost, ctx->copy_stream));
+            IMT_TRY_CUDA(ctx, cudaEventRecord(drained[bsel], ctx->copy_stream));
+        }
+        IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        return finish(ctx);
+    });
 }

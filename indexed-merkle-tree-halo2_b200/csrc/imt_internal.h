@@ -2,6 +2,8 @@
 //   imt_capi.cu     context, batched hashing, tree build, paths, folds, traces, sharding cap, calibration
 //   imt_indexed.cu  sorted-key index, low-leaf lookups, non-inclusion witnesses, batched inserts
 //   imt_spec.cu     any-width Poseidon instances (T = 2..5, run-time r_f / r_p / input length): kernels + entry points
+//   imt_comm.cu     NCCL inside the library: communicators (one process per GPU, or one process driving N GPUs), the
+//                   root exchange of a sharded build, the collectives the sharded lookups / inserts use
 // All hashing kernels live in imt_capi.cu (one __constant__ copy of the Poseidon parameters); imt_indexed.cu prepares
 // operands and calls them through imt_host::launch_hash / launch_level.
 #pragma once
@@ -14,6 +16,8 @@
 #include "imt_b200.h"
 #include "poseidon.cuh"
 #include "poseidon_spec.cuh"
+
+struct imt_group;  // the ranks of a sharded tree this process drives + their transport (imt_comm.cu)
 
 struct imt_ctx {
     int device = 0;
@@ -32,6 +36,10 @@ struct imt_ctx {
     imt::SpecLayout spec{3, 8, 57};
     bool generic = false;
     imt::Fr* d_spec = nullptr;  // SpecLayout-ordered parameter array (derived and uploaded on first use)
+    // multi-GPU: the group this context belongs to (imt_comm_create / imt_multi_create) and its position among the group's
+    // local contexts; null for a single-GPU context
+    imt_group* group = nullptr;
+    unsigned group_slot = 0;
     uint64_t launches = 0;
     std::string last_error;
     // optional per-launch device timing of the hash kernels
@@ -165,13 +173,41 @@ imt_status launch_hash(imt_ctx* ctx, int arity, const void* d_in, void* d_out, s
 // dense FE array between formats (validates < p)
 imt_status launch_convert(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int from_fmt, int to_fmt);
 // batched get_proof from device indices into device buffers (any of d_helpers / d_helpers_fe may be null)
-imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe);
+// select = true (sharded calls): indices owned by other ranks yield zeros instead of IMT_ERR_INDEX_OOB
+imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_siblings, uint8_t* d_helpers, void* d_helpers_fe,
+                                bool select = false);
+
+// witness traces of the paths of a resident tree, queued on the compute stream (q x depth independent traced hashes)
+imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr);
 
 // one tree level, Montgomery in / out: d_dst[i] = H(d_src[2i], d_src[2i+1]); small levels take the cooperative kernel
 imt_status launch_level(imt_ctx* ctx, const imt::Fr* d_src, imt::Fr* d_dst, size_t nodes);
 
+// asynchronous halves of the build, for callers that drive several devices from one host thread:
+// enqueue_rebuild queues the leaf hashing (with the H2D pipeline when the leaves are on the host) and every level on the
+// context's streams and returns; wait_staging blocks until the caller's HOST buffer has been consumed; finish() ends the call.
+imt_status enqueue_rebuild(imt_tree* t, const void* preimages, bool device_src);
+imt_status wait_staging(imt_ctx* ctx);
+imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out);
+imt_status check_leaf_count(imt_ctx* ctx, size_t n);
+
 // ---- implemented in imt_indexed.cu
 void invalidate_index(imt_tree* t);
+imt_status ensure_index(imt_tree* t);
+
+// ---- implemented in imt_comm.cu: collectives over the ranks of a group. Element i of every vector belongs to the group's
+// i-th LOCAL context (one entry in process-per-GPU mode, all ranks in single-process mode); every operation is queued on
+// that context's compute stream (stream-ordered after the kernels that produced the send buffers).
+// all_gather: recv[i] = concatenation over ranks r of that rank's `bytes` bytes (rank-major), on every local rank
+imt_status group_all_gather(imt_group* g, const std::vector<const void*>& send, const std::vector<void*>& recv, size_t bytes);
+// in-place sum over ranks of `count` uint64 / uint8 values (exactly one rank holds a non-zero value per element: a select)
+imt_status group_all_reduce_sum(imt_group* g, const std::vector<void*>& buf, size_t count, bool bytes8);
+unsigned group_world(const imt_group* g);
+unsigned group_local_count(const imt_group* g);
+imt_ctx* group_ctx(imt_group* g, unsigned slot);
+unsigned group_rank(const imt_group* g, unsigned slot);
+// the group and the local shards behind a single-process multi-GPU tree
+imt_status mtree_parts(imt_mtree* mt, imt_group** g, std::vector<imt_tree*>* trees);
 
 // ---- implemented in imt_spec.cu (any-width instances)
 // permutations of one hash of `arity` inputs, and FE per hash of its witness trace

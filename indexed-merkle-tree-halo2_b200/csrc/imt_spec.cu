@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(kHashThreads) k_spec_fold(const uint4* __restr
         }
         index >>= 1;
     }
-    if (!ok) atomicOr(err, kErrNonCanonical);
     canonicalize(h);
     if (ok_out) {
         uint32_t r[8];
@@ -170,6 +169,7 @@ __global__ void __launch_bounds__(kHashThreads) k_spec_fold(const uint4* __restr
         for (int k = 0; k < 8; ++k) same &= r[k] == h[k];
         ok_out[i] = (uint8_t)same;
     }
+    if (!ok) atomicOr(err, kErrNonCanonical);
     if (roots_out) {
         egress(h, fmt);
         store_fe(roots_out + 2 * i, h);

@@ -99,10 +99,12 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __rest
 
 // Batched get_proof: one thread per (query, level). For a sharded tree the top `cap_depth` levels come from the
 // replicated cap (built over the gathered subtree roots) and `rank` locates this subtree inside it.
+// n_total_select != 0 ("select" mode of the sharded calls): an index owned by ANOTHER rank (still < n_total_select) is not an
+// error — this rank writes zeros for it, and the sum over ranks (one owner per query) assembles the replicated result.
 __global__ void k_gather_proofs(const uint4* __restrict__ levels, const uint4* __restrict__ cap, size_t n_local,
                                 unsigned depth_local, unsigned cap_depth, unsigned rank, const uint64_t* __restrict__ idx,
                                 size_t q, int fmt, uint4* __restrict__ siblings, uint8_t* __restrict__ helpers,
-                                uint4* __restrict__ helpers_fe, uint32_t* __restrict__ err) {
+                                uint4* __restrict__ helpers_fe, uint32_t* __restrict__ err, uint64_t n_total_select) {
     const unsigned depth = depth_local + cap_depth;
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= q * depth) return;
@@ -111,6 +113,13 @@ __global__ void k_gather_proofs(const uint4* __restrict__ levels, const uint4* _
     const uint64_t g = idx[qi];
     const uint64_t base = (uint64_t)rank * n_local;
     if (g < base || g >= base + n_local) {
+        if (n_total_select && g < n_total_select) {
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            store_fe(siblings + 2 * t, z);
+            if (helpers) helpers[t] = 0;
+            if (helpers_fe) store_fe(helpers_fe + 2 * t, z);
+            return;
+        }
         atomicOr(err, kErrIndexOob);
         return;
     }
@@ -176,18 +185,18 @@ __global__ void __launch_bounds__(kHashThreads) k_fold_paths(const uint4* __rest
         }
         index >>= 1;
     }
-    if (!ok) atomicOr(err, kErrNonCanonical);
     canonicalize(h);  // depth 0: the leaf itself, possibly semi-reduced after ingest
     if (ok_out) {
         uint32_t r[8];
         load_fe(r, roots + 2 * i);
-        ok &= ingest(r, fmt);
+        ok &= ingest(r, fmt);  // a root encoded as root + p must be rejected, not folded onto its canonical twin
         canonicalize(r);
         bool same = true;
 #pragma unroll
         for (int k = 0; k < 8; ++k) same &= r[k] == h[k];
         ok_out[i] = (uint8_t)same;
     }
+    if (!ok) atomicOr(err, kErrNonCanonical);
     if (roots_out) {
         egress(h, fmt);
         store_fe(roots_out + 2 * i, h);

@@ -94,7 +94,9 @@ class Engine:
         if getattr(self, "_h", None):
             for t in list(getattr(self, "_trees", ())):
                 t.close()
-            self._lib.imt_ctx_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._lib.imt_comm_destroy(self._h)
+                self._lib.imt_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -349,6 +351,38 @@ class Engine:
                                                  int(n_total), 1 if head_next_zero else 0, _ptr(low), _ptr(matched)))
         return low, matched.astype(bool)
 
+    # ---- multi-GPU inside the library (one process per GPU): NCCL communicator attached to this context
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId: rank 0 makes it and hands it to every rank (any transport)"""
+        lib = _ffi.load()
+        buf = (ctypes.c_uint8 * 128)()
+        st = lib.imt_comm_unique_id(buf)
+        if st != _ffi.OK:
+            raise ImtError(st, "imt_comm_unique_id failed: libnccl.so.2 could not be loaded")
+        return bytes(buf)
+
+    def comm_create(self, rank, world, unique_id):
+        uid = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.imt_comm_create(self._h, int(rank), int(world), uid))
+
+    def comm_destroy(self):
+        self._check(self._lib.imt_comm_destroy(self._h))
+
+    def comm_info(self):
+        """(rank, world, NCCL version code) of this context's group"""
+        r, w, v = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_int()
+        self._check(self._lib.imt_comm_info(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v)))
+        return r.value, w.value, v.value
+
+    def sharded_build_from_leaves(self, local_preimages):
+        """IndexedMerkleTree::new for this rank's slice of the leaves, root exchange (NCCL, inside the library) included"""
+        a = _fe_array(local_preimages, (3,))
+        return self._tree(self._lib.imt_sharded_build_from_leaves, _ptr(a), a.shape[0])
+
+    def sharded_build_from_leaves_dev(self, d_local_preimages, n_local):
+        return self._tree(self._lib.imt_sharded_build_from_leaves_dev, _dev_ptr(d_local_preimages), n_local)
+
     def calibrate_imad(self, ms=200.0):
         rate, mhz = ctypes.c_double(), ctypes.c_double()
         self._check(self._lib.imt_calibrate_imad(self._h, float(ms), ctypes.byref(rate), ctypes.byref(mhz)))
@@ -389,6 +423,17 @@ class Tree:
         self.engine._check(self._lib.imt_tree_root(self._h, _ptr(out)))
         return out
 
+    def subtree_root(self):
+        """this rank's OWN root (level `local depth` of its subtree) — root() reports the global root once a cap is attached"""
+        n_local = self.shard_info()[2]
+        return self.level(n_local.bit_length() - 1, 1)[0]
+
+    def shard_info(self):
+        """(rank, world, leaves held by this rank)"""
+        r, w, n = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_size_t()
+        self.engine._check(self._lib.imt_tree_shard_info(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(n)))
+        return int(r.value), int(w.value), int(n.value)
+
     def root_dev(self, d_out):
         self.engine._check(self._lib.imt_tree_root_dev(self._h, _dev_ptr(d_out)))
 
@@ -409,6 +454,8 @@ class Tree:
         """Checkpoint: the leaves as the reference's serde derive would write them — per leaf val, next_val,
         next_idx (utils.rs:12-17), 32 little-endian bytes each in the engine's format (canonical = halo2curves `to_repr`) —
         plus the root. The levels are NOT stored: load_tree() re-hashes (0.55 s at depth 24) and verifies the root."""
+        if self.shard_info()[1] > 1:
+            raise ValueError("checkpoint a sharded tree shard by shard is not supported: gather the preimages and save the whole tree")
         n = self.num_leaves
         e = self.engine
         np.savez(path, preimages=self.preimages(n), root=self.root(), format=np.int64(e.fmt),
@@ -541,6 +588,88 @@ class Tree:
         self.engine._check(self._lib.imt_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
         return o
 
+    # ---- sharded tree, exchanges inside the library (the engine has a communicator: Engine.comm_create)
+    def exchange_roots(self):
+        """NCCL all-gather of the subtree roots out of / into the trees' device buffers + the cap levels"""
+        self.engine._check(self._lib.imt_tree_exchange_roots(self._h))
+
+    def sharded_rebuild_from_leaves(self, local_preimages):
+        a = _fe_array(local_preimages, (3,))
+        self.engine._check(self._lib.imt_sharded_rebuild_from_leaves(self._h, _ptr(a)))
+
+    def sharded_rebuild_from_leaves_ptr(self, host_ptr):
+        self.engine._check(self._lib.imt_sharded_rebuild_from_leaves(self._h, ctypes.c_void_p(host_ptr)))
+
+    def sharded_rebuild_from_leaves_dev(self, d_local_preimages):
+        self.engine._check(self._lib.imt_sharded_rebuild_from_leaves_dev(self._h, _dev_ptr(d_local_preimages)))
+
+    def sharded_get_proofs(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q, d = idx.shape[0], self.depth
+        sib, hel = np.empty((q, d, 4), np.uint64), np.empty((q, d), np.uint8)
+        self.engine._check(self._lib.imt_sharded_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
+        return sib, hel
+
+    def sharded_leaves(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        out, lg = np.empty((q, 3, 4), np.uint64), np.empty(q, np.uint8)
+        self.engine._check(self._lib.imt_sharded_leaves(self._h, _ptr(idx), q, _ptr(out), _ptr(lg)))
+        return out, lg
+
+    def sharded_low_leaf_lookup(self, values):
+        v = _fe_array(values, ())
+        q = v.shape[0]
+        low, matched = np.empty(q, np.uint64), np.empty(q, np.uint8)
+        self.engine._check(self._lib.imt_sharded_low_leaf_lookup(self._h, _ptr(v), q, _ptr(low), _ptr(matched)))
+        return low, matched.astype(bool)
+
+    @property
+    def sharded_occupied(self):
+        m = ctypes.c_uint64()
+        self.engine._check(self._lib.imt_sharded_occupied(self._h, ctypes.byref(m)))
+        return int(m.value)
+
+    def sharded_non_inclusion_paths(self, values, out=None):
+        v = _fe_array(values, ())
+        q, d = v.shape[0], self.depth
+        o = out if out is not None else self.non_inclusion_buffers(q, d)
+        self.engine._check(self._lib.imt_sharded_non_inclusion_paths(self._h, _ptr(v), q, _ptr(o["low_idx"]), _ptr(o["matched"]),
+                                                                     _ptr(o["low_leaves"]), _ptr(o["siblings"]), _ptr(o["helpers"]),
+                                                                     _ptr(o["is_largest"])))
+        return o
+
+    def sharded_insert_batch(self, new_vals, first_idx=None, out=None):
+        v = _fe_array(new_vals, ())
+        if first_idx is None:
+            first_idx = self.sharded_occupied
+        b, d = v.shape[0], self.depth
+        o = out if out is not None else self.insert_buffers(b, d)
+        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        self.engine._check(self._lib.imt_sharded_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
+        return o
+
+    def sharded_trace_proofs(self, indices, out_states=None):
+        """owner-sharded witness traces: (positions into `indices` of the queries this rank owns, their traces)"""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        pos, n_mine = np.empty(q, np.uint64), ctypes.c_size_t()
+        if out_states is None:  # sized for the queries this rank owns
+            lo = np.uint64(self.shard_rank * self.shard_leaves)
+            owned = int(np.count_nonzero((idx >= lo) & (idx < lo + np.uint64(self.shard_leaves))))
+            out_states = np.empty((owned, self.depth, self.engine.states_per_hash(2), self.engine.t, 4), np.uint64)
+        self.engine._check(self._lib.imt_sharded_trace_proofs(self._h, _ptr(idx), q, _ptr(pos), ctypes.byref(n_mine), _ptr(out_states)))
+        return pos[: n_mine.value].astype(np.int64), out_states[: n_mine.value]
+
+    @property
+    def shard_rank(self):
+        return self.shard_info()[0]
+
+    @property
+    def shard_leaves(self):
+        """leaves held by this rank"""
+        return self.shard_info()[2]
+
     # ---- subtree sharding
     def set_shard(self, rank, world):
         self.engine._check(self._lib.imt_tree_set_shard(self._h, rank, world))
@@ -595,3 +724,164 @@ class Tree:
         if r.shape[0] != world:
             raise ValueError("need one subtree root per rank")
         self.engine._check(self._lib.imt_tree_attach_cap(self._h, rank, world, _ptr(r)))
+
+
+class Multi:
+    """imt_multi: ONE process drives N GPUs (a power of two). One context per device + their NCCL communicators
+    (ncclCommInitAll) inside the library; build_from_leaves() is `IndexedMerkleTree::new` over all of them in one call."""
+
+    def __init__(self, devices, fmt="canonical"):
+        self._lib = _ffi.load()
+        self.fmt = {"canonical": _ffi.FE_CANONICAL, "montgomery": _ffi.FE_MONTGOMERY}[fmt]
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        st = self._lib.imt_multi_create(devs, len(devices), self.fmt, ctypes.byref(h))
+        if st != _ffi.OK:
+            raise ImtError(st, f"imt_multi_create({list(devices)}) failed with status {st}")
+        self._h = h
+        self.devices = [int(d) for d in devices]
+        self._trees = weakref.WeakSet()
+
+    @property
+    def size(self):
+        return int(self._lib.imt_multi_size(self._h))
+
+    @property
+    def nccl_version(self):
+        """NCCL version code in use; 0 = the copy transport (a device listed twice)"""
+        return int(self._lib.imt_multi_uses_nccl(self._h))
+
+    def engine(self, i):
+        """Engine view of device i's context (owned by this Multi)"""
+        e = Engine.__new__(Engine)
+        e._lib, e.fmt, e._h = self._lib, self.fmt, ctypes.c_void_p(self._lib.imt_multi_ctx(self._h, i))
+        e.t, e.rate, e.r_f, e.r_p, e.generic, e.device = 3, 2, 8, 57, False, self.devices[i]
+        e.states_per_perm = 66
+        e._trees = weakref.WeakSet()
+        e._borrowed = True
+        return e
+
+    def _check(self, st):
+        if st != _ffi.OK:
+            msg = self._lib.imt_multi_last_error(self._h).decode() or self._lib.imt_status_string(st).decode()
+            raise ImtError(st, msg)
+
+    def build_from_leaves(self, preimages):
+        a = _fe_array(preimages, (3,))
+        h = ctypes.c_void_p()
+        self._check(self._lib.imt_multi_build_from_leaves(self._h, _ptr(a), a.shape[0], ctypes.byref(h)))
+        return MTree(self, h)
+
+    def build_from_leaves_ptr(self, host_ptr, n):
+        h = ctypes.c_void_p()
+        self._check(self._lib.imt_multi_build_from_leaves(self._h, ctypes.c_void_p(host_ptr), n, ctypes.byref(h)))
+        return MTree(self, h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for t in list(self._trees):
+                t.close()
+            self._lib.imt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MTree:
+    """imt_mtree: a tree sharded by subtree over the devices of a Multi; host arrays are whole-tree arrays"""
+
+    def __init__(self, multi, handle):
+        self.multi, self._lib, self._h = multi, multi._lib, handle
+        multi._trees.add(self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if getattr(self.multi, "_h", None):
+                self._lib.imt_mtree_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_leaves(self):
+        return int(self._lib.imt_mtree_num_leaves(self._h))
+
+    @property
+    def depth(self):
+        return int(self._lib.imt_mtree_depth(self._h))
+
+    def root(self):
+        out = np.empty(4, np.uint64)
+        self.multi._check(self._lib.imt_mtree_root(self._h, _ptr(out)))
+        return out
+
+    def rebuild_from_leaves(self, preimages):
+        a = _fe_array(preimages, (3,))
+        self.multi._check(self._lib.imt_mtree_rebuild_from_leaves(self._h, _ptr(a)))
+
+    def rebuild_from_leaves_ptr(self, host_ptr):
+        self.multi._check(self._lib.imt_mtree_rebuild_from_leaves(self._h, ctypes.c_void_p(host_ptr)))
+
+    def get_proofs(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q, d = idx.shape[0], self.depth
+        sib, hel = np.empty((q, d, 4), np.uint64), np.empty((q, d), np.uint8)
+        self.multi._check(self._lib.imt_mtree_get_proofs(self._h, _ptr(idx), q, _ptr(sib), _ptr(hel)))
+        return sib, hel
+
+    def leaves(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        out, lg = np.empty((q, 3, 4), np.uint64), np.empty(q, np.uint8)
+        self.multi._check(self._lib.imt_mtree_leaves(self._h, _ptr(idx), q, _ptr(out), _ptr(lg)))
+        return out, lg
+
+    def low_leaf_lookup(self, values):
+        v = _fe_array(values, ())
+        q = v.shape[0]
+        low, matched = np.empty(q, np.uint64), np.empty(q, np.uint8)
+        self.multi._check(self._lib.imt_mtree_low_leaf_lookup(self._h, _ptr(v), q, _ptr(low), _ptr(matched)))
+        return low, matched.astype(bool)
+
+    @property
+    def occupied(self):
+        m = ctypes.c_uint64()
+        self.multi._check(self._lib.imt_mtree_occupied(self._h, ctypes.byref(m)))
+        return int(m.value)
+
+    def non_inclusion_paths(self, values, out=None):
+        v = _fe_array(values, ())
+        q, d = v.shape[0], self.depth
+        o = out if out is not None else Tree.non_inclusion_buffers(q, d)
+        self.multi._check(self._lib.imt_mtree_non_inclusion_paths(self._h, _ptr(v), q, _ptr(o["low_idx"]), _ptr(o["matched"]),
+                                                                  _ptr(o["low_leaves"]), _ptr(o["siblings"]), _ptr(o["helpers"]),
+                                                                  _ptr(o["is_largest"])))
+        return o
+
+    def insert_batch(self, new_vals, first_idx=None, out=None):
+        v = _fe_array(new_vals, ())
+        if first_idx is None:
+            first_idx = self.occupied
+        b, d = v.shape[0], self.depth
+        o = out if out is not None else Tree.insert_buffers(b, d)
+        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        self.multi._check(self._lib.imt_mtree_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
+        return o
+
+    def trace_proofs(self, indices, out_states=None):
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        q = idx.shape[0]
+        shape = (q, self.depth, STATES_PER_HASH, 3, 4)
+        states = out_states if out_states is not None else np.empty(shape, np.uint64)
+        if states.shape != shape or states.dtype != np.uint64 or not states.flags.c_contiguous:
+            raise ValueError(f"out_states must be a C-contiguous uint64 array of shape {shape}")
+        self.multi._check(self._lib.imt_mtree_trace_proofs(self._h, _ptr(idx), q, _ptr(states)))
+        return states

@@ -6,9 +6,11 @@ The only exchange of the build is ONE all-gather of the N subtree roots (N x 32 
 redundantly. Queries shard by leaf owner (paths, preimages) or arbitrarily (folds / witness traces); low-leaf lookups
 take one more all-gather of per-rank predecessor candidates.
 
-With the `nccl` backend the root exchange stays on the device (subtree root -> send buffer -> ncclAllGather over
-NVLink -> cap build, no host round trip); with `gloo` the same steps are staged through host memory, which is what the
-CPU tests drive. The engine argument only needs the Engine/Tree methods used here, so the tests can substitute an
+With the `nccl` backend every exchange happens INSIDE the C library (csrc/imt_comm.cu: the engine gets its own NCCL
+communicator via imt_comm_create — torch.distributed only carries the 128-byte NCCL id to the ranks — and the calls
+below are one-line forwards to imt_sharded_*: the same entry points a Rust host binds). With `gloo` the same steps run
+through the piecewise C calls with the exchanges staged through host memory by torch.distributed, which is what the CPU
+tests drive. The engine argument only needs the Engine/Tree methods used here, so the tests can substitute an
 oracle-backed double for the host-side logic.
 """
 import numpy as np
@@ -17,6 +19,21 @@ import numpy as np
 def _dist():
     import torch.distributed as dist
     return dist
+
+
+def attach_communicator(engine, group=None):
+    """Gives `engine` its own NCCL communicator over the ranks of the torch.distributed group (imt_comm_create). torch only
+    moves the 128-byte NCCL id from rank 0 to the others; every later collective is issued by the C library."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if engine.comm_info()[1] == world and world > 1:
+        return
+    uid = engine.comm_unique_id() if rank == 0 else bytes(128)
+    dev = torch.device("cuda", engine.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine.comm_create(rank, world, bytes(t.cpu().numpy().tobytes()))
 
 
 class ShardedTree:
@@ -33,34 +50,34 @@ class ShardedTree:
         self._torch = torch
         self._cdev = torch.device("cuda", engine.device) if self.on_device else torch.device("cpu")
         if self.on_device:
-            # NCCL orders its work against torch's current stream: run the engine's kernels on that stream too, so the
-            # send buffer is written before the all-gather reads it and the cap build starts after it lands
-            engine.set_stream(torch.cuda.current_stream(self._cdev).cuda_stream)
+            attach_communicator(engine, group)
         if d_preimages is not None:
-            self.tree = engine.build_from_leaves_dev(d_preimages, n_local)
             self.n_local = int(n_local)
+            self.tree = (engine.sharded_build_from_leaves_dev(d_preimages, n_local) if self.on_device
+                         else engine.build_from_leaves_dev(d_preimages, n_local))
         else:
-            self.tree = engine.build_from_leaves(local_preimages)
             self.n_local = int(np.asarray(local_preimages).reshape(-1, 3, 4).shape[0])
-        self.tree.set_shard(self.rank, self.world)
-        if self.on_device:
-            self._send = torch.zeros(4, dtype=torch.int64, device=self._cdev)
-            self._recv = torch.zeros((self.world, 4), dtype=torch.int64, device=self._cdev)
-        self.exchange_roots()
+            self.tree = engine.sharded_build_from_leaves(local_preimages) if self.on_device else engine.build_from_leaves(local_preimages)
+        if not self.on_device:
+            self.tree.set_shard(self.rank, self.world)
+            self.exchange_roots()
 
     # ---- build
     def exchange_roots(self):
         """all-gather of the N subtree roots + the replicated cap levels; call again after every rebuild"""
-        dist = _dist()
         if self.on_device:
-            self.tree.root_dev(self._send)
-            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
-            self.tree.attach_cap_dev(self.rank, self.world, self._recv)
+            self.tree.exchange_roots()          # imt_tree_exchange_roots: ncclAllGather inside the library
         else:
-            roots = self._all_gather(self.tree.root())
+            roots = self._all_gather(self.tree.subtree_root())
             self.tree.attach_cap(self.rank, self.world, roots)
 
     def rebuild(self, local_preimages=None, d_preimages=None):
+        if self.on_device:
+            if d_preimages is not None:
+                self.tree.sharded_rebuild_from_leaves_dev(d_preimages)
+            else:
+                self.tree.sharded_rebuild_from_leaves(local_preimages)
+            return
         if d_preimages is not None:
             self.tree.rebuild_from_leaves_dev(d_preimages)
         else:
@@ -119,16 +136,34 @@ class ShardedTree:
     def get_proofs(self, indices):
         """get_proof (utils.rs:63-85) for GLOBAL leaf indices: the bottom d-k siblings come from the owner's subtree,
         the top k from the replicated cap. Returns (siblings [q, d, 4], helpers [q, d]) on every rank."""
+        if self.on_device:
+            return self._native(lambda: self.tree.sharded_get_proofs(indices))
         d = self.depth
         return tuple(self._served_by_owner(indices, lambda ix: self.tree.get_proofs(ix), [((d, 4), np.uint64), ((d,), np.uint8)]))
 
     def leaves(self, indices):
+        if self.on_device:
+            return self._native(lambda: self.tree.sharded_leaves(indices))
         return tuple(self._served_by_owner(indices, lambda ix: self.tree.leaves(ix), [((3, 4), np.uint64), ((), np.uint8)]))
+
+    @staticmethod
+    def _native(call):
+        """the C library reports an out-of-range index as ImtError(INDEX_OOB); the gloo path raises IndexError"""
+        from .engine import ImtError
+        from . import _ffi
+        try:
+            return call()
+        except ImtError as e:
+            if e.status == _ffi.ERR_INDEX_OOB:
+                raise IndexError("index out of bounds") from e
+            raise
 
     def low_leaf_lookup(self, values):
         """update_idx_leaf's scan (IMT:632-660) over the sharded tree: per-rank predecessor candidates from each rank's
         sorted index, one all-gather, then the same decision as the single-GPU lookup. Replicated result."""
         v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        if self.on_device:
+            return self.tree.sharded_low_leaf_lookup(v)      # candidates + ncclAllGather + merge inside the library
         keys, slots, flags = self.tree.low_leaf_candidates(v)
         occ = self._all_gather(np.array([self.tree.occupied, 1 if (self.rank == 0 and self.tree.head_next_zero) else 0], np.uint64))
         gk, gs, gf = self._all_gather(keys), self._all_gather(slots), self._all_gather(flags)
@@ -136,6 +171,10 @@ class ShardedTree:
 
     def non_inclusion_paths(self, values):
         """witnesses of verify_non_inclusion (IMT:127-137) for every value, replicated on every rank"""
+        if self.on_device:
+            o = self.tree.sharded_non_inclusion_paths(values)
+            o["matched"] = o["matched"].astype(bool)
+            return o
         low, matched = self.low_leaf_lookup(values)
         leaves, largest = self.leaves(low)
         sib, hel = self.get_proofs(low)
@@ -147,6 +186,15 @@ class ShardedTree:
         rank's index -> all-gather -> replicated plan -> every rank applies its own writes to its subtree -> all-gather
         of the subtree-root versions and local paths -> every rank applies all writes to the replicated cap."""
         v = np.ascontiguousarray(new_vals, dtype=np.uint64).reshape(-1, 4)
+        if self.on_device:
+            from .engine import ImtError
+            from . import _ffi
+            try:
+                return self.tree.sharded_insert_batch(v)     # the same rounds, exchanged by NCCL inside the library
+            except ImtError as e:
+                if e.status == _ffi.ERR_TREE_FULL:
+                    raise ValueError("not enough empty slots") from e
+                raise
         b_total, d = v.shape[0], self.depth
         d_local = self.n_local.bit_length() - 1
         d_cap = d - d_local

@@ -663,6 +663,23 @@ int imto_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+/* Dense FE array between the canonical form (to_repr bytes) and halo2curves' in-memory Montgomery form [u64; 4]:
+ * to_montgomery != 0: out = in * 2^256 mod p, else out = in * 2^-256 mod p. bench.py's headline run feeds the synthetic
+ * stream to a Montgomery-format context, i.e. interprets the same bit patterns as Montgomery values: this is how the
+ * golden root of that run is produced on the CPU (tests/golden/make_golden.py --bench24). */
+typedef struct { const uint64_t *in; uint64_t *out; int to_m; } conv_arg;
+static void conv_range(size_t lo, size_t hi, void *p) {
+    conv_arg *a = (conv_arg *)p;
+    for (size_t i = lo; i < hi; ++i) {
+        if (a->to_m) { fr m = to_mont(a->in + 4 * i); memcpy(a->out + 4 * i, m.l, 32); }
+        else { fr m = {{a->in[4 * i], a->in[4 * i + 1], a->in[4 * i + 2], a->in[4 * i + 3]}}; from_mont(m, a->out + 4 * i); }
+    }
+}
+void imto_convert(const uint64_t *in, size_t n, uint64_t *out, int to_montgomery, int threads) {
+    imto_init();
+    conv_arg a = {in, out, to_montgomery};
+    parallel_for(n, threads, conv_range, &a);
+}
 /* The reference's CPU path as one call: hash n preimages (IMT:662-671) then build (UT:41-51). Returns the root. */
 int imto_build_from_preimages(const uint64_t *pre, size_t n, uint64_t *root, int threads) {
     uint64_t *hashes = (uint64_t *)malloc(n * 32);

@@ -59,6 +59,7 @@ def lib():
         L.imto_max_threads.restype = ctypes.c_int
         L.imto_build_from_preimages.argtypes = [_u64p, ctypes.c_size_t, _u64p, ctypes.c_int]
         L.imto_build_from_preimages.restype = ctypes.c_int
+        L.imto_convert.argtypes = [_u64p, ctypes.c_size_t, _u64p, ctypes.c_int, ctypes.c_int]
         L.imto_init()
         _lib = L
     return _lib
@@ -224,6 +225,14 @@ class InsertState:
 def synth_fe(seed, first, n):
     out = np.zeros((n, 4), np.uint64)
     lib().imto_synth_fe(seed, first, n, _p(out))
+    return out
+
+
+def convert(a, to_montgomery, threads=1):
+    """dense FE array canonical <-> halo2curves' in-memory Montgomery form (x * 2^256 mod p)"""
+    a = _c(a)
+    out = np.empty_like(a)
+    lib().imto_convert(_p(a), a.size // 4, _p(out), 1 if to_montgomery else 0, threads)
     return out
 
 

@@ -30,6 +30,9 @@ class OracleTree:
     def root(self):
         return (self.cap if self.cap is not None else self.tree)[-1].copy()
 
+    def subtree_root(self):
+        return self.tree[-1].copy()
+
     def attach_cap(self, rank, world, roots):
         self.rank, self.world = rank, world
         self.cap = O.tree_build(np.ascontiguousarray(roots, dtype=np.uint64).reshape(world, 4), 1) if world > 1 else None

@@ -30,7 +30,29 @@ def spec_vectors():
     return out
 
 
+def bench_root(depth, th):
+    """Root of bench.py's headline input: the synthetic stream fed to a MONTGOMERY-format context, i.e. the same bit patterns
+    read as x * 2^256 mod p. Returned as bench.py prints it: the root's Montgomery-form bytes as one big-endian hex number."""
+    pre = O.convert(synth.random_preimages(1 << depth), False, th)        # the canonical values those bit patterns stand for
+    root = O.convert(O.build_from_preimages(pre, th).reshape(1, 4), True)  # back to the in-memory form
+    return f"{O.to_int(root):064x}"
+
+
 def main():
+    if "--bench-roots" in sys.argv:  # refresh only bench.py's expected roots (depth 24: ~6 min on 8 cores), keep the rest
+        path = os.path.join(HERE, "golden.json")
+        g = json.load(open(path))
+        th = O.max_threads()
+        br = g.get("bench_roots", {})
+        for depth in (10, 16, 20) + ((24,) if "--depth24" in sys.argv else ()):
+            t0 = time.time()
+            br[str(depth)] = bench_root(depth, th)
+            print(f"bench root depth {depth}: {br[str(depth)]} ({time.time() - t0:.1f}s)", flush=True)
+        g["bench_roots"] = br
+        with open(path, "w") as f:
+            json.dump(g, f, indent=1)
+        print("updated golden.json: bench_roots")
+        return
     if "--spec-only" in sys.argv:  # refresh only the any-width vectors, keep everything else byte for byte
         path = os.path.join(HERE, "golden.json")
         g = json.load(open(path))
