@@ -8,12 +8,15 @@ PKG     := indexed-merkle-tree-halo2_b200
 CSRC    := $(PKG)/csrc
 OBJDIR  := $(PKG)/build
 LIB     := $(PKG)/libimt_b200.so
-UNITS   := imt_capi.cu imt_indexed.cu imt_spec.cu imt_comm.cu poseidon_params.cpp
+UNITS   := imt_capi.cu imt_indexed.cu imt_spec.cu imt_latency.cu imt_comm.cu imt_io.cu poseidon_params.cpp
 OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(basename $(UNITS))))
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 550 -Iinclude -I$(CSRC)
 HEADERS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/imt_b200.h
 
 all: $(LIB)
+
+# the latency kernels: the same field source with free carry chains (csrc/fr.cuh IMT_FREE_MASK; swept on a B200)
+$(OBJDIR)/imt_latency.o: NVFLAGS += -DIMT_FREE_MASK=29
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HEADERS)
 	@mkdir -p $(OBJDIR)

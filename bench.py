@@ -28,6 +28,10 @@ TRACE_DRAM_BYTES_PER_HASH = 12568.0  # dram__bytes_read+write of k_trace_tree_pa
 METRIC = "poseidon_hashes_per_s_depth24_tree_build"
 
 
+def workload_name(depth):
+    return f"depth-{depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,10 +164,13 @@ def run_reference(a):
     import imt_b200
     from imt_b200 import synth
     th = O.max_threads()
-    # a step = a bounded sample of the depth-24 workload: one depth-S build, S sized for ~3 s per step
+    # a step = a bounded sample of the depth-D workload: one depth-S build, S sized for ~3 s per step. Poseidon's cost is data-
+    # and size-independent (every hash is the same 2 permutations), so hashes/s of the sample IS hashes/s of the full build;
+    # ms_per_step is reported for the DECLARED workload (hashes_per_step / value) and flagged as extrapolated, the measured
+    # sample time sits beside it.
     rate, _, _, _, _ = cpu_build_rate(1.0, th)
-    S = max(10, min(24, int(rate * 3.0 / 2).bit_length() - 1))
-    pre = synth.random_preimages(1 << S)
+    S = max(10, min(a.depth, int(rate * 3.0 / 2).bit_length() - 1))
+    pre = O.convert(synth.random_preimages(1 << S), False, th)   # the GPU arm's input: the same stream read as Montgomery values
     hashes = 2 * (1 << S) - 1
     for _ in range(a.warmup):
         O.build_from_preimages(pre, th)
@@ -172,14 +179,16 @@ def run_reference(a):
         O.build_from_preimages(pre, th)
     dt = time.perf_counter() - t0
     v = hashes * a.steps / dt
+    full_hashes = 2 * (1 << a.depth) - 1
     sample = f"each step = depth-{S} build ({hashes} hashes) of the depth-{a.depth} workload, {th} host threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "hashes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery(cpu: u64x4)",
-        "data": "synthetic", "config": {"workload": f"depth-{a.depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57",
-                                        "depth": a.depth, "leaves": 1 << a.depth, "hashes_per_step": 2 * (1 << a.depth) - 1,
-                                        "sharding": "host threads", "seed": synth.DEFAULT_SEED, "fe_format": "canonical",
-                                        "sample_depth": S, "sample_hashes_per_step": hashes},
+        "ms_per_step": 1e3 * full_hashes / v, "ms_per_step_extrapolated": S != a.depth, "sample_ms_per_step": 1e3 * dt / a.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery(cpu: u64x4)",
+        "data": "synthetic", "config": {"workload": workload_name(a.depth), "depth": a.depth, "leaves": 1 << a.depth, "hashes_per_step": full_hashes,
+                                        "sharding": f"host threads x{th}", "seed": synth.DEFAULT_SEED, "fe_format": "montgomery",
+                                        "sample_depth": S, "sample_hashes_per_step": hashes,
+                                        "sample_note": f"timed on depth-{S} sample builds (hash cost is size-independent); ms_per_step is value-consistent for depth {a.depth}"},
         "cpu_baseline": {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample,
                          "single_thread": dict(zip(("value", "sample"), cpu_single_thread_rate()))},
         "e2e": {"value": v, "unit": "hashes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -430,7 +439,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # plumbing only: barrier, max-over-ranks of the timing, the NCCL id
 
     depth = a.depth
     n_total = 1 << depth
@@ -438,30 +447,36 @@ def main():
     eng = imt_b200.Engine(local_rank, "montgomery")   # Montgomery = halo2curves' in-memory form: zero-copy from Rust
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    nccl_version = 0
+    if world > 1:
+        # the data-path collective lives INSIDE the C library (csrc/imt_comm.cu): the engine gets its own NCCL communicator
+        # (imt_comm_create); torch.distributed only carries the 128-byte id from rank 0 to the other ranks
+        from imt_b200.sharding import attach_communicator
+        attach_communicator(eng)
+        nccl_version = eng.comm_info()[2]
 
     # ---- synthetic leaves, generated on the device (setup, untimed): rank r owns leaves [r n, (r+1) n)
     d_pre = synth.field_elements_torch(3 * n, synth.DEFAULT_SEED, first=3 * n * rank, device=dev).view(n, 3, 4)
     h_pre = torch.empty((n, 3, 4), dtype=torch.int64, pin_memory=True)
     h_pre.copy_(d_pre)
     torch.cuda.synchronize(dev)
-    tree = eng.build_from_leaves_dev(d_pre, n)
+    # N > 1: imt_sharded_build_from_leaves_dev = local subtree build -> ncclAllGather of the N roots (sent straight out of the
+    # tree's level buffer, received straight into the cap) -> log2(N) cap levels, all queued on one stream by one C call
+    tree = eng.sharded_build_from_leaves_dev(d_pre, n) if world > 1 else eng.build_from_leaves_dev(d_pre, n)
     send = torch.zeros(4, dtype=torch.int64, device=dev)
-    recv = torch.zeros((world, 4), dtype=torch.int64, device=dev)
     h_root = torch.zeros(4, dtype=torch.int64, pin_memory=True)
 
-    def exchange():
-        if world > 1:
-            tree.root_dev(send)                                         # this rank's subtree root -> send buffer
-            dist.all_gather_into_tensor(recv, send)                      # N x 32 B over NVLink
-            tree.attach_cap_dev(rank, world, recv)                       # log2(N) cap levels, replicated
-
     def step_resident():
-        tree.rebuild_from_leaves_dev(d_pre)
-        exchange()
+        if world > 1:
+            tree.sharded_rebuild_from_leaves_dev(d_pre)                  # imt_sharded_rebuild_from_leaves_dev
+        else:
+            tree.rebuild_from_leaves_dev(d_pre)
 
     def step_e2e():
-        tree.rebuild_from_leaves_ptr(h_pre.data_ptr())                   # pinned host -> device inside the call
-        exchange()
+        if world > 1:
+            tree.sharded_rebuild_from_leaves_ptr(h_pre.data_ptr())       # pinned host -> device inside the call, exchange included
+        else:
+            tree.rebuild_from_leaves_ptr(h_pre.data_ptr())
         tree.root_dev(send)
         h_root.copy_(send, non_blocking=True)                            # the step's result back on the host
         stream.synchronize()
@@ -525,6 +540,15 @@ def main():
             step_e2e_alloc()
         ms_e2e_alloc = (time.perf_counter() - t0) / 2 * 1e3
     root_hex = "".join(f"{int(x) & 0xFFFFFFFFFFFFFFFF:016x}" for x in reversed(h_root.tolist()))
+    # the root of THIS input is pinned: tests/golden/golden.json "bench_roots" holds the CPU oracle's root of the same
+    # Montgomery-interpreted synthetic stream (tests/golden/make_golden.py --bench-roots); every rank count must reproduce it
+    try:
+        gold_root = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json"))).get("bench_roots", {}).get(str(depth))
+    except Exception:
+        gold_root = None
+    if gold_root is not None and root_hex != gold_root:
+        raise SystemExit(f"bench.py: root {root_hex} differs from the oracle's golden root {gold_root} (depth {depth}, {world} GPUs)")
+    root_check = "equals the CPU oracle's golden root (tests/golden/golden.json bench_roots)" if gold_root else "no golden root for this depth"
 
     # ---- roofline of the dominant kernel (leaf hashing: half of all hashes in one launch)
     imad_rate, imad_mhz = eng.calibrate_imad(150.0)
@@ -561,16 +585,18 @@ def main():
         "metric": METRIC, "value": value, "unit": "hashes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8-montgomery", "data": "synthetic",
-        "config": {"workload": f"depth-{depth} indexed Merkle tree build (leaf H3 + all levels), BN254 Poseidon T=3 R_F=8 R_P=57",
+        "config": {"workload": workload_name(depth),
                    "depth": depth, "leaves": n_total, "leaves_per_gpu": n, "hashes_per_step": hashes_per_step,
                    "sharding": f"subtree x{world} + all-gather of {world} roots" if world > 1 else "single GPU",
                    "l2_policy": f"inputs larger than L2 ({n * 96 / 2**20:.0f} MiB of leaves per GPU per step)", "seed": synth.DEFAULT_SEED,
                    "fe_format": "montgomery"},
         "e2e": {"value": e2e, "unit": "hashes/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n_total * 96,
-                "d2h_bytes_per_step": 32 * world, "call": "imt_tree_rebuild_from_leaves (host leaves -> existing tree) + root read back",
+                "d2h_bytes_per_step": 32 * world, "call": ("imt_sharded_rebuild_from_leaves" if world > 1 else "imt_tree_rebuild_from_leaves") + " (host leaves -> existing tree) + root read back",
                 "ms_per_step_with_alloc": ms_e2e_alloc,
                 "with_alloc_note": "wall clock of imt_tree_build_from_leaves + root + imt_tree_destroy per step (2.5 GiB of tree buffers recycled through the stream-ordered pool), N=1 only"},
-        "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex,
+        "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex, "root_check": root_check,
+        "collective": (f"ncclAllGather of {world} x 32 B issued inside libimt_b200.so (imt_sharded_rebuild_from_leaves*, NCCL {nccl_version})"
+                       if world > 1 else None),
     }
     if rank == 0 and not a.no_cpu_baseline:
         v, th, sample, _, _ = cpu_build_rate(a.cpu_seconds)

@@ -237,6 +237,25 @@ imt_status imt_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint
  * is_new_leaf_largest = (low.next_val == 0), :226-228) — a witness that fails them makes the chip panic before MockProver. */
 imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leaves, const void* new_vals, size_t b, void* limbs, uint8_t* flags);
 
+/* The Poseidon witness trace of everything the chip's insert_leaf hashes (src/indexed_merkle_tree.rs:231-314), for a whole
+ * batch in ONE call: per insert 3 + 4 x depth hashes in the chip's call order —
+ *     [0] H3(low leaf before)                      :193-194      [1 .. d]          its fold up the low path -> old root    :196-204
+ *     [d+1] H3(low.val, new.val, new_idx)          :265-275      [d+2 .. 2d+1]     its fold up the SAME path -> interim    :277-284
+ *     [2d+2 .. 3d+1] fold of the empty leaf H3(0,0,0) (a constant in the chip, :247-251) up the new leaf's path -> interim :286-294
+ *     [3d+2] H3(new leaf)                          :299-303      [3d+3 .. 4d+2]    its fold up the same path -> new root   :305-313
+ * each as imt_trace_fe_per_hash states (132 x 3 FE). Input: the witnesses imt_insert_batch returned for the batch (low_leaves,
+ * low_idx, low_siblings, new_leaves, new_siblings must be set; the rest of `w` is not read) and the slot of its first insert.
+ * Outputs (any may be NULL): states[b][3 + 4 depth][132][3] FE; roots[b][4] FE = the roots the four folds end in (old,
+ * interim, interim again via the empty leaf, new); new_low_leaves[b][3] FE = the rewired low leaf's preimage; limbs[b][6] FE +
+ * limb_flags[b][3] = imt_non_inclusion_limbs of (low leaf, new value). On the device the four folds of all inserts advance
+ * level by level, one traced launch of 4b hashes per level — no serial traced fold. The _dev variant takes DEVICE pointers in
+ * `w` and for every output. Default instance only (any-width contexts: compose imt_poseidon_trace / imt_trace_merkle_proofs). */
+size_t imt_insert_trace_hashes(unsigned depth); /* 3 + 4 depth */
+imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_witness* w, size_t b, unsigned depth, uint64_t first_idx, void* states,
+                                    void* roots, void* new_low_leaves, void* limbs, uint8_t* limb_flags);
+imt_status imt_insert_witness_trace_dev(imt_ctx* ctx, const imt_insert_witness* d_w, size_t b, unsigned depth, uint64_t first_idx,
+                                        void* d_states, void* d_roots, void* d_new_low_leaves, void* d_limbs, uint8_t* d_limb_flags);
+
 /* ---------------------------------------------------------------- subtree sharding (one process per GPU) ----- */
 /* A depth-d tree over N = 2^k ranks: rank g owns leaves [g n/N, (g+1) n/N) and builds that subtree with the calls
  * above (n = leaves per rank). The N subtree roots are exchanged by the caller (ncclAllGather / torch.distributed
@@ -370,6 +389,27 @@ imt_status imt_mtree_insert_batch(imt_mtree* tree, const void* new_vals, size_t 
 /* imt_tree_trace_proofs for GLOBAL indices: every device traces the queries it owns and drains them over its own PCIe link
  * into states[q][depth][fe per hash] (caller order). */
 imt_status imt_mtree_trace_proofs(imt_mtree* tree, const uint64_t* indices, size_t q, void* states);
+
+/* ---------------------------------------------------------------- checkpoints -------------------------------- */
+/* A built tree on disk, readable by a serde consumer of the reference's native leaf struct (src/utils.rs:12-17): a 64-byte
+ * header, then n x 96 bytes = the leaves as `val, next_val, next_idx`, each the canonical 32-byte little-endian `to_repr()`
+ * bytes (whatever the context's format), then the 32-byte canonical root. Layout:
+ *     0 "IMTB200\0" | 8 u32 version = 1 | 12 u32 t | 16 u32 rate | 20 u32 r_f | 24 u32 r_p | 28 u32 depth | 32 u64 n | 40 zero[24]
+ *     64 leaves[n][3][32] | 64 + 96 n root[32]
+ * The levels are not stored: imt_tree_load re-hashes the leaves on the GPU and fails with IMT_ERR_INVALID_ARG ("checkpoint
+ * is corrupt") when the rebuilt root differs from the stored one; leaves >= p give IMT_ERR_NON_CANONICAL. */
+typedef struct imt_checkpoint_info {
+    uint64_t num_leaves;
+    uint32_t version, t, rate, r_f, r_p, depth;
+    uint8_t root[32];
+} imt_checkpoint_info;
+imt_status imt_tree_save(imt_tree* tree, const char* path);
+imt_status imt_tree_load(imt_ctx* ctx, const char* path, imt_tree** out);
+/* the same file from / into a tree sharded over the devices of an imt_multi (shards are written in rank order = leaf order) */
+imt_status imt_mtree_save(imt_mtree* tree, const char* path);
+imt_status imt_multi_load(imt_multi* m, const char* path, imt_mtree** out);
+/* header + root of a checkpoint; touches no device */
+imt_status imt_checkpoint_read_info(const char* path, imt_checkpoint_info* info);
 
 /* ---------------------------------------------------------------- calibration -------------------------------- */
 /* Integer-multiply roofline calibration: saturates every SM with IMAD.WIDE.U32.X carry chains (the instruction the

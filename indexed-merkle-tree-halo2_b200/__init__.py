@@ -9,6 +9,7 @@ kernels (csrc/, include/imt_b200.h) plus this thin host layer:
 The directory name contains '-', so import it through the repo-root shim:  `import imt_b200`.
 """
 from . import build as _build  # noqa: F401
+from . import _ffi  # noqa: F401
 from .engine import Engine, Tree, Multi, MTree, ImtError, P, STATES_PER_HASH, fe_from_int, fe_to_int, fes_from_ints, fes_to_ints  # noqa: F401
 from .reference_api import Poseidon, IndexedMerkleTree, IndexedMerkleTreeLeaf, hash_nullifier_pre_images, default_engine  # noqa: F401
 from . import synth  # noqa: F401

@@ -136,7 +136,21 @@ SIGNATURES = {
     "imt_mtree_non_inclusion_paths": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "imt_mtree_insert_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_u64, ctypes.POINTER(InsertWitness)]),
     "imt_mtree_trace_proofs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "imt_insert_trace_hashes": (c_size_t, [c_uint]),
+    "imt_insert_witness_trace": (c_int, [c_void_p, ctypes.POINTER(InsertWitness), c_size_t, c_uint, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "imt_insert_witness_trace_dev": (c_int, [c_void_p, ctypes.POINTER(InsertWitness), c_size_t, c_uint, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    # ---- checkpoints
+    "imt_tree_save": (c_int, [c_void_p, ctypes.c_char_p]),
+    "imt_tree_load": (c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "imt_mtree_save": (c_int, [c_void_p, ctypes.c_char_p]),
+    "imt_multi_load": (c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "imt_checkpoint_read_info": (c_int, [ctypes.c_char_p, c_void_p]),
 }
+
+
+class CheckpointInfo(ctypes.Structure):
+    _fields_ = [("num_leaves", c_u64), ("version", c_uint), ("t", c_uint), ("rate", c_uint), ("r_f", c_uint), ("r_p", c_uint),
+                ("depth", c_uint), ("root", ctypes.c_uint8 * 32)]
 
 _lib = None
 

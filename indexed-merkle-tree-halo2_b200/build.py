@@ -7,8 +7,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
-SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "imt_comm.cu", "poseidon_params.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "poseidon_quad.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
+SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "imt_latency.cu", "imt_comm.cu", "imt_io.cu", "poseidon_params.cpp"]
+# per-unit flags: the latency kernels are the same field source compiled with free carry chains (csrc/fr.cuh IMT_FREE_MASK;
+# all 32 masks were swept on a B200, tools/lab/latency_lab.cu: 29 = product rows (even chain), reduction rows, squarings)
+UNIT_FLAGS = {"imt_latency.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_LATENCY_FREE_MASK", "29")]}
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
 OBJ_DIR = os.path.join(HERE, "build")
 
 
@@ -43,7 +46,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-        subprocess.run([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj], check=True, env=env)
+        subprocess.run([_nvcc(), *flags, *UNIT_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj], check=True, env=env)
         return obj
 
     with ThreadPoolExecutor(len(SOURCES)) as pool:

@@ -13,7 +13,6 @@
 #include "imt_b200.h"
 #include "imt_internal.h"
 #include "kernels.cuh"
-#include "poseidon_coop.cuh"
 #include "poseidon_params.h"
 
 using namespace imt;
@@ -70,6 +69,10 @@ namespace {
 // lanes for latency. IMT_COOP_MAX_NODES overrides the threshold (tuning / A-B measurements only).
 constexpr size_t kCoopMaxNodesDefault = 8192;
 size_t coop_max_nodes();
+// Above that and up to this many hashes a batch is <= ~2 warps per scheduler of the thread-per-hash kernel: latency still
+// dominates, so the free-carry-chain build of the same kernel is used (IMT_LAT_MAX_NODES overrides; 0 disables).
+constexpr size_t kLatMaxNodesDefault = 32768;
+size_t lat_max_nodes();
 
 template <int ARITY>
 imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
@@ -81,8 +84,10 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
         IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
         IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
     }
-    if (n <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh)
-        k_hash_coop<ARITY><<<grid_for(4 * n, 128), 128, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, ctx->d_err);
+    if (n <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh, imt_latency.cu)
+        launch_hash_coop(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
+    else if (n <= lat_max_nodes())  // under ~2 warps per scheduler: the same thread-per-hash kernel built for latency (imt_latency.cu)
+        launch_hash_lat(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
     else
         k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
                                                                       ctx->d_err);
@@ -99,6 +104,14 @@ size_t coop_max_nodes() {
     static const size_t v = [] {
         const char* e = std::getenv("IMT_COOP_MAX_NODES");
         return e ? (size_t)std::strtoull(e, nullptr, 10) : kCoopMaxNodesDefault;
+    }();
+    return v;
+}
+
+size_t lat_max_nodes() {
+    static const size_t v = [] {
+        const char* e = std::getenv("IMT_LAT_MAX_NODES");
+        return e ? (size_t)std::strtoull(e, nullptr, 10) : kLatMaxNodesDefault;
     }();
     return v;
 }
@@ -314,6 +327,33 @@ extern "C" const char* imt_status_string(imt_status st) {
     return "unknown status";
 }
 
+// Every kernel family hashes the same inputs at context creation and must agree bit for bit: the throughput kernel, the
+// 3-lanes-per-hash kernel and the latency build of the thread-per-hash kernel are three compilations of one field source (two
+// carry disciplines), and a toolchain that mis-schedules one of them must not go unnoticed (0.7 ms, once per context).
+static imt_status self_test(imt_ctx* ctx, const PoseidonParams& hp) {
+    constexpr size_t kN = 8;
+    DevBuf in(ctx), out(ctx);
+    IMT_TRY_CUDA(ctx, in.alloc(3 * kN * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, out.alloc(6 * kN * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(in.p, &hp.partial[0], 3 * kN * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));  // canonical Montgomery values
+    Fr* o = out.as<Fr>();
+    IMT_TRY(clear_err(ctx));
+    k_hash<2><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 0 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
+    launch_hash_coop(ctx, 2, in.p, o + 1 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    launch_hash_lat(ctx, 2, in.p, o + 2 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    k_hash<3><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 3 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
+    launch_hash_coop(ctx, 3, in.p, o + 4 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    launch_hash_lat(ctx, 3, in.p, o + 5 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    Fr h[6 * kN];
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY(finish(ctx));
+    for (int a = 0; a < 2; ++a)
+        for (int v = 1; v < 3; ++v)
+            if (std::memcmp(h + (3 * a) * kN, h + (3 * a + v) * kN, kN * sizeof(Fr)) != 0)
+                return fail(ctx, IMT_ERR_CUDA, "self-test failed: the latency kernels and the throughput kernel disagree (toolchain problem)");
+    return IMT_OK;
+}
+
 extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx** out) {
     if (!out || (format != IMT_FE_CANONICAL && format != IMT_FE_MONTGOMERY)) return IMT_ERR_INVALID_ARG;
     *out = nullptr;
@@ -342,12 +382,19 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_params, sizeof(PoseidonParams));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_params, &host_params, sizeof(PoseidonParams), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
+    if (e == cudaSuccess) e = latency_upload_params(&host_params);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "imt_ctx_create: %s\n", cudaGetErrorString(e));
         imt_ctx_destroy(ctx);
         return IMT_ERR_CUDA;
     }
+    if (self_test(ctx, host_params) != IMT_OK) {
+        std::fprintf(stderr, "imt_ctx_create: %s\n", ctx->last_error.c_str());
+        imt_ctx_destroy(ctx);
+        return IMT_ERR_CUDA;
+    }
+    ctx->launches = 0;
     *out = ctx;
     return IMT_OK;
 }
@@ -362,6 +409,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_spec) cudaFree(ctx->d_spec);
+    if (ctx->d_zero_leaf) cudaFree(ctx->d_zero_leaf);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     delete ctx;
 }
@@ -685,9 +733,7 @@ static void launch_fold(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_in
         return;
     }
     if (q <= coop_max_nodes()) {
-        k_fold_paths_coop<<<grid_for(4 * q, 128), 128, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
-                                                                         (const uint4*)d_roots, q, depth, ctx->fmt, d_ok, (uint4*)d_roots_out,
-                                                                         (uint4*)d_states, ctx->d_params, ctx->d_err);
+        launch_fold_coop(ctx, d_leaves, d_indices, d_roots, d_siblings, q, depth, d_ok, d_roots_out, d_states);
     } else {
         const unsigned threads = q >= (size_t)1 << 20 ? kHashThreads : 32;  // mid-size batches: one warp per block spreads evenly over the SMs
         k_fold_paths<<<grid_for(q, threads), threads, 0, ctx->stream>>>((const uint4*)d_leaves, d_indices, (const uint4*)d_siblings,
@@ -713,9 +759,10 @@ static imt_status fold_paths_dev(imt_ctx* ctx, const void* d_leaves, const uint6
 // device buffers while the copy stream drains chunk c-1 to the caller's memory — device memory stays bounded and the PCIe
 // transfer, which is the bound of these calls, overlaps the hashing.
 template <class Launch>
-static imt_status drain_chunks(imt_ctx* ctx, size_t q, size_t per_query, void* host_out, Launch launch) {
-    size_t chunk = 8192;  // queries per launch: enough warps to hide most of the hash latency, 2.5 GB of trace at depth 24
-    while (chunk > 64 && chunk * per_query > ((size_t)3 << 30)) chunk >>= 1;
+static imt_status drain_chunks(imt_ctx* ctx, size_t q, size_t per_query, void* host_out, Launch launch, size_t max_chunk = 8192,
+                               size_t max_bytes = (size_t)3 << 30) {
+    size_t chunk = max_chunk;  // queries per launch: enough warps to hide most of the hash latency, 2.5 GB of trace at depth 24
+    while (chunk > 64 && chunk * per_query > max_bytes) chunk >>= 1;
     if (chunk > q) chunk = q;
     DevBuf buf0(ctx), buf1(ctx);
     IMT_TRY_CUDA(ctx, buf0.alloc(chunk * per_query));
@@ -884,6 +931,109 @@ extern "C" imt_status imt_tree_trace_proofs(imt_tree* t, const uint64_t* indices
     }));
     IMT_TRY(st);
     return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------- insert_leaf witness trace
+extern "C" size_t imt_insert_trace_hashes(unsigned depth) { return 3 + 4 * (size_t)depth; }
+
+// all pointers are device pointers; the level loop is 1 + depth launches whatever the batch size
+static imt_status insert_trace_dev(imt_ctx* ctx, const imt_insert_witness& w, size_t b, unsigned depth, uint64_t first_idx, void* d_states,
+                                   void* d_roots, void* d_new_low, void* d_limbs, uint8_t* d_flags) {
+    if (ctx->generic) return fail(ctx, IMT_ERR_INVALID_ARG, "imt_insert_witness_trace supports the default Poseidon instance only");
+    if (!w.low_leaves || !w.new_leaves || !w.low_idx || (depth && (!w.low_siblings || !w.new_siblings)))
+        return fail(ctx, IMT_ERR_INVALID_ARG, "low_leaves, low_idx, low_siblings, new_leaves and new_siblings are required");
+    if (b == 0) return IMT_OK;
+    if (!ctx->d_zero_leaf) {  // H3(0, 0, 0), once per context
+        IMT_TRY_CUDA(ctx, cudaMalloc((void**)&ctx->d_zero_leaf, 4 * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_zero_leaf, 0, 4 * sizeof(Fr), ctx->stream));
+        IMT_TRY(launch_hash_t<3>(ctx, ctx->d_zero_leaf + 1, ctx->d_zero_leaf, 1, kFmtMontgomery, kFmtMontgomery, ctx->stream));  // zero is zero in both formats
+    }
+    DevBuf dig(ctx);
+    IMT_TRY_CUDA(ctx, dig.alloc(4 * b * sizeof(Fr)));
+    k_trace_insert_leaves<<<grid_for(3 * b, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+        (const uint4*)w.low_leaves, (const uint4*)w.new_leaves, first_idx, b, depth, ctx->fmt, (const uint4*)ctx->d_zero_leaf, (uint4*)d_states,
+        dig.as<uint4>(), (uint4*)d_new_low, ctx->d_err);
+    ++ctx->launches;
+    for (unsigned l = 0; l < depth; ++l) {
+        k_trace_insert_level<<<grid_for(4 * b, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+            (const uint4*)w.low_siblings, (const uint4*)w.new_siblings, w.low_idx, first_idx, b, depth, l, ctx->fmt, (uint4*)d_states, dig.as<uint4>(),
+            (uint4*)d_roots, ctx->d_err);
+        ++ctx->launches;
+    }
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    if (depth == 0 && d_roots) {  // a one-leaf tree: every fold is the leaf hash itself
+        k_convert<<<grid_for(4 * b, 256), 256, 0, ctx->stream>>>(dig.as<uint4>(), (uint4*)d_roots, 4 * b, kFmtMontgomery, ctx->fmt, ctx->d_err);
+        ++ctx->launches;
+    }
+    if (d_limbs) IMT_TRY(launch_limb_witness(ctx, w.low_leaves, w.new_leaves, 3, b, d_limbs, d_flags));
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_insert_witness_trace_dev(imt_ctx* ctx, const imt_insert_witness* d_w, size_t b, unsigned depth, uint64_t first_idx,
+                                                   void* d_states, void* d_roots, void* d_new_low_leaves, void* d_limbs, uint8_t* d_limb_flags) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (!d_w) return fail(ctx, IMT_ERR_INVALID_ARG, "null witness");
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(insert_trace_dev(ctx, *d_w, b, depth, first_idx, d_states, d_roots, d_new_low_leaves, d_limbs, d_limb_flags));
+    return finish(ctx);
+}
+
+// Host arrays in and out. The traces are 12 672 B per hash — 1.25 MB per depth-24 insert — so the batch is cut into chunks of
+// inserts: each chunk runs its level loop into one of two device buffers while the copy stream drains the previous chunk.
+extern "C" imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_witness* w, size_t b, unsigned depth, uint64_t first_idx,
+                                               void* states, void* roots, void* new_low_leaves, void* limbs, uint8_t* limb_flags) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (!w) return fail(ctx, IMT_ERR_INVALID_ARG, "null witness");
+    if (!w->low_leaves || !w->new_leaves || !w->low_idx || (depth && (!w->low_siblings || !w->new_siblings)))
+        return fail(ctx, IMT_ERR_INVALID_ARG, "low_leaves, low_idx, low_siblings, new_leaves and new_siblings are required");
+    if (b == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dll(ctx), dnl(ctx), dli(ctx), dls(ctx), dns(ctx), dro(ctx), dnw(ctx), dlm(ctx), dfl(ctx);
+    IMT_TRY_CUDA(ctx, dll.alloc(b * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dnl.alloc(b * 3 * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dli.alloc(b * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dls.alloc(b * (size_t)depth * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dns.alloc(b * (size_t)depth * sizeof(Fr)));
+    if (roots) IMT_TRY_CUDA(ctx, dro.alloc(b * 4 * sizeof(Fr)));
+    if (new_low_leaves) IMT_TRY_CUDA(ctx, dnw.alloc(b * 3 * sizeof(Fr)));
+    if (limbs) IMT_TRY_CUDA(ctx, dlm.alloc(b * 6 * sizeof(Fr)));
+    if (limbs && limb_flags) IMT_TRY_CUDA(ctx, dfl.alloc(b * 3));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dll.p, w->low_leaves, b * 3 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dnl.p, w->new_leaves, b * 3 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dli.p, w->low_idx, b * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dls.p, w->low_siblings, b * (size_t)depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dns.p, w->new_siblings, b * (size_t)depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    const size_t S = imt_insert_trace_hashes(depth), per_insert = S * trace_fe_per_hash(ctx, 2) * sizeof(Fr);
+    auto chunk_of = [&](size_t off, size_t cnt, void* d_states_chunk) -> imt_status {
+        imt_insert_witness dw = {};
+        dw.low_leaves = dll.as<Fr>() + 3 * off;
+        dw.new_leaves = dnl.as<Fr>() + 3 * off;
+        dw.low_idx = dli.as<uint64_t>() + off;
+        dw.low_siblings = dls.as<Fr>() + off * depth;
+        dw.new_siblings = dns.as<Fr>() + off * depth;
+        return insert_trace_dev(ctx, dw, cnt, depth, first_idx + off, d_states_chunk, roots ? dro.as<Fr>() + 4 * off : nullptr,
+                                new_low_leaves ? dnw.as<Fr>() + 3 * off : nullptr, limbs ? dlm.as<Fr>() + 6 * off : nullptr,
+                                (limbs && limb_flags) ? dfl.as<uint8_t>() + 3 * off : nullptr);
+    };
+    if (states) {
+        imt_status st = IMT_OK;
+        IMT_TRY(drain_chunks(ctx, b, per_insert, states, [&](size_t off, size_t cnt, void* d_buf) {
+            const imt_status s1 = chunk_of(off, cnt, d_buf);
+            if (s1 != IMT_OK) st = s1;
+        }, 4096, (size_t)6 << 30));  // a chunk's level launches carry 4 x chunk hashes: keep chunks large (5.1 GB at depth 24)
+        IMT_TRY(st);
+    } else {
+        IMT_TRY(chunk_of(0, b, nullptr));
+    }
+    IMT_TRY(finish(ctx));
+    if (roots) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(roots, dro.p, b * 4 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (new_low_leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(new_low_leaves, dnw.p, b * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (limbs) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limbs, dlm.p, b * 6 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (limbs && limb_flags) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limb_flags, dfl.p, b * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- sharding

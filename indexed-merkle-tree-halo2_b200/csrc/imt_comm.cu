@@ -515,14 +515,17 @@ extern "C" const char* imt_multi_last_error(const imt_multi* m) {
 extern "C" int imt_multi_uses_nccl(const imt_multi* m) { return m && m->g.use_nccl ? m->g.nccl_version : 0; }
 
 namespace {
+// preimages == nullptr: re-hash the leaves already resident in every shard's preimage buffer (checkpoint load)
 imt_status mtree_rebuild(imt_mtree* mt, const void* preimages) {
     imt_group* g = &mt->m->g;
     const size_t n_local = mt->n_total / g->world;
     // queue every device's pipeline first (H2D chunks + leaf kernels + levels are all asynchronous), THEN wait: the N builds overlap
     imt_status st = IMT_OK;
-    for (unsigned i = 0; i < g->world && st == IMT_OK; ++i)
-        st = enqueue_rebuild(mt->shards[i], static_cast<const char*>(preimages) + (size_t)i * n_local * 3 * sizeof(Fr), false);
-    for (unsigned i = 0; i < g->world; ++i) {
+    for (unsigned i = 0; i < g->world && st == IMT_OK; ++i) {
+        if (preimages) st = enqueue_rebuild(mt->shards[i], static_cast<const char*>(preimages) + (size_t)i * n_local * 3 * sizeof(Fr), false);
+        else st = enqueue_rebuild(mt->shards[i], mt->shards[i]->d_pre, true);
+    }
+    for (unsigned i = 0; i < g->world && preimages; ++i) {
         const imt_status s2 = wait_staging(g->ctxs[i]);
         if (st == IMT_OK) st = s2;
     }
@@ -536,6 +539,32 @@ imt_status mtree_rebuild(imt_mtree* mt, const void* preimages) {
 }
 }  // namespace
 
+namespace imt_host {
+// an imt_mtree of n leaves with every buffer allocated and nothing built (imt_multi_build_from_leaves, checkpoint load)
+imt_status mtree_alloc(imt_multi* m, size_t n, imt_mtree** out) {
+    imt_group* g = &m->g;
+    imt_ctx* c0 = g->ctxs[0];
+    imt_mtree* mt = new (std::nothrow) imt_mtree();
+    if (!mt) return fail(c0, IMT_ERR_CUDA, "out of host memory");
+    mt->m = m;
+    mt->n_total = n;
+    for (unsigned i = 0; i < g->world; ++i) {
+        cudaSetDevice(g->ctxs[i]->device);
+        imt_tree* t = nullptr;
+        const imt_status st = tree_alloc(g->ctxs[i], n / g->world, true, &t);
+        if (st != IMT_OK) {
+            c0->last_error = g->ctxs[i]->last_error;
+            imt_mtree_destroy(mt);
+            return st;
+        }
+        mt->shards.push_back(t);
+    }
+    *out = mt;
+    return IMT_OK;
+}
+imt_status mtree_rebuild_resident(imt_mtree* mt) { return mtree_rebuild(mt, nullptr); }
+}  // namespace imt_host
+
 // IndexedMerkleTree::new (src/utils.rs:20-57) fused with the leaf hashing (src/indexed_merkle_tree.rs:662-671) over all devices
 extern "C" imt_status imt_multi_build_from_leaves(imt_multi* m, const void* preimages, size_t n, imt_mtree** out) {
     if (!m || !out) return IMT_ERR_INVALID_ARG;
@@ -545,18 +574,9 @@ extern "C" imt_status imt_multi_build_from_leaves(imt_multi* m, const void* prei
     IMT_TRY(check_leaf_count(c0, n));
     if (!preimages) return fail(c0, IMT_ERR_INVALID_ARG, "null preimages");
     if (n < g->world || (n / g->world) * g->world != n) return fail(c0, IMT_ERR_INVALID_ARG, "fewer leaves than devices");
-    imt_mtree* mt = new (std::nothrow) imt_mtree();
-    if (!mt) return fail(c0, IMT_ERR_CUDA, "out of host memory");
-    mt->m = m;
-    mt->n_total = n;
-    imt_status st = IMT_OK;
-    for (unsigned i = 0; i < g->world && st == IMT_OK; ++i) {
-        cudaSetDevice(g->ctxs[i]->device);
-        imt_tree* t = nullptr;
-        st = tree_alloc(g->ctxs[i], n / g->world, true, &t);
-        if (st == IMT_OK) mt->shards.push_back(t);
-    }
-    if (st == IMT_OK) st = mtree_rebuild(mt, preimages);
+    imt_mtree* mt = nullptr;
+    IMT_TRY(mtree_alloc(m, n, &mt));
+    const imt_status st = mtree_rebuild(mt, preimages);
     if (st != IMT_OK) {
         imt_mtree_destroy(mt);
         return st;

@@ -293,12 +293,13 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const uint4* __restrict__
 // them: nl_q, nl_r, ll_q, ll_r, llv_q, llv_r; plus the three bits it derives from them (is_less_than, IMT:98-125):
 // flags[3i] = nl < ll (is_next_val_greater, IMT:178), flags[3i+1] = llv < nl (check_less_than, IMT:226), flags[3i+2] = the
 // witness satisfies both prover-side assertions (IMT:180-191 with is_new_leaf_largest = (ll == 0), IMT:226-228).
-__global__ void __launch_bounds__(256) k_limb_witness(const uint4* __restrict__ low_leaves, const uint4* __restrict__ new_vals, size_t b, int fmt,
-                                                      uint4* __restrict__ limbs, uint8_t* __restrict__ flags, uint32_t* __restrict__ err) {
+__global__ void __launch_bounds__(256) k_limb_witness(const uint4* __restrict__ low_leaves, const uint4* __restrict__ new_vals, size_t new_stride,
+                                                      size_t b, int fmt, uint4* __restrict__ limbs, uint8_t* __restrict__ flags,
+                                                      uint32_t* __restrict__ err) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= b) return;
     uint32_t v[3][8];  // nl, ll, llv as canonical integers
-    load_fe(v[0], new_vals + 2 * i);
+    load_fe(v[0], new_vals + 2 * new_stride * i);  // new_stride = 3: the val field of an array of leaf preimages
     load_fe(v[1], low_leaves + 2 * (3 * i + 1));
     load_fe(v[2], low_leaves + 2 * (3 * i));
     bool ok = true;
@@ -768,6 +769,15 @@ bool sharded(const imt_tree* t) { return t->world > 1; }
 }  // namespace
 
 namespace imt_host {
+imt_status launch_limb_witness(imt_ctx* ctx, const void* d_low_leaves, const void* d_new_vals, size_t new_stride, size_t b, void* d_limbs,
+                               uint8_t* d_flags) {
+    if (b == 0) return IMT_OK;
+    k_limb_witness<<<grid_for(b, 256), 256, 0, ctx->stream>>>((const uint4*)d_low_leaves, (const uint4*)d_new_vals, new_stride, b, ctx->fmt,
+                                                              (uint4*)d_limbs, d_flags, ctx->d_err);
+    ++ctx->launches;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    return IMT_OK;
+}
 void invalidate_index(imt_tree* t) {  // the buffers are kept for the next build of the index
     t->index_valid = false;
     t->occupied = 0;
@@ -1121,7 +1131,7 @@ extern "C" imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leav
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dl.p, low_leaves, b * 3 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, new_vals, b * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     IMT_TRY(clear_err(ctx));
-    k_limb_witness<<<grid_for(b, 256), 256, 0, ctx->stream>>>(dl.as<uint4>(), dv.as<uint4>(), b, ctx->fmt, dout.as<uint4>(), df.as<uint8_t>(),
+    k_limb_witness<<<grid_for(b, 256), 256, 0, ctx->stream>>>(dl.as<uint4>(), dv.as<uint4>(), 1, b, ctx->fmt, dout.as<uint4>(), df.as<uint8_t>(),
                                                               ctx->d_err);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());

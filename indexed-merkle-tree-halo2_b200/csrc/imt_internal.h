@@ -36,6 +36,7 @@ struct imt_ctx {
     imt::SpecLayout spec{3, 8, 57};
     bool generic = false;
     imt::Fr* d_spec = nullptr;  // SpecLayout-ordered parameter array (derived and uploaded on first use)
+    imt::Fr* d_zero_leaf = nullptr;  // H3(0, 0, 0) in Montgomery form: the empty leaf (indexed_merkle_tree.rs:247-251); made on first use
     // multi-GPU: the group this context belongs to (imt_comm_create / imt_multi_create) and its position among the group's
     // local contexts; null for a single-GPU context
     imt_group* group = nullptr;
@@ -191,7 +192,19 @@ imt_status wait_staging(imt_ctx* ctx);
 imt_status tree_alloc(imt_ctx* ctx, size_t n, bool with_pre, imt_tree** out);
 imt_status check_leaf_count(imt_ctx* ctx, size_t n);
 
+// ---- implemented in imt_latency.cu (compiled with free carry chains): the kernels of small batches
+cudaError_t latency_upload_params(const imt::PoseidonParams* host_params);
+// 3 lanes per hash (poseidon_coop.cuh): batches of <= coop_max_nodes() hashes
+void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
+// one thread per hash, latency build: batches that leave the schedulers under-filled
+void launch_hash_lat(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
+void launch_fold_coop(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
+                      unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);
+
 // ---- implemented in imt_indexed.cu
+// 128-bit limb witnesses of (low leaf, new value) pairs on the compute stream; new values are read with a stride in FE
+imt_status launch_limb_witness(imt_ctx* ctx, const void* d_low_leaves, const void* d_new_vals, size_t new_stride, size_t b, void* d_limbs,
+                               uint8_t* d_flags);
 void invalidate_index(imt_tree* t);
 imt_status ensure_index(imt_tree* t);
 
@@ -208,6 +221,8 @@ imt_ctx* group_ctx(imt_group* g, unsigned slot);
 unsigned group_rank(const imt_group* g, unsigned slot);
 // the group and the local shards behind a single-process multi-GPU tree
 imt_status mtree_parts(imt_mtree* mt, imt_group** g, std::vector<imt_tree*>* trees);
+imt_status mtree_alloc(imt_multi* m, size_t n, imt_mtree** out);  // buffers only, nothing built
+imt_status mtree_rebuild_resident(imt_mtree* mt);                // re-hash the preimages resident in every shard + exchange
 
 // ---- implemented in imt_spec.cu (any-width instances)
 // permutations of one hash of `arity` inputs, and FE per hash of its witness trace

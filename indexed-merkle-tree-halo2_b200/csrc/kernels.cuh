@@ -234,6 +234,114 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* 
     hash_fixed<2>(d, x, c_params, sink);
 }
 
+// ---- witness trace of the chip's insert_leaf (indexed_merkle_tree.rs:253-313), one insert = 3 + 4 depth hashes in call order:
+//   slot 0            H3(low leaf before)                       verify_non_inclusion, IMT:193-194
+//   1 .. d            fold of that hash up the low path          -> old root, IMT:196-204
+//   d + 1             H3(low.val, new.val, new_idx)              the rewired low leaf, IMT:265-275
+//   d + 2 .. 2d + 1   its fold up the SAME siblings              -> interim root, IMT:277-284
+//   2d + 2 .. 3d + 1  fold of the empty leaf H3(0,0,0) (a constant in the chip, IMT:247-251) up the new leaf's path -> interim root, IMT:286-294
+//   3d + 2            H3(new leaf)                               IMT:299-303
+//   3d + 3 .. 4d + 2  its fold up the same path                  -> new root, IMT:305-313
+// The four folds of an insert are independent of each other and of every other insert, so a batch of b inserts is one launch
+// of 3b traced leaf hashes and then, level by level, one launch of 4b traced node hashes (digests carried in `dig`, Montgomery).
+__device__ __forceinline__ unsigned insert_trace_slot(unsigned fold, unsigned level, unsigned depth) {
+    return fold == 0 ? 1 + level : fold == 1 ? depth + 2 + level : fold == 2 ? 2 * depth + 2 + level : 3 * depth + 3 + level;
+}
+__global__ void __launch_bounds__(kHashThreads) k_trace_insert_leaves(const uint4* __restrict__ low_leaves, const uint4* __restrict__ new_leaves,
+                                                                      uint64_t first_idx, size_t b, unsigned depth, int fmt,
+                                                                      const uint4* __restrict__ zero_leaf_hash, uint4* __restrict__ states,
+                                                                      uint4* __restrict__ dig, uint4* __restrict__ new_low_out,
+                                                                      uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= 3 * b) return;
+    const size_t k = i / 3;
+    const unsigned j = (unsigned)(i % 3);
+    uint32_t x[3][8], d[8];
+    bool ok = true;
+    if (j == 1) {  // { low.val, new.val, new_idx }: the low leaf after it has been pointed at the new one (IMT:265-270)
+        load_fe(x[0], low_leaves + 2 * (3 * k));
+        load_fe(x[1], new_leaves + 2 * (3 * k));
+        ok &= ingest(x[0], fmt);
+        ok &= ingest(x[1], fmt);
+        const uint64_t slot = first_idx + k;
+        uint32_t c[8] = {(uint32_t)slot, (uint32_t)(slot >> 32), 0, 0, 0, 0, 0, 0};
+        if (new_low_out) {  // the preimage itself, in the caller's format
+            uint32_t o[3][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[q][t] = x[q][t];
+                canonicalize(o[q]);
+                egress(o[q], fmt);
+                store_fe(new_low_out + 2 * (3 * k + q), o[q]);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[2][t] = c[t];
+            if (fmt == kFmtMontgomery) {
+                to_mont(o[2], o[2]);
+                canonicalize(o[2]);
+            }
+            store_fe(new_low_out + 2 * (3 * k + 2), o[2]);
+        }
+        to_mont(x[2], c);
+    } else {
+        const uint4* src = (j == 0 ? low_leaves : new_leaves) + 2 * (3 * k);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            load_fe(x[q], src + 2 * q);
+            ok &= ingest(x[q], fmt);
+        }
+    }
+    if (!ok) atomicOr(err, kErrNonCanonical);
+    const unsigned S = 3 + 4 * depth, slot = j == 0 ? 0 : j == 1 ? depth + 1 : 3 * depth + 2;
+    if (states) {
+        TraceSink sink{states + (k * S + slot) * (size_t)(kStatesPerHash * 3 * 2), fmt};
+        hash_fixed<3>(d, x, c_params, sink);
+    } else {
+        NoTrace nt;
+        hash_fixed<3>(d, x, c_params, nt);
+    }
+    store_fe(dig + 2 * (4 * k + (j == 2 ? 3 : j)), d);
+    if (j == 0) {  // the empty leaf the new one replaces: fold 2 starts from the constant
+        uint32_t z[8];
+        load_fe(z, zero_leaf_hash);
+        store_fe(dig + 2 * (4 * k + 2), z);
+    }
+}
+__global__ void __launch_bounds__(kHashThreads) k_trace_insert_level(const uint4* __restrict__ low_sib, const uint4* __restrict__ new_sib,
+                                                                     const uint64_t* __restrict__ low_idx, uint64_t first_idx, size_t b,
+                                                                     unsigned depth, unsigned level, int fmt, uint4* __restrict__ states,
+                                                                     uint4* __restrict__ dig, uint4* __restrict__ roots_out,
+                                                                     uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= 4 * b) return;
+    const size_t k = i >> 2;
+    const unsigned f = (unsigned)(i & 3);
+    uint32_t h[8], s[8], x[2][8], d[8];
+    load_fe(h, dig + 2 * i);
+    load_fe(s, (f < 2 ? low_sib : new_sib) + 2 * (k * depth + level));
+    if (!ingest(s, fmt)) atomicOr(err, kErrNonCanonical);
+    const uint64_t node = (f < 2 ? low_idx[k] : first_idx + k) >> level;
+    const bool left = (node & 1) == 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        x[0][t] = left ? h[t] : s[t];
+        x[1][t] = left ? s[t] : h[t];
+    }
+    if (states) {
+        TraceSink sink{states + (k * (3 + 4 * depth) + insert_trace_slot(f, level, depth)) * (size_t)(kStatesPerHash * 3 * 2), fmt};
+        hash_fixed<2>(d, x, c_params, sink);
+    } else {
+        NoTrace nt;
+        hash_fixed<2>(d, x, c_params, nt);
+    }
+    store_fe(dig + 2 * i, d);
+    if (roots_out && level + 1 == depth) {
+        egress(d, fmt);
+        store_fe(roots_out + 2 * i, d);
+    }
+}
+
 // Format conversion of a dense FE array (used for roots / levels / preimages crossing the boundary)
 __global__ void k_convert(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int from_fmt, int to_fmt,
                           uint32_t* __restrict__ err) {

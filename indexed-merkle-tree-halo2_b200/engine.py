@@ -227,19 +227,24 @@ class Engine:
         return self._tree(self._lib.imt_tree_build_from_hashes_dev, _dev_ptr(d_hashes), n)
 
     def load_tree(self, path):
-        """Rebuilds a tree from a checkpoint written by Tree.save(): re-hashes the stored leaves on the GPU and checks the
-        result against the stored root."""
-        with np.load(path) as z:
-            pre, root, fmt = z["preimages"], z["root"], int(z["format"])
-            inst = tuple(int(x) for x in z["instance"]) if "instance" in z else (3, 2, 8, 57)
-        if inst != (self.t, self.rate, self.r_f, self.r_p):
-            raise ValueError(f"checkpoint was written with Poseidon instance {inst}")
-        if fmt != self.fmt:
-            raise ValueError("checkpoint was written by an engine of the other field-element format")
-        tree = self.build_from_leaves(pre)
-        if not np.array_equal(tree.root(), root):
-            raise ImtError(_ffi.ERR_INVALID_ARG, "checkpoint is corrupt: the rebuilt root differs from the stored one")
-        return tree
+        """imt_tree_load: rebuilds a tree from a checkpoint written by Tree.save() (flat header + n x 96 bytes of canonical
+        little-endian `val, next_val, next_idx` + root): the leaves are re-hashed on the GPU and the file is refused
+        (ImtError) when the rebuilt root differs from the stored one."""
+        import os
+        h = ctypes.c_void_p()
+        self._check(self._lib.imt_tree_load(self._h, os.fsencode(path), ctypes.byref(h)))
+        return Tree(self, h)
+
+    @staticmethod
+    def checkpoint_info(path):
+        """header + root of a checkpoint file (no device needed): dict(num_leaves, depth, instance, root)"""
+        import os
+        info = _ffi.CheckpointInfo()
+        st = _ffi.load().imt_checkpoint_read_info(os.fsencode(path), ctypes.byref(info))
+        if st != _ffi.OK:
+            raise ImtError(st, f"{path} is not an imt_b200 checkpoint")
+        return dict(num_leaves=int(info.num_leaves), depth=int(info.depth), instance=(info.t, info.rate, info.r_f, info.r_p),
+                    root=np.frombuffer(bytes(info.root), dtype=np.uint64).copy())
 
     # ---- path folding
     def verify_proofs(self, leaves, indices, roots, siblings):
@@ -283,34 +288,29 @@ class Engine:
                                                           _dev_ptr(d_states) if d_states is not None else None,
                                                           _dev_ptr(d_roots) if d_roots is not None else None))
 
-    def trace_insert_witness(self, w, first_idx):
-        """Poseidon witness traces of everything the chip's insert_leaf hashes, per insert and in its call order
-        (indexed_merkle_tree.rs:253-313): 3 leaf hashes + 4 x depth node hashes = (6 + 8 depth) permutations.
-        `w` is the dict Tree.insert_batch returned, first_idx the slot of its first insert. Returns traces
-        (b, 132, 3, 4) for the leaf hashes / (b, depth, 132, 3, 4) for the folds, plus the roots each fold ends in."""
+    def trace_insert_witness(self, w, first_idx, out_states=None):
+        """imt_insert_witness_trace — the Poseidon witness traces of everything the chip's insert_leaf hashes, per insert and in
+        its call order (indexed_merkle_tree.rs:253-313): 3 leaf hashes + 4 x depth node hashes = (6 + 8 depth) permutations, ONE
+        C call for the whole batch. `w` is the dict Tree.insert_batch returned, first_idx the slot of its first insert.
+        Returns views into states[b][3 + 4 depth][132][3][4] under the names of the chip's steps, plus the roots each fold
+        ends in, the rewired low leaf and the 128-bit limb witnesses."""
         b, d = w["low_idx"].shape[0], w["low_siblings"].shape[1]
-        new_idx = np.arange(first_idx, first_idx + b, dtype=np.uint64)
-        idx_fe = np.zeros((b, 4), np.uint64)
-        if self.fmt == _ffi.FE_CANONICAL:
-            idx_fe[:, 0] = new_idx
-        else:
-            idx_fe = fes_from_ints([(int(i) << 256) % P for i in new_idx])
-        new_low = w["low_leaves"].copy()                                    # {low.val, new.val, new_idx}   IMT:265-270
-        new_low[:, 1] = w["new_leaves"][:, 0]
-        new_low[:, 2] = idx_fe
-        zero = np.zeros((b, 3, 4), np.uint64)                               # the empty slot the new leaf replaces, IMT:247-251
-        h_low, t_low = self.trace_hashes(w["low_leaves"], 3)                # verify_non_inclusion: low leaf hash      IMT:193-194
-        r_old, t_low_path = self.trace_merkle_proofs(h_low, w["low_idx"], w["low_siblings"])            # ... under old_root IMT:196-204
-        h_nl, t_nl = self.trace_hashes(new_low, 3)                          # updated low leaf                         IMT:271-275
-        r_int, t_int_path = self.trace_merkle_proofs(h_nl, w["low_idx"], w["low_siblings"])             # interim root       IMT:277-284
-        h_zero, _ = self.trace_hashes(zero[:1], 3, want_states=False)
-        r_zero, t_zero_path = self.trace_merkle_proofs(np.broadcast_to(h_zero, (b, 4)), new_idx, w["new_siblings"])  # IMT:286-294
-        h_new, t_new = self.trace_hashes(w["new_leaves"], 3)                # new leaf hash                            IMT:299-303
-        r_new, t_new_path = self.trace_merkle_proofs(h_new, new_idx, w["new_siblings"])                 # new root           IMT:305-313
-        limbs, limb_flags = self.non_inclusion_limbs(w["low_leaves"], w["new_leaves"][:, 0])            # hi/lo splits       IMT:143-172, 206-222
-        return dict(limbs=limbs, limb_flags=limb_flags, low_leaf=t_low, low_path=t_low_path, new_low_leaf=t_nl, interim_path=t_int_path, zero_path=t_zero_path,
-                    new_leaf=t_new, new_path=t_new_path, old_root=r_old, interim_root=r_int, zero_leaf_root=r_zero, new_root=r_new,
-                    new_low_leaf_preimage=new_low)
+        S = 3 + 4 * d
+        shape = (b, S, self.states_per_hash(2), self.t, 4)
+        states = out_states if out_states is not None else np.empty(shape, np.uint64)
+        if states.shape != shape or states.dtype != np.uint64 or not states.flags.c_contiguous:
+            raise ValueError(f"out_states must be a C-contiguous uint64 array of shape {shape}")
+        roots, new_low = np.empty((b, 4, 4), np.uint64), np.empty((b, 3, 4), np.uint64)
+        limbs, flags = np.empty((b, 6, 4), np.uint64), np.empty((b, 3), np.uint8)
+        cw = _ffi.InsertWitness()
+        for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings"):
+            setattr(cw, k, np.ascontiguousarray(w[k]).ctypes.data)
+        self._check(self._lib.imt_insert_witness_trace(self._h, ctypes.byref(cw), b, d, int(first_idx), _ptr(states), _ptr(roots), _ptr(new_low),
+                                                       _ptr(limbs), _ptr(flags)))
+        return dict(states=states, limbs=limbs, limb_flags=flags.astype(bool), low_leaf=states[:, 0], low_path=states[:, 1:1 + d],
+                    new_low_leaf=states[:, d + 1], interim_path=states[:, d + 2:2 * d + 2], zero_path=states[:, 2 * d + 2:3 * d + 2],
+                    new_leaf=states[:, 3 * d + 2], new_path=states[:, 3 * d + 3:4 * d + 3], old_root=roots[:, 0], interim_root=roots[:, 1],
+                    zero_leaf_root=roots[:, 2], new_root=roots[:, 3], new_low_leaf_preimage=new_low)
 
     def non_inclusion_limbs(self, low_leaves, new_vals):
         """128-bit limb witnesses of verify_non_inclusion (indexed_merkle_tree.rs:143-172, 206-222): (b, 6, 4) FE in the
@@ -451,15 +451,12 @@ class Tree:
         return out
 
     def save(self, path):
-        """Checkpoint: the leaves as the reference's serde derive would write them — per leaf val, next_val,
-        next_idx (utils.rs:12-17), 32 little-endian bytes each in the engine's format (canonical = halo2curves `to_repr`) —
-        plus the root. The levels are NOT stored: load_tree() re-hashes (0.55 s at depth 24) and verifies the root."""
-        if self.shard_info()[1] > 1:
-            raise ValueError("checkpoint a sharded tree shard by shard is not supported: gather the preimages and save the whole tree")
-        n = self.num_leaves
-        e = self.engine
-        np.savez(path, preimages=self.preimages(n), root=self.root(), format=np.int64(e.fmt),
-                 instance=np.array([e.t, e.rate, e.r_f, e.r_p], np.int64))
+        """imt_tree_save — checkpoint: a 64-byte header, the leaves as the reference's serde derive would lay
+        them out (utils.rs:12-17: val, next_val, next_idx, each the canonical 32-byte little-endian `to_repr` bytes whatever
+        the engine's format) and the canonical root. The levels are NOT stored: load_tree() re-hashes (0.55 s at depth 24)
+        and verifies the root."""
+        import os
+        self.engine._check(self._lib.imt_tree_save(self._h, os.fsencode(path)))
 
     def rebuild_from_leaves(self, preimages):
         a = _fe_array(preimages, (3,))
@@ -777,6 +774,13 @@ class Multi:
         self._check(self._lib.imt_multi_build_from_leaves(self._h, ctypes.c_void_p(host_ptr), n, ctypes.byref(h)))
         return MTree(self, h)
 
+    def load_tree(self, path):
+        """imt_multi_load: a checkpoint (of a single-GPU or a sharded tree: the file is the same) into a tree sharded over this group"""
+        import os
+        h = ctypes.c_void_p()
+        self._check(self._lib.imt_multi_load(self._h, os.fsencode(path), ctypes.byref(h)))
+        return MTree(self, h)
+
     def close(self):
         if getattr(self, "_h", None):
             for t in list(self._trees):
@@ -829,6 +833,10 @@ class MTree:
 
     def rebuild_from_leaves_ptr(self, host_ptr):
         self.multi._check(self._lib.imt_mtree_rebuild_from_leaves(self._h, ctypes.c_void_p(host_ptr)))
+
+    def save(self, path):
+        import os
+        self.multi._check(self._lib.imt_mtree_save(self._h, os.fsencode(path)))
 
     def get_proofs(self, indices):
         idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)

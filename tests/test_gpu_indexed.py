@@ -378,18 +378,42 @@ def test_checkpoint_round_trip(eng, tmp_path):
     pre = synth.indexed_preimages(n, m, seed=12)
     tree = eng.build_from_leaves(pre)
     tree.insert_batch(synth.field_elements(20, seed=13))
-    path = str(tmp_path / "tree.npz")
+    path = str(tmp_path / "tree.imt")
     tree.save(path)
     back = eng.load_tree(path)
     assert np.array_equal(back.root(), tree.root()) and np.array_equal(back.preimages(n), tree.preimages(n)) and back.occupied == m + 20
-    raw = np.load(path)
-    assert raw["preimages"].tobytes()[:96] == tree.preimages(n)[0].tobytes()       # 3 x 32-byte little-endian canonical FE per leaf
-    bad = dict(raw)
-    bad["preimages"] = raw["preimages"].copy()
-    bad["preimages"][5, 0, 0] ^= np.uint64(1)
-    np.savez(path, **bad)
+    raw = open(path, "rb").read()
+    assert len(raw) == 64 + 96 * n + 32 and raw[:8] == b"IMTB200\0"
+    assert raw[64:64 + 96] == tree.preimages(n)[0].tobytes()       # 3 x 32-byte little-endian canonical FE per leaf (utils.rs:12-17 order)
+    assert raw[-32:] == tree.root().tobytes()
+    info = eng.checkpoint_info(path)
+    assert info["num_leaves"] == n and info["instance"] == (3, 2, 8, 57) and np.array_equal(info["root"], tree.root())
+    # a Montgomery-format engine reads and writes the SAME bytes (the file is canonical whatever the context format)
+    em = imt_b200.Engine(0, "montgomery")
+    tm = em.load_tree(path)
+    path2 = str(tmp_path / "tree_m.imt")
+    tm.save(path2)
+    assert open(path2, "rb").read() == raw
+    em.close()
+    bad = bytearray(raw)
+    bad[64 + 96 * 5] ^= 1                                           # one bit of leaf 5's val
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(imt_b200.ImtError, match="corrupt"):
+        eng.load_tree(path)
+    bad = bytearray(raw)
+    bad[64 + 31] = 0xFF                                             # leaf 0's val >= p
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(imt_b200.ImtError) as ei:
+        eng.load_tree(path)
+    assert ei.value.status == imt_b200._ffi.ERR_NON_CANONICAL
+    open(path, "wb").write(raw[: 64 + 96 * 7])                      # truncated
     with pytest.raises(imt_b200.ImtError):
         eng.load_tree(path)
+    e5 = imt_b200.Engine(0, "canonical", t=5, rate=4, r_f=8, r_p=60)
+    open(path, "wb").write(raw)
+    with pytest.raises(imt_b200.ImtError, match="another Poseidon instance"):
+        e5.load_tree(path)
+    e5.close()
 
 
 def test_reference_test_insert_leaf_mirror(eng):

@@ -2,10 +2,10 @@
 // instruction forms it is built from cost when nothing else runs on the SM sub-partition. Evidence for DESIGN.md
 // "Cooperative kernel"; not part of the library.
 //
-// Build (twice: the default carry discipline and the free-chain one), from the repo root:
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Iinclude -Iindexed-merkle-tree-halo2_b200/csrc \
-//        tools/latency_lab.cu indexed-merkle-tree-halo2_b200/csrc/poseidon_params.cpp -o tools/_build/latency_lab
-//   ... -DIMT_FREE_CHAINS ... -o tools/_build/latency_lab_free
+// Build, from the repo root, once per carry discipline (IMT_FREE_MASK = 0 .. 31, see csrc/fr.cuh; -DLAB_SWEEP keeps only the level
+// timings and the known-answer check, -DLAB_PROBES adds the instruction-form probes):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Iinclude -Iindexed-merkle-tree-halo2_b200/csrc -Itools/lab \
+//        -DIMT_FREE_MASK=29 tools/lab/latency_lab.cu indexed-merkle-tree-halo2_b200/csrc/poseidon_params.cpp -o tools/_build/lab_m29
 // Run on a B200: prints cycles per operation (clock64 inside the kernel, one warp) and microseconds per level (CUDA events).
 #include <cuda_runtime.h>
 
@@ -318,6 +318,7 @@ int main() {
     CK(cudaMalloc(&d_err, 4));
     CK(cudaMemset(d_err, 0, 4));
 
+#ifndef LAB_SWEEP
     // ---- field-operation chains, one warp
     const char* names[6] = {"mont_mul", "mont_sqr", "mul_add", "sbox_add (x^5 + c)", "dot3", "fma2 (a b + c + d)"};
     for (int lanes : {32}) {
@@ -349,6 +350,7 @@ int main() {
         CK(cudaMemcpy(&h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost));
         std::printf("mont_mul, 5 warps in the block (2 on sub-partition 0): %9.1f cycles per operation per warp\n", (double)h / kChain);
     }
+#endif  // LAB_SWEEP
 #if IMT_FREE_MASK == 0 && defined(LAB_PROBES)
     {
         std::printf("## radix-2^29 carry-free arithmetic (9 limbs, 64-bit column sums), one warp: cycles per operation\n");
@@ -460,6 +462,15 @@ int main() {
         bad = 0;
         for (size_t i = 0; i < n / 2; ++i) bad += std::memcmp(&a[i], &b[i], sizeof(Fr)) != 0;
         std::printf("k_hash_quad<3> vs k_hash_coop<3> on %zu triples (canonical format): %zu differ%s\n", n / 2, bad, bad ? "  <-- MISMATCH" : " (bit-exact)");
+    }
+    {   // known answer: H2(0, 0) = 0x2b2ceb...: both latency kernels on canonical zeros (SURVEY.md 8c derived vector)
+        CK(cudaMemset(d_in, 0, 64 * sizeof(Fr)));
+        k_hash_coop<2><<<1, 128>>>((const uint4*)d_in, (uint4*)d_out, 4, kFmtCanonical, kFmtCanonical, d_params, d_err);
+        k_hash_quad<2><<<1, 128>>>((const uint4*)d_in, (uint4*)d_out2, 4, kFmtCanonical, kFmtCanonical, d_params, d_aux, d_err);
+        uint32_t a[8], b[8];
+        CK(cudaMemcpy(a, d_out, 32, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b, d_out2, 32, cudaMemcpyDeviceToHost));
+        std::printf("H2(0,0) coop %08x%08x...%08x quad %08x%08x...%08x   (want 2b2ceb8eb042a119...80eeb04f)\n", a[7], a[6], a[0], b[7], b[6], b[0]);
     }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

@@ -1,3 +1,8 @@
+// LAB ONLY (tools/lab/latency_lab.cu) — measured and NOT shipped, see DESIGN.md "Cooperative kernel": 258 us per level against
+// 283 us for the shipped 3-lane kernel under the serial carry discipline, but only 227 us against 233 us once both run with free
+// carry chains — and under 7 of the 32 chain-head masks this kernel (never the shipped one) returned WRONG digests whose value
+// changed with the ptxas optimisation level, i.e. a code-generation hazard we could not pin down. Kept as evidence.
+//
 // Latency-oriented Poseidon, second generation: FOUR lanes per hash and THREE dependent multiply slots per partial round.
 //
 // poseidon_coop.cuh spends 4 dependent multiply-reduce slots per partial round (x^2, x^4, x^4 x + c, row . s). The last two
@@ -18,6 +23,16 @@
 // field elements as poseidon.cuh, bit for bit after canonicalisation (the representatives in [0, 2p) differ in between).
 #pragma once
 #include "poseidon_coop.cuh"
+
+#ifdef IMT_QUAD_CLEAR_AT_LOOP_TOP
+#define IMT_QUAD_LOOP_CLEAR cc::clear()
+#else
+#define IMT_QUAD_LOOP_CLEAR (void)0
+#endif
+#ifndef IMT_QUAD_DBG
+#define IMT_QUAD_DBG 0
+#endif
+#define IMT_DBG_CLEAR(bit) do { if (IMT_QUAD_DBG & (bit)) cc::clear(); } while (0)
 
 namespace imt {
 
@@ -82,8 +97,10 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
     // ---- first half of the full rounds
 #pragma unroll 1
     for (int round = 0; round < kHalfF; ++round) {
+        IMT_QUAD_LOOP_CLEAR;
         uint32_t c[8], u0[8], u1[8], u2[8], m0[8], m1[8], m2[8];
         ld_fe(c, &G->full[round][rr]);
+        IMT_DBG_CLEAR(1);
         sbox_add(x, x, c);
         shfl_fe(u0, x, base);
         shfl_fe(u1, x, base + 1);
@@ -92,6 +109,7 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
         ld_fe(m0, &m[rr][0]);
         ld_fe(m1, &m[rr][1]);
         ld_fe(m2, &m[rr][2]);
+        IMT_DBG_CLEAR(2);
         dot3(x, u0, u1, u2, m0, m1, m2);
         sink.emit(x, r, 1 + round);
     }
@@ -110,6 +128,7 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
     }
 #pragma unroll 1
     for (int k = 0; k < kRP; ++k) {
+        IMT_QUAD_LOOP_CLEAR;
         const PartialRound* pr = &G->partial[k];
         const PartialRound* pp = &G->partial[k ? k - 1 : 0];
         uint32_t T1[8], T2[8], B[8], C[8];
@@ -117,6 +136,7 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
         ld_fe(B, side ? &pp->col[r - 1] : &pr->row[0]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) B[i] = lead ? X[i] : B[i];
+        IMT_DBG_CLEAR(4);
         fma1(T1, X, B, S);
         if (k) sink.emit(T1, side ? r : 3, kHalfF + k);  // s1, s2 of the state after partial round k - 1
         uint32_t Y[8];
@@ -128,7 +148,9 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
         ld_fe(C, r == 1 ? &A->kc[k] : &A->zero);
 #pragma unroll
         for (int i = 0; i < 8; ++i) B[i] = lead ? T1[i] : B[i];
+        IMT_DBG_CLEAR(8);
         fma1(T2, T1, B, C);
+        IMT_DBG_CLEAR(32);
         cond_sub_p(T2);  // canonical: lane 0 adds two of these on top of a product
         // exchange: lane 0 <- P1, P2; lane 3 <- x4
         uint32_t V1[8], V2[8];
@@ -144,6 +166,7 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
             c3[i] = lead ? V1[i] : c3[i];
             V2[i] = lead ? V2[i] : 0u;
         }
+        IMT_DBG_CLEAR(16);
         fma2(T3, a3, b3, c3, V2);
         sink.emit(T3, lead ? 0 : 3, kHalfF + 1 + k);  // s0 of the state after partial round k
         // exchange: lanes 1, 2 <- u (lane 3); lane 3 <- x' (lane 0)
@@ -163,8 +186,10 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
     // ---- second half of the full rounds
 #pragma unroll 1
     for (int round = kHalfF; round < kRF; ++round) {
+        IMT_QUAD_LOOP_CLEAR;
         uint32_t c[8], u0[8], u1[8], u2[8], m0[8], m1[8], m2[8];
         ld_fe(c, &G->full[round][rr]);
+        IMT_DBG_CLEAR(1);
         sbox_add(x, x, c);
         shfl_fe(u0, x, base);
         shfl_fe(u1, x, base + 1);
@@ -172,6 +197,7 @@ __device__ __forceinline__ void permute_quad(uint32_t* x, const PoseidonParams* 
         ld_fe(m0, &G->mds[rr][0]);
         ld_fe(m1, &G->mds[rr][1]);
         ld_fe(m2, &G->mds[rr][2]);
+        IMT_DBG_CLEAR(2);
         dot3(x, u0, u1, u2, m0, m1, m2);
         sink.emit(x, r, 1 + kRP + round);
     }
