@@ -15,7 +15,8 @@ HEADERS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/imt_b200.h
 
 all: $(LIB)
 
-# the latency kernels: the same field source with free carry chains (csrc/fr.cuh IMT_FREE_MASK; swept on a B200)
+# carry discipline per kernel family (csrc/fr.cuh IMT_FREE_MASK; all 32 masks swept on a B200, profiles/r02_latency_lab.md)
+$(OBJDIR)/imt_capi.o: NVFLAGS += -DIMT_FREE_MASK=22
 $(OBJDIR)/imt_latency.o: NVFLAGS += -DIMT_FREE_MASK=29
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HEADERS)

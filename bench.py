@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=0, help="query count of the paths / lookups workloads (default 2^16 / 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the paths / lookups / insert legs of the default run")
     return ap.parse_args()
 
 
@@ -151,6 +152,21 @@ def cpu_single_thread_rate(seconds=2.0):
     dt = time.perf_counter() - t0
     hashes = 2 * (1 << d) - 1
     return hashes / dt, f"depth-{d} build ({hashes} hashes) in {dt:.2f}s, 1 thread"
+
+
+def cpu_trace_rate(seconds=2.0):
+    """the oracle's traced hash (132 x 3 states recorded) on one thread: the CPU side of the witness-trace legs"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as O
+    from imt_b200 import synth
+    pairs = synth.field_elements(64).reshape(32, 2, 4)
+    t0, cnt = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        for p_ in pairs:
+            O.hash_trace(p_)
+        cnt += len(pairs)
+    return {"value": cnt / (time.perf_counter() - t0), "unit": "hashes/s", "cores": 1, "kind": "port", "sample": f"{cnt} traced hashes, oracle, 1 thread"}
 
 
 def run_reference(a):
@@ -413,6 +429,169 @@ def run_lookups(a):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- secondary legs of the default run
+def secondary_paths(torch, dist, eng, tree, d_pre, depth, n_local, world, rank, dev, stream, imad_rate, steps):
+    """BASELINE config 4 inside the default run, sharded BY LEAF OWNER with no exchange: 2^16 uniform random GLOBAL leaf indices
+    (the same on every rank); every rank traces the paths whose leaves it owns from its own stored levels + the replicated cap
+    (imt_tree_trace_proofs_dev) and drains its traces over its own PCIe link. Aggregate over ranks, max time over ranks."""
+    import numpy as np
+    import imt_b200
+    from imt_b200 import synth
+    q = 1 << 16
+    n_total = n_local * world
+    g = torch.Generator(device=dev)
+    g.manual_seed(synth.DEFAULT_SEED)
+    idx = torch.randint(0, n_total, (q,), generator=g, device=dev, dtype=torch.int64)
+    mine = idx[(idx // n_local) == rank].contiguous()
+    qm = int(mine.numel())
+    d_states = torch.empty((max(qm, 1), depth, 132, 3, 4), dtype=torch.int64, device=dev)
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    l0 = eng.launches
+    ms = maxr(_ev_time(torch, stream, lambda: tree.trace_proofs_dev(mine, qm, d_states), steps, 2))
+    launches = (eng.launches - l0) // (steps + 2)
+    root = torch.empty(4, dtype=torch.int64, device=dev)
+    tree.root_dev(root)
+    stream.synchronize()
+    assert qm == 0 or bool((d_states[:, -1, -1, 1] == root).all()), "a traced path does not end in the root"
+    # e2e: host indices in, traces out into pinned host memory, every rank over its own link
+    qe = min(qm, max(1, (1 << 14) // world))
+    h_idx = mine[:qe].cpu().numpy().astype(np.uint64)
+    h_states = torch.empty((qe, depth, 132, 3, 4), dtype=torch.int64, pin_memory=True)
+    view = h_states.numpy().view(np.uint64)
+    tree.trace_proofs(h_idx, out_states=view)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tree.trace_proofs(h_idx, out_states=view)
+    dt = maxr(time.perf_counter() - t0)
+    assert bool((h_states[:, -1, -1, 1] == root.cpu()).all())
+    qe_total = torch.tensor([qe], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(qe_total)
+    qe_total = int(qe_total.item())
+    # the fold-based trace (another kernel: leaf hash + get_proofs siblings, folded serially) must write the same bytes
+    ks = min(qm, 64)
+    if ks:
+        sel = mine[:ks].contiguous()
+        sib = torch.empty((ks, depth, 4), dtype=torch.int64, device=dev)
+        leaf = torch.empty((ks, 4), dtype=torch.int64, device=dev)
+        st2 = torch.empty((ks, depth, 132, 3, 4), dtype=torch.int64, device=dev)
+        r2 = torch.empty((ks, 4), dtype=torch.int64, device=dev)
+        tree.get_proofs_dev(sel, ks, sib)
+        eng.hash3_dev(d_pre[sel - rank * n_local].contiguous(), ks, leaf)
+        eng.trace_merkle_proofs_dev(leaf, sel, sib, ks, depth, st2, r2)
+        stream.synchronize()
+        assert bool((st2 == d_states[:ks]).all()) and bool((r2 == root).all()), "tree trace differs from the fold trace"
+    hashes = q * depth
+    peaks = _peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    return {
+        "metric": "merkle_path_witness_trace_hashes_per_s", "value": hashes / (ms * 1e-3), "unit": "hashes/s", "ms_per_step": ms, "n_gpus": world,
+        "config": {"workload": f"2^16 uniform random paths of the depth-{depth} tree, verify_merkle_proof witness trace (132 x 3 FE per hash), "
+                               f"sharded by leaf owner x{world}", "queries": q, "hashes_per_step": hashes, "trace_bytes_per_step": hashes * 132 * 96},
+        "e2e": {"value": qe_total * depth / dt, "unit": "hashes/s", "d2h_gbs": qe_total * depth * 132 * 96 / dt / 1e9,
+                "sample": f"{qe_total} queries through imt_tree_trace_proofs (host indices in, traces into pinned host memory, one PCIe link per GPU)",
+                "h2d_bytes_per_step": qe_total * 8, "d2h_bytes_per_step": qe_total * depth * 132 * 96},
+        "gpu_launches": launches * world,
+        "roofline": {"bound": "imad", "kernel": "k_trace_tree_paths", "achieved": hashes * MACS_PER_HASH / (ms * 1e-3) / 1e9,
+                     "peak": imad_rate * world / 1e9, "unit": "GMAC/s", "frac": hashes * MACS_PER_HASH / (ms * 1e-3) / (imad_rate * world),
+                     "traffic": TRACE_DRAM_BYTES_PER_HASH * hashes / world, "traffic_source": "profiles/r01e_summary.md (ncu, per traced hash) x hashes per launch per GPU",
+                     "hbm": {"achieved_gbs": hashes * 132 * 96 / (ms * 1e-3) / 1e9, "peak_gbs": hbm * world}},
+    }
+
+
+def secondary_lookups(torch, eng, depth, dev, stream, steps):
+    """BASELINE config 5 inside the default run (one GPU): 2^20 low-leaf lookups on the depth-D indexed tree, their non-inclusion
+    witnesses through the host API, then batches of 4096 inserts with per-insert roots and both paths."""
+    import numpy as np
+    from imt_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    q, b = 1 << 20, 4096
+    n = 1 << depth
+    m = n - b * (steps + 3)
+    ec = eng if eng.fmt == 0 else None
+    import imt_b200
+    own = ec is None
+    if own:
+        ec = imt_b200.Engine(eng.device, "canonical")
+        ec.set_stream(stream.cuda_stream)
+    d_pre = synth.indexed_preimages_torch(n, m, device=dev)
+    tree = ec.build_from_leaves_dev(d_pre, n)
+    t0 = time.perf_counter()
+    assert tree.occupied == m
+    t_index = time.perf_counter() - t0
+    d_vals = synth.field_elements_torch(q, seed=555, device=dev)
+    d_low = torch.empty(q, dtype=torch.int64, device=dev)
+    d_match = torch.empty(q, dtype=torch.uint8, device=dev)
+    l0 = ec.launches
+    t_lookup = _ev_time(torch, stream, lambda: tree.low_leaf_lookup_dev(d_vals, q, d_low, d_match), steps, 2)
+    launches = (ec.launches - l0) // (steps + 2)
+    assert bool(d_match.all())
+    h_pre = d_pre.cpu().numpy().view(np.uint64)
+    h_vals = d_vals[:3].cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    for k in range(3):                                                           # the reference's literal scan (IMT:632-660), the oracle
+        assert (int(d_low[k]), True) == O.low_leaf(h_pre, h_vals[k])
+    cpu_lookup = 3 / (time.perf_counter() - t0)
+    bufs = tree.non_inclusion_buffers(q, depth, pinned=True)
+    h_q = torch.empty((q, 4), dtype=torch.int64, pin_memory=True)
+    h_q.copy_(d_vals)
+    hq = h_q.numpy().view(np.uint64)
+    tree.non_inclusion_paths(hq, out=bufs)
+    t0 = time.perf_counter()
+    o = tree.non_inclusion_paths(hq, out=bufs)
+    t_e2e = time.perf_counter() - t0
+    assert np.array_equal(o["low_idx"], d_low.cpu().numpy().astype(np.uint64))
+    ins_out = tree.insert_buffers(b, depth, pinned=True)
+    next_slot, ins = m, []
+    for s_ in range(steps + 2):
+        vals = synth.field_elements(b, seed=9000 + s_)
+        t0 = time.perf_counter()
+        w = tree.insert_batch(vals, first_idx=next_slot, out=ins_out)
+        ins.append(time.perf_counter() - t0)
+        next_slot += b
+    t_ins = sum(ins[2:]) / steps
+    assert np.array_equal(w["new_roots"][-1], tree.root())
+    # the whole insert_leaf witness trace of the last batch, one call, device resident
+    dw = {k: torch.from_numpy(np.ascontiguousarray(w[k]).view(np.int64) if w[k].dtype == np.uint64 else w[k]).to(dev)
+          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings")}
+    S = 3 + 4 * depth
+    d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
+    d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
+    t_wt = _ev_time(torch, stream, lambda: ec.trace_insert_witness_dev(dw, b, depth, next_slot - b, d_states, d_roots), 2, 1)
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
+    hbm = _peaks().get("hbm_gbs", 6650.0)
+    probes = max(1, m.bit_length())
+    out = {
+        "metric": "low_leaf_lookups_per_s", "value": q / (t_lookup * 1e-3), "unit": "lookups/s", "ms_per_step": t_lookup, "n_gpus": 1,
+        "config": {"workload": f"2^20 uniform random low-leaf lookups on the depth-{depth} indexed tree ({m} occupied), non-inclusion witnesses, "
+                               f"then {b}-insert batches with per-insert roots and paths", "queries": q, "occupied": m},
+        "e2e": {"value": q / t_e2e, "unit": "lookups/s", "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": q * 32,
+                "d2h_bytes_per_step": q * (8 + 1 + 96 + depth * 33 + 1), "call": "imt_non_inclusion_paths into reused page-locked buffers"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_low_leaf_lookup", "achieved": q * probes * 32 / (t_lookup * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": q * probes * 32 / (t_lookup * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "note": f"algorithmic bytes = {probes} dependent 32-byte probes per lookup (latency-bound gather)"},
+        "cpu_baseline": {"value": cpu_lookup, "unit": "lookups/s", "cores": 1, "kind": "port", "sample": "3 lookups by the reference's linear scan over the same preimages (oracle)"},
+        "insert": {"metric": "inserts_per_s", "value": b / t_ins, "unit": "inserts/s", "ms_per_batch": t_ins * 1e3, "batch": b,
+                   "hashes_per_s": 2 * b * (depth + 1) / t_ins, "call": "imt_insert_batch (host values in, witness bundle out into page-locked buffers)",
+                   "witness_trace": {"call": "imt_insert_witness_trace_dev", "hashes": b * S, "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3),
+                                     "bytes": b * S * 132 * 96}},
+        "index_build_s": t_index,
+    }
+    tree.close()
+    if own:
+        ec.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse()
@@ -539,6 +718,25 @@ def main():
         for _ in range(2):
             step_e2e_alloc()
         ms_e2e_alloc = (time.perf_counter() - t0) / 2 * 1e3
+    # the same call from PAGEABLE host memory (a Rust Vec<F> is plain malloc memory): the library copies straight from the
+    # caller's pointer chunk by chunk, the driver stages each chunk while the previous chunk's kernel runs
+    h_page = h_pre.numpy().copy()
+    def step_e2e_pageable():
+        if world > 1:
+            tree.sharded_rebuild_from_leaves_ptr(h_page.ctypes.data)
+        else:
+            tree.rebuild_from_leaves_ptr(h_page.ctypes.data)
+        tree.root_dev(send)
+        h_root.copy_(send, non_blocking=True)
+        stream.synchronize()
+    ms_e2e_pageable, _ = timed(step_e2e_pageable, max(2, a.steps // 2), 1)
+    ms_e2e_pageable /= max(2, a.steps // 2)
+    del h_page
+    # what a wrapper that creates a context per `IndexedMerkleTree::new` would add (INTEGRATION.md keeps ONE per process instead)
+    t0 = time.perf_counter()
+    tmp_eng = imt_b200.Engine(local_rank, "montgomery")
+    tmp_eng.close()
+    ctx_create_ms = (time.perf_counter() - t0) * 1e3
     root_hex = "".join(f"{int(x) & 0xFFFFFFFFFFFFFFFF:016x}" for x in reversed(h_root.tolist()))
     # the root of THIS input is pinned: tests/golden/golden.json "bench_roots" holds the CPU oracle's root of the same
     # Montgomery-interpreted synthetic stream (tests/golden/make_golden.py --bench-roots); every rank count must reproduce it
@@ -592,13 +790,37 @@ def main():
                    "fe_format": "montgomery"},
         "e2e": {"value": e2e, "unit": "hashes/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": n_total * 96,
                 "d2h_bytes_per_step": 32 * world, "call": ("imt_sharded_rebuild_from_leaves" if world > 1 else "imt_tree_rebuild_from_leaves") + " (host leaves -> existing tree) + root read back",
+                "pageable": {"value": hashes_per_step / (ms_e2e_pageable * 1e-3), "ms_per_step": ms_e2e_pageable,
+                             "note": "the same call with the leaves in plain malloc (pageable) memory, as a Rust Vec<F> is"},
+                "ctx_create_ms": ctx_create_ms,
                 "ms_per_step_with_alloc": ms_e2e_alloc,
                 "with_alloc_note": "wall clock of imt_tree_build_from_leaves + root + imt_tree_destroy per step (2.5 GiB of tree buffers recycled through the stream-ordered pool), N=1 only"},
         "gpu_launches": launches * world, "clocks": clocks, "roofline": roofline, "root": root_hex, "root_check": root_check,
         "collective": (f"ncclAllGather of {world} x 32 B issued inside libimt_b200.so (imt_sharded_rebuild_from_leaves*, NCCL {nccl_version})"
                        if world > 1 else None),
     }
+    # ---- BASELINE configs 4 and 5 as secondary legs of the same run (so that the driver's line carries them)
+    if not a.no_secondary:
+        sec = {}
+        try:
+            sec["paths"] = secondary_paths(torch, dist, eng, tree, d_pre, depth, n, world, rank, dev, stream, imad_rate, max(2, a.steps // 2))
+        except Exception as e:  # a secondary leg must never cost the headline line
+            sec["paths"] = {"error": repr(e)}
+        tree.close()
+        del d_pre, h_pre
+        torch.cuda.empty_cache()
+        eng.trim()
+        if world == 1:
+            try:
+                sec["lookups"] = secondary_lookups(torch, eng, depth, dev, stream, max(2, a.steps // 2))
+            except Exception as e:
+                sec["lookups"] = {"error": repr(e)}
+        else:
+            sec["lookups"] = {"skipped": "one-GPU leg (python bench.py --workload lookups); the sharded lookups / inserts are covered by tests and tools/multi_gpu_check.py"}
+        out["secondary"] = sec
     if rank == 0 and not a.no_cpu_baseline:
+        if "paths" in out.get("secondary", {}) and "error" not in out["secondary"]["paths"]:
+            out["secondary"]["paths"]["cpu_baseline"] = cpu_trace_rate()
         v, th, sample, _, _ = cpu_build_rate(a.cpu_seconds)
         out["cpu_baseline"] = {"value": v, "unit": "hashes/s", "cores": th, "kind": "port", "sample": sample,
                                "single_thread": dict(zip(("value", "sample"), cpu_single_thread_rate()))}

@@ -87,6 +87,11 @@ imt_status imt_poseidon_hash3(imt_ctx* ctx, const void* in, size_t n, void* out)
 imt_status imt_poseidon_hash2_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out);
 imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* d_in, size_t n, void* d_out);
 
+/* Dense field-element arrays between the two formats (canonical `to_repr()` bytes <-> halo2curves' in-memory Montgomery
+ * form), n elements; inputs >= p are rejected. Independent of the context's own format. */
+imt_status imt_fe_convert(imt_ctx* ctx, const void* in, size_t n, imt_fe_format from, imt_fe_format to, void* out);
+imt_status imt_fe_convert_dev(imt_ctx* ctx, const void* d_in, size_t n, imt_fe_format from, imt_fe_format to, void* d_out);
+
 /* Witness trace of `hash_fix_len_array` (src/indexed_merkle_tree.rs:92, 194, 271, 299): for each of the n hashes
  * of `arity` (2 or 3) inputs, the 132 x 3 FE states (per permutation: after the pre-constant add, then after the
  * linear layer of each of the 4 + 57 + 4 rounds) and the digest. states may be NULL. Other input lengths and

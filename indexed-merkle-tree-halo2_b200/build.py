@@ -8,10 +8,13 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimt_b200.so")
 SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "imt_latency.cu", "imt_comm.cu", "imt_io.cu", "poseidon_params.cpp"]
-# per-unit flags: the latency kernels are the same field source compiled with free carry chains (csrc/fr.cuh IMT_FREE_MASK;
-# all 32 masks were swept on a B200, tools/lab/latency_lab.cu: 29 = product rows (even chain), reduction rows, squarings)
-UNIT_FLAGS = {"imt_latency.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_LATENCY_FREE_MASK", "29")]}
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh", "poseidon_params.h"]
+# per-unit flags: which multiply-accumulate chains start without reading the carry flag (csrc/fr.cuh IMT_FREE_MASK). All 32 masks
+# were swept on a B200 for both kernel families (tools/lab/latency_lab.cu, profiles/r02_latency_lab.md):
+#   22 = odd product chains + even reduction chains + squarings free: the thread-per-hash kernels (-2.4 % time at full occupancy,
+#        -12 % on a 32768-node level) — more freedom (31) makes ptxas spill carry predicates, +8 %
+#   29 = the 3-lanes-per-hash latency kernels (one warp per scheduler): 283 -> 233 us per small level
+UNIT_FLAGS = {"imt_capi.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_THROUGHPUT_FREE_MASK", "22")],
+              "imt_latency.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_LATENCY_FREE_MASK", "29")]}
 OBJ_DIR = os.path.join(HERE, "build")
 
 

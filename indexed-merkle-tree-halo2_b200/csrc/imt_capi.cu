@@ -69,10 +69,6 @@ namespace {
 // lanes for latency. IMT_COOP_MAX_NODES overrides the threshold (tuning / A-B measurements only).
 constexpr size_t kCoopMaxNodesDefault = 8192;
 size_t coop_max_nodes();
-// Above that and up to this many hashes a batch is <= ~2 warps per scheduler of the thread-per-hash kernel: latency still
-// dominates, so the free-carry-chain build of the same kernel is used (IMT_LAT_MAX_NODES overrides; 0 disables).
-constexpr size_t kLatMaxNodesDefault = 32768;
-size_t lat_max_nodes();
 
 template <int ARITY>
 imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
@@ -86,8 +82,6 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
     }
     if (n <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh, imt_latency.cu)
         launch_hash_coop(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
-    else if (n <= lat_max_nodes())  // under ~2 warps per scheduler: the same thread-per-hash kernel built for latency (imt_latency.cu)
-        launch_hash_lat(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
     else
         k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
                                                                       ctx->d_err);
@@ -104,14 +98,6 @@ size_t coop_max_nodes() {
     static const size_t v = [] {
         const char* e = std::getenv("IMT_COOP_MAX_NODES");
         return e ? (size_t)std::strtoull(e, nullptr, 10) : kCoopMaxNodesDefault;
-    }();
-    return v;
-}
-
-size_t lat_max_nodes() {
-    static const size_t v = [] {
-        const char* e = std::getenv("IMT_LAT_MAX_NODES");
-        return e ? (size_t)std::strtoull(e, nullptr, 10) : kLatMaxNodesDefault;
     }();
     return v;
 }
@@ -327,30 +313,27 @@ extern "C" const char* imt_status_string(imt_status st) {
     return "unknown status";
 }
 
-// Every kernel family hashes the same inputs at context creation and must agree bit for bit: the throughput kernel, the
-// 3-lanes-per-hash kernel and the latency build of the thread-per-hash kernel are three compilations of one field source (two
-// carry disciplines), and a toolchain that mis-schedules one of them must not go unnoticed (0.7 ms, once per context).
+// Both kernel families hash the same inputs at context creation and must agree bit for bit: the thread-per-hash kernels and the
+// 3-lanes-per-hash kernels are two compilations of one field source under two carry disciplines (fr.cuh IMT_FREE_MASK), and a
+// toolchain that mis-schedules one of them must not go unnoticed (0.6 ms, once per context).
 static imt_status self_test(imt_ctx* ctx, const PoseidonParams& hp) {
     constexpr size_t kN = 8;
     DevBuf in(ctx), out(ctx);
     IMT_TRY_CUDA(ctx, in.alloc(3 * kN * sizeof(Fr)));
-    IMT_TRY_CUDA(ctx, out.alloc(6 * kN * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, out.alloc(4 * kN * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(in.p, &hp.partial[0], 3 * kN * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));  // canonical Montgomery values
     Fr* o = out.as<Fr>();
     IMT_TRY(clear_err(ctx));
     k_hash<2><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 0 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
     launch_hash_coop(ctx, 2, in.p, o + 1 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    launch_hash_lat(ctx, 2, in.p, o + 2 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    k_hash<3><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 3 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
-    launch_hash_coop(ctx, 3, in.p, o + 4 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    launch_hash_lat(ctx, 3, in.p, o + 5 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    Fr h[6 * kN];
+    k_hash<3><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 2 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
+    launch_hash_coop(ctx, 3, in.p, o + 3 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    Fr h[4 * kN];
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY(finish(ctx));
     for (int a = 0; a < 2; ++a)
-        for (int v = 1; v < 3; ++v)
-            if (std::memcmp(h + (3 * a) * kN, h + (3 * a + v) * kN, kN * sizeof(Fr)) != 0)
-                return fail(ctx, IMT_ERR_CUDA, "self-test failed: the latency kernels and the throughput kernel disagree (toolchain problem)");
+        if (std::memcmp(h + (2 * a) * kN, h + (2 * a + 1) * kN, kN * sizeof(Fr)) != 0)
+            return fail(ctx, IMT_ERR_CUDA, "self-test failed: the latency kernels and the throughput kernels disagree (toolchain problem)");
     return IMT_OK;
 }
 
@@ -492,6 +475,29 @@ extern "C" imt_status imt_poseidon_hash2(imt_ctx* ctx, const void* in, size_t n,
 extern "C" imt_status imt_poseidon_hash3(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_host<3>(ctx, in, n, out); }
 extern "C" imt_status imt_poseidon_hash2_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<2>(ctx, in, n, out); }
 extern "C" imt_status imt_poseidon_hash3_dev(imt_ctx* ctx, const void* in, size_t n, void* out) { return hash_dev<3>(ctx, in, n, out); }
+
+extern "C" imt_status imt_fe_convert_dev(imt_ctx* ctx, const void* d_in, size_t n, imt_fe_format from, imt_fe_format to, void* d_out) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if ((n && (!d_in || !d_out)) || (int)from < 0 || (int)from > 1 || (int)to < 0 || (int)to > 1) return fail(ctx, IMT_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(launch_convert(ctx, d_in, d_out, n, (int)from, (int)to));
+    return finish(ctx);
+}
+extern "C" imt_status imt_fe_convert(imt_ctx* ctx, const void* in, size_t n, imt_fe_format from, imt_fe_format to, void* out) {
+    if (!ctx) return IMT_ERR_INVALID_ARG;
+    if (n && (!in || !out)) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf d(ctx);
+    IMT_TRY_CUDA(ctx, d.alloc(n * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(d.p, in, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(imt_fe_convert_dev(ctx, d.p, n, from, to, d.p));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(out, d.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
 
 // n traced hashes on the compute stream: tuned kernels for this context's own instance and arity 2 / 3, any-width otherwise.
 // d_sbox (may be null) receives the extended S-box trace.
@@ -640,6 +646,8 @@ extern "C" void imt_tree_destroy(imt_tree* t) {
     if (t->d_sorted_slots) tree_free(ctx, t->d_sorted_slots);
     if (t->d_alt_keys) tree_free(ctx, t->d_alt_keys);
     if (t->d_alt_slots) tree_free(ctx, t->d_alt_slots);
+    if (t->d_prefix) tree_free(ctx, t->d_prefix);
+    if (t->d_top) tree_free(ctx, t->d_top);
     delete t;
 }
 

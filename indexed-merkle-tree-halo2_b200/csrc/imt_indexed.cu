@@ -192,6 +192,96 @@ __global__ void __launch_bounds__(256) k_low_leaf_lookup(const uint4* __restrict
     if (matched) matched[i] = hit;
 }
 
+// ---- the fast lookup. A binary search over m 32-byte keys is ~log2(m) DEPENDENT 32-byte sector reads per query (24 at depth
+// 24, half of them from DRAM: the key array is 512 MB). Instead:
+//   * prefix[i] = the top 64 bits of sorted key i: 8 bytes per key, four keys per sector, 128 MB at depth 24 (L2-sized);
+//   * top[kIndexTop] = the last prefix of each of kIndexTop equal blocks of the prefix array, staged in SHARED memory: the first
+//     12 levels of the search cost no global traffic at all;
+//   * the remaining log2(m / 4096) levels run on the prefix array inside one block of it (the last two share a sector);
+//   * the 32-byte keys are read only when a 64-bit prefix ties with the query's (a present value, or — 2^-40 per pair for
+//     random keys — a coincidence): ties are resolved on the full keys, long runs of equal prefixes by the plain binary search.
+// ~10 sector reads per query, mostly L2 hits, instead of ~26.
+constexpr unsigned kIndexTop = 4096;
+__device__ __forceinline__ unsigned long long key_prefix(const uint32_t* k) { return ((unsigned long long)k[7] << 32) | k[6]; }
+__global__ void __launch_bounds__(256) k_index_prefix(const uint4* __restrict__ keys, size_t m, unsigned long long* __restrict__ prefix) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint4 hi = __ldg(keys + 2 * i + 1);
+    prefix[i] = ((unsigned long long)hi.w << 32) | hi.z;
+}
+__global__ void __launch_bounds__(256) k_index_top(const unsigned long long* __restrict__ prefix, size_t m, size_t stride,
+                                                   unsigned long long* __restrict__ top) {
+    const size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (b >= kIndexTop) return;
+    const size_t first = b * stride;
+    top[b] = first < m ? prefix[(first + stride < m ? first + stride : m) - 1] : ~0ull;  // blocks past the end never match
+}
+// first j in [0, m) with keys[j] >= v, else m — through the shared-memory top and the prefix array
+__device__ __forceinline__ size_t lower_bound_fast(const uint4* __restrict__ keys, const unsigned long long* __restrict__ prefix,
+                                                   const unsigned long long* s_top, size_t stride, size_t m, const uint32_t* v) {
+    const unsigned long long pv = key_prefix(v);
+    unsigned lo = 0, hi = kIndexTop;  // first block whose last prefix is >= pv
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (s_top[mid] < pv) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo == kIndexTop) return m;
+    size_t a = (size_t)lo * stride, b = a + stride < m ? a + stride : m;
+    if (a >= m) return m;
+    while (a < b) {  // first index in the block with prefix >= pv (the block's last entry qualifies)
+        const size_t mid = a + ((b - a) >> 1);
+        if (__ldg(prefix + mid) < pv) a = mid + 1;
+        else b = mid;
+    }
+    // ties on the 64-bit prefix: decide on the full keys
+    for (int step = 0; step < 4; ++step) {
+        if (a >= m || __ldg(prefix + a) != pv) return a;
+        uint32_t k[8];
+        load_fe(k, keys + 2 * a);
+        if (cmp256(k, v) >= 0) return a;
+        ++a;
+    }
+    return lower_bound(keys, m, v);  // a long run of equal prefixes (adversarial keys): the plain search is always right
+}
+__global__ void __launch_bounds__(512) k_low_leaf_lookup_fast(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots,
+                                                              const unsigned long long* __restrict__ prefix,
+                                                              const unsigned long long* __restrict__ top, size_t stride, size_t m, size_t n,
+                                                              uint32_t head_next_zero, const uint4* __restrict__ values, size_t q, int fmt,
+                                                              uint64_t* __restrict__ low_idx, uint8_t* __restrict__ matched,
+                                                              uint32_t* __restrict__ err) {
+    __shared__ unsigned long long s_top[kIndexTop];
+    for (unsigned i = threadIdx.x; i < kIndexTop; i += blockDim.x) s_top[i] = top[i];
+    __syncthreads();
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    uint32_t v[8];
+    load_fe(v, values + 2 * i);
+    if (!to_int(v, fmt)) atomicOr(err, kErrNonCanonical);
+    uint64_t low = 0;
+    uint8_t hit = 0;
+    if (head_next_zero) {  // IMT:640
+        hit = 1;
+    } else {
+        const size_t j = lower_bound_fast(keys, prefix, s_top, stride, m, v);
+        bool present = false;
+        if (j < m && __ldg(prefix + j) == key_prefix(v)) {
+            uint32_t k[8];
+            load_fe(k, keys + 2 * j);
+            present = cmp256(k, v) == 0;
+        }
+        if (j >= 1 && !present) {
+            low = slots[j - 1];
+            hit = 1;
+        } else if (!zero256(v) && m < n) {
+            low = m;
+            hit = 1;
+        }
+    }
+    low_idx[i] = low;
+    if (matched) matched[i] = hit;
+}
+
 // Sharded lookup, per-rank half: the largest LOCAL key below v (as a canonical integer) with its GLOBAL slot.
 // flags bit 0: a candidate exists, bit 1: v itself is a local key.
 __global__ void __launch_bounds__(256) k_low_leaf_candidates(const uint4* __restrict__ keys, const uint32_t* __restrict__ slots, size_t m,
@@ -750,12 +840,47 @@ imt_status imt_host::ensure_index(imt_tree* t) {
     t->occupied = m;
     t->head_next_zero = (uint32_t)got[2] != 0;
     t->index_valid = true;
+    t->prefix_valid = false;
     return IMT_OK;
 }
 namespace {
 
+// the prefix array + its top samples, rebuilt when the sorted keys changed (one pass over the keys: ~0.1 ms at depth 24)
+imt_status ensure_prefix(imt_tree* t) {
+    imt_ctx* ctx = t->ctx;
+    if (t->prefix_valid) return IMT_OK;
+    if (t->prefix_capacity < t->index_capacity) {
+        if (t->d_prefix) tree_free(ctx, t->d_prefix), t->d_prefix = nullptr;
+        IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_prefix, t->index_capacity * sizeof(unsigned long long)));
+        t->prefix_capacity = t->index_capacity;
+    }
+    if (!t->d_top) IMT_TRY_CUDA(ctx, tree_malloc(ctx, (void**)&t->d_top, kIndexTop * sizeof(unsigned long long)));
+    const size_t m = t->occupied;
+    t->top_stride = (m + kIndexTop - 1) / kIndexTop;
+    if (t->top_stride == 0) t->top_stride = 1;
+    if (m) k_index_prefix<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, m, t->d_prefix);
+    k_index_top<<<grid_for(kIndexTop, 256), 256, 0, ctx->stream>>>(t->d_prefix, m, t->top_stride, t->d_top);
+    ctx->launches += 2;
+    IMT_TRY_CUDA(ctx, cudaGetLastError());
+    t->prefix_valid = true;
+    return IMT_OK;
+}
+
 imt_status lookup_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low, uint8_t* d_matched) {
     imt_ctx* ctx = t->ctx;
+    // small indices sit in L1 / L2 anyway: the plain search is as good. IMT_FAST_LOOKUP_MIN moves the threshold (tests force the fast
+    // path on small trees with 0; a huge value gives the plain search for A/B measurements); read per call, it is one getenv.
+    const char* env_min = std::getenv("IMT_FAST_LOOKUP_MIN");
+    const size_t fast_min = env_min ? (size_t)std::strtoull(env_min, nullptr, 10) : 65536;
+    if (t->occupied >= fast_min && t->occupied > 0) {
+        IMT_TRY(ensure_prefix(t));
+        k_low_leaf_lookup_fast<<<grid_for(q, 512), 512, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->d_prefix, t->d_top,
+                                                                          t->top_stride, t->occupied, t->n, t->head_next_zero ? 1u : 0u,
+                                                                          (const uint4*)d_values, q, ctx->fmt, d_low, d_matched, ctx->d_err);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+        return IMT_OK;
+    }
     k_low_leaf_lookup<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_sorted_keys, t->d_sorted_slots, t->occupied, t->n,
                                                                  t->head_next_zero ? 1u : 0u, (const uint4*)d_values, q, ctx->fmt, d_low,
                                                                  d_matched, ctx->d_err);
@@ -780,6 +905,7 @@ imt_status launch_limb_witness(imt_ctx* ctx, const void* d_low_leaves, const voi
 }
 void invalidate_index(imt_tree* t) {  // the buffers are kept for the next build of the index
     t->index_valid = false;
+    t->prefix_valid = false;
     t->occupied = 0;
 }
 }  // namespace imt_host
@@ -1006,6 +1132,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::swap(t->d_sorted_keys, t->d_alt_keys);  // the merged arrays become the index; the old ones the next merge target
         std::swap(t->d_sorted_slots, t->d_alt_slots);
+        t->prefix_valid = false;
         t->occupied += cb;
         t->head_next_zero = false;
         lap("merge");
@@ -1308,6 +1435,7 @@ extern "C" imt_status imt_shard_insert_apply(imt_tree* t, const uint64_t* x, con
         IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::swap(t->d_sorted_keys, t->d_alt_keys);
         std::swap(t->d_sorted_slots, t->d_alt_slots);
+        t->prefix_valid = false;
         t->occupied += nk;
     }
     if (t->rank == 0) t->head_next_zero = false;

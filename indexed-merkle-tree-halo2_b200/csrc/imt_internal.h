@@ -77,6 +77,12 @@ struct imt_tree {
     imt::Fr* d_alt_keys = nullptr;       // merge target of the next insert batch (allocated by the first one; the two
     uint32_t* d_alt_slots = nullptr;     // buffer pairs swap roles after every merge)
     bool head_next_zero = false;         // preimage[0].next_val == 0  (the reference's first-insert branch, IMT:640)
+    // search accelerator of the lookups (rebuilt lazily after the sorted keys change): the top 64 bits of every sorted key
+    // (8 B per key: four per 32-byte sector) and kIndexTop evenly spaced samples of those (staged in shared memory)
+    unsigned long long* d_prefix = nullptr;
+    unsigned long long* d_top = nullptr;
+    size_t prefix_capacity = 0, top_stride = 0;
+    bool prefix_valid = false;
 };
 
 namespace imt {
@@ -196,8 +202,6 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n);
 cudaError_t latency_upload_params(const imt::PoseidonParams* host_params);
 // 3 lanes per hash (poseidon_coop.cuh): batches of <= coop_max_nodes() hashes
 void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
-// one thread per hash, latency build: batches that leave the schedulers under-filled
-void launch_hash_lat(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
 void launch_fold_coop(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
                       unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);
 

@@ -159,6 +159,18 @@ class Engine:
         self._check(self._lib.imt_poseidon_hash(self._h, _ptr(a) if arity else None, arity, a.shape[0], _ptr(out)))
         return out
 
+    def convert(self, a, to_montgomery):
+        """dense FE array canonical <-> Montgomery (imt_fe_convert), independent of the engine's own format"""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        frm, to = (_ffi.FE_CANONICAL, _ffi.FE_MONTGOMERY) if to_montgomery else (_ffi.FE_MONTGOMERY, _ffi.FE_CANONICAL)
+        self._check(self._lib.imt_fe_convert(self._h, _ptr(a), a.size // 4, frm, to, _ptr(out)))
+        return out
+
+    def convert_dev(self, d_in, n, d_out, to_montgomery):
+        frm, to = (_ffi.FE_CANONICAL, _ffi.FE_MONTGOMERY) if to_montgomery else (_ffi.FE_MONTGOMERY, _ffi.FE_CANONICAL)
+        self._check(self._lib.imt_fe_convert_dev(self._h, _dev_ptr(d_in), n, frm, to, _dev_ptr(d_out)))
+
     def hash_dev(self, d_in, arity, n, d_out):
         self._check(self._lib.imt_poseidon_hash_dev(self._h, _dev_ptr(d_in), arity, n, _dev_ptr(d_out)))
 
@@ -311,6 +323,16 @@ class Engine:
                     new_low_leaf=states[:, d + 1], interim_path=states[:, d + 2:2 * d + 2], zero_path=states[:, 2 * d + 2:3 * d + 2],
                     new_leaf=states[:, 3 * d + 2], new_path=states[:, 3 * d + 3:4 * d + 3], old_root=roots[:, 0], interim_root=roots[:, 1],
                     zero_leaf_root=roots[:, 2], new_root=roots[:, 3], new_low_leaf_preimage=new_low)
+
+    def trace_insert_witness_dev(self, d_w, b, depth, first_idx, d_states=None, d_roots=None, d_new_low=None, d_limbs=None, d_flags=None):
+        """imt_insert_witness_trace_dev: everything on the device. d_w: dict with CUDA tensors low_leaves, low_idx, low_siblings,
+        new_leaves, new_siblings (the layouts Tree.insert_batch returns); outputs are CUDA tensors or None."""
+        cw = _ffi.InsertWitness()
+        for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings"):
+            setattr(cw, k, _dev_ptr(d_w[k]).value)
+        opt = lambda t: _dev_ptr(t) if t is not None else None
+        self._check(self._lib.imt_insert_witness_trace_dev(self._h, ctypes.byref(cw), b, depth, int(first_idx), opt(d_states), opt(d_roots),
+                                                           opt(d_new_low), opt(d_limbs), opt(d_flags)))
 
     def non_inclusion_limbs(self, low_leaves, new_vals):
         """128-bit limb witnesses of verify_non_inclusion (indexed_merkle_tree.rs:143-172, 206-222): (b, 6, 4) FE in the

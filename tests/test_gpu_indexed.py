@@ -519,3 +519,97 @@ def test_insert_batch_chunk_boundary_and_single_inserts(eng, monkeypatch):
     low, matched = tree.low_leaf_lookup(np.stack([vals[7], synth.field_elements(1, seed=47)[0]]))   # present value, full tree
     assert (int(low[0]), bool(matched[0])) == O.low_leaf(st.pre, vals[7]) == (0, False)
     assert (int(low[1]), bool(matched[1])) == O.low_leaf(st.pre, synth.field_elements(1, seed=47)[0])
+
+
+def test_insert_witness_trace_depth24_batch_4096_sampled_against_the_oracle(eng_mont):
+    """imt_insert_witness_trace at the size BASELINE config 5 names: 4096 inserts into the depth-24 tree = 405 504 traced
+    hashes (5.1 GB of states, kept on the device). Sampled (insert, slot) pairs are recomputed by the oracle from the
+    witnesses alone: fold with O.hash_trace up to the sampled level, compare all 132 x 3 states."""
+    import torch
+    depth, b = 24, 4096
+    n = 1 << depth
+    m = n - 3 * b
+    dev = torch.device("cuda", 0)
+    d_pre = synth.indexed_preimages_torch(n, m, device=dev)                    # canonical integers
+    e = eng_mont
+    d_pre_m = torch.empty_like(d_pre)
+    e.convert_dev(d_pre, 3 * n, d_pre_m, to_montgomery=True)
+    del d_pre
+    tree = e.build_from_leaves_dev(d_pre_m, n)
+    vals = to_mont(synth.field_elements(b, seed=4242))
+    w = tree.insert_batch(vals, m)
+    dw = {k: torch.from_numpy(np.ascontiguousarray(w[k]).view(np.int64) if w[k].dtype == np.uint64 else w[k]).to(dev)
+          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings")}
+    S = 3 + 4 * depth
+    d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
+    d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
+    e.trace_insert_witness_dev(dw, b, depth, m, d_states, d_roots)
+    roots = d_roots.cpu().numpy().view(np.uint64)
+    assert np.array_equal(roots[:, 0], w["old_roots"]) and np.array_equal(roots[:, 3], w["new_roots"])
+    assert np.array_equal(roots[:, 1], roots[:, 2])                            # both routes to the interim root (IMT:277-294)
+    assert np.array_equal(roots[1:, 0], roots[:-1, 3])                         # insert k starts where k - 1 ended
+    rng = np.random.default_rng(7)
+    for k in [0, b - 1] + [int(x) for x in rng.integers(0, b, 6)]:
+        low, new = from_mont(w["low_leaves"][k]), from_mont(w["new_leaves"][k])
+        new_low = np.stack([low[0], new[0], O.fe(m + k)])
+        lsib, nsib = from_mont(w["low_siblings"][k]), from_mont(w["new_siblings"][k])
+        got = d_states[k].cpu().numpy().view(np.uint64)
+        folds = ((low, int(w["low_idx"][k]), lsib, 0, 1), (new_low, int(w["low_idx"][k]), lsib, depth + 1, depth + 2),
+                 (np.zeros((3, 4), np.uint64), m + k, nsib, None, 2 * depth + 2), (new, m + k, nsib, 3 * depth + 2, 3 * depth + 3))
+        for leaf, idx, sib, leaf_slot, path_slot in folds:
+            h, ws = O.hash_trace(leaf)
+            if leaf_slot is not None:
+                assert np.array_equal(from_mont(got[leaf_slot].reshape(-1, 4)).reshape(132, 3, 4), ws), (k, leaf_slot)
+            sample = set(int(x) for x in rng.integers(0, depth, 3)) | {0, depth - 1}
+            for lvl in range(depth):
+                pair = np.stack([h, sib[lvl]]) if idx % 2 == 0 else np.stack([sib[lvl], h])
+                if lvl in sample:
+                    h, ws = O.hash_trace(pair)
+                    assert np.array_equal(from_mont(got[path_slot + lvl].reshape(-1, 4)).reshape(132, 3, 4), ws), (k, path_slot, lvl)
+                else:
+                    h = O.hash2(pair.reshape(1, 2, 4), 1)[0]
+                idx //= 2
+
+
+def test_fast_lookup_equals_plain_search_and_the_linear_scan(monkeypatch):
+    """The prefix / shared-memory-top lookup (k_low_leaf_lookup_fast) against the plain binary search and the oracle's literal
+    scan (IMT:632-660) — on random keys, on queries equal to keys, and on ADVERSARIAL keys: long runs that share their top 64
+    bits (ties are resolved on the full keys), keys that differ only in the top limb, the smallest and largest values."""
+    e = imt_b200.Engine(0, "canonical")
+    rng = random.Random(99)
+    n = 1 << 12
+    C = (0x1234567890ABCDEF >> 2) << 192                                           # one top-64-bit prefix ...
+    run = [C + (i << 64) + rng.getrandbits(60) for i in range(300)]                # ... shared by 300 keys
+    top_only = [(k << 224) + 5 for k in range(1, 200)]                             # differ only in the top limb
+    others = [rng.randrange(1, P) for _ in range(2000)] + [1, 2, P - 1, P - 2]
+    vals = sorted(set(run + top_only + others))
+    m = len(vals) + 1
+    order = list(range(1, m))
+    rng.shuffle(order)                                                             # slots in random (insertion) order
+    slot_of = {v: s for v, s in zip(vals, order)}
+    pre = np.zeros((n, 3, 4), np.uint64)
+    chain = [0] + vals
+    for a, b in zip(chain, chain[1:] + [None]):
+        s = slot_of.get(a, 0)
+        pre[s, 0] = O.fe(a)
+        if b is not None:
+            pre[s, 1], pre[s, 2] = O.fe(b), O.fe(slot_of[b])
+    queries = ([v for v in run[::7]] + [v + 1 for v in run[::5]] + [v - 1 for v in run[::5]] + [C - 1, C + (301 << 64), C + (1 << 63)]
+               + top_only[::9] + [v + 1 for v in top_only[::9]] + [0, 1, 2, 3, P - 1, P - 2, P - 3] + [rng.randrange(P) for _ in range(1500)])
+    qv = O.fes(queries)
+    want = [O.low_leaf(pre, qv[k]) for k in range(len(queries))]
+    for fast_min in ("0", "1000000000"):                                           # the fast kernel, then the plain one
+        monkeypatch.setenv("IMT_FAST_LOOKUP_MIN", fast_min)
+        tree = e.build_from_leaves(pre)
+        low, matched = tree.low_leaf_lookup(qv)
+        for k in range(len(queries)):
+            assert (int(low[k]) if matched[k] else 0, bool(matched[k])) == (want[k][0] if want[k][1] else 0, want[k][1]), (fast_min, k, hex(queries[k]))
+        new = O.fes([C + (i << 64) + (1 << 62) for i in range(0, 300, 3)])        # inserts INTO the run: the prefix array is rebuilt
+        tree.insert_batch(new)
+        low2, matched2 = tree.low_leaf_lookup(qv)
+        cur = tree.preimages(n)
+        for k in range(0, len(queries), 11):
+            w = O.low_leaf(cur, qv[k])
+            assert (int(low2[k]) if matched2[k] else 0, bool(matched2[k])) == (w[0] if w[1] else 0, w[1]), (fast_min, k)
+        tree.close()
+    e.close()

@@ -304,7 +304,7 @@ def test_subtree_sharding_reassembles_the_single_tree(eng, world):
         assert np.array_equal(sib, wsib) and np.array_equal(hel, whel)
         with pytest.raises(imt_b200.ImtError):
             s.get_proofs(np.array([((r + 1) % world) * per], np.uint64))
-    assert imt_b200.fe_to_int(whole.root()) == int(GOLD["build_roots"]["10"]["indexed"])
+    assert np.array_equal(whole.root(), O.build_from_preimages(pre, 4))     # (seed 11: not the golden file's default-seed tree)
 
 
 def test_depth16_roots_match_golden(eng):
@@ -346,3 +346,33 @@ def test_depth24_roots_match_golden(eng):
     t.rebuild_from_leaves_dev(d_pre)
     assert imt_b200.fe_to_int(t.root()) == int(GOLD["build_roots"]["24"]["indexed"])
     assert t.occupied == n
+
+
+def test_verify_rejects_a_root_encoded_as_root_plus_p(eng):
+    """a root given as root + p (still < 2^256) must not fold onto its canonical twin: every verify path — the
+    3-lanes-per-path kernel (q <= 8192), the thread-per-path kernel (q > 8192) and the any-width kernels — reports
+    IMT_ERR_NON_CANONICAL, as the header promises for every input >= p."""
+    from imt_b200 import _ffi
+    n, depth = 64, 6
+    pre = synth.indexed_preimages(n, 40, seed=3)
+    tree = eng.build_from_leaves(pre)
+    root = tree.root()
+    bad_root = imt_b200.fe_from_int(imt_b200.fe_to_int(root) + imt_b200.P)
+    assert imt_b200.fe_to_int(bad_root) < (1 << 256)
+    leaves = eng.hash3(pre)
+    for q in (1, 9000):
+        idx = (np.arange(q) % n).astype(np.uint64)
+        sib, _ = tree.get_proofs(idx)
+        assert eng.verify_proofs(leaves[idx], idx, root, sib).all()
+        with pytest.raises(imt_b200.ImtError) as ei:
+            eng.verify_proofs(leaves[idx], idx, bad_root, sib)
+        assert ei.value.status == _ffi.ERR_NON_CANONICAL
+    g = imt_b200.Engine(0, "canonical", generic=True)
+    gt = g.build_from_leaves(pre)
+    idx = np.array([5], np.uint64)
+    sib, _ = gt.get_proofs(idx)
+    assert g.verify_proofs(leaves[idx], idx, root, sib).all()
+    with pytest.raises(imt_b200.ImtError) as ei:
+        g.verify_proofs(leaves[idx], idx, bad_root, sib)
+    assert ei.value.status == _ffi.ERR_NON_CANONICAL
+    g.close()

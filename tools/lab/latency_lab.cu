@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -57,6 +58,19 @@ __global__ void k_chain(const uint4* __restrict__ in, uint4* __restrict__ out, l
     const long long t1 = clock64();
     store_fe(out + 2 * threadIdx.x, x);
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// ---------------------------------------------------------------------------------- one thread per hash (k_hash of the library)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_hash_tph(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+    const size_t i = blockIdx.x * (size_t)128 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[2][8], d[8];
+    load_fe(x[0], in + 2 * (2 * i));
+    load_fe(x[1], in + 2 * (2 * i + 1));
+    NoTrace nt;
+    hash_fixed<2>(d, x, c_params, nt);
+    store_fe(out + 2 * i, d);
 }
 
 // ---------------------------------------------------------------------------------- radix-2^29 carry-free multiplication
@@ -424,6 +438,35 @@ int main() {
             if (rep && ms < best) best = ms;
         }
         std::printf("n = %6zu  %9.1f us\n", n, best * 1e3);
+    }
+    // ---- one thread per hash at the sizes of the middle levels (occupancy hint 7 = the library's throughput kernel, 1 = none)
+    std::printf("## thread-per-hash kernel: microseconds per level  (launch bounds 128 x 7 | 128 x 1)\n");
+    {
+        const size_t big = (size_t)1 << 22;
+        Fr *b_in, *b_out;
+        CK(cudaMalloc(&b_in, 2 * big * sizeof(Fr)));
+        CK(cudaMalloc(&b_out, big * sizeof(Fr)));
+        for (size_t off = 0; off < 2 * big; off += h_in.size())
+            CK(cudaMemcpy(b_in + off, h_in.data(), std::min(h_in.size(), 2 * big - off) * sizeof(Fr), cudaMemcpyHostToDevice));
+        for (size_t n : {(size_t)4096, (size_t)8192, (size_t)16384, (size_t)32768, (size_t)65536, (size_t)131072, (size_t)262144, (size_t)1 << 22}) {
+            float best7 = 1e9f, best1 = 1e9f;
+            for (int rep = 0; rep < 5; ++rep) {
+                float ms;
+                CK(cudaEventRecord(e0));
+                k_hash_tph<7><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep && ms < best7) best7 = ms;
+                CK(cudaEventRecord(e0));
+                k_hash_tph<1><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep && ms < best1) best1 = ms;
+            }
+            std::printf("n = %6zu  %9.1f us | %9.1f us\n", n, best7 * 1e3, best1 * 1e3);
+        }
     }
     // ---- second generation: 4 lanes per hash, 3 slots per partial round (poseidon_quad.cuh); must give the same digests
     QuadAux* d_aux;

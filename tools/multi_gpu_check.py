@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """NCCL check of the sharded path, run under torchrun on an N-GPU box:
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py [depth]
-Every rank builds its subtree on its own GPU, the roots cross NVLink in one ncclAllGather, and the sharded tree is
-compared with (a) the single-GPU tree of the same leaves built on rank 0's GPU and (b) the CPU oracle."""
+Every rank builds its subtree on its own GPU; every exchange (the root all-gather, the lookup candidates, the insert rounds) is
+issued by libimt_b200.so's own NCCL communicator (csrc/imt_comm.cu) — torch.distributed only launches the ranks and carries the
+128-byte NCCL id. The sharded tree is compared with (a) the single-GPU tree of the same leaves built on this rank's GPU and
+(b) the CPU oracle."""
 import os
 import random
 import sys
@@ -53,14 +55,15 @@ def main():
     assert np.array_equal(own_states, want_states), "owner-sharded traces differ from the fold traces"
     # sharded insert batch == the single-GPU insert batch of the same tree, field by field
     vals = synth.field_elements(min(3000, n - occupied), seed=99)
-    got = st.insert_batch(vals, chunk=1024)
+    got = st.insert_batch(vals)
     want = whole.insert_batch(vals)
     for k in want:
         assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), f"sharded insert: {k}"
     assert np.array_equal(st.root(), whole.root())
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU check ok: world={world} depth={depth} root={imt_b200.fe_to_int(st.root()):#x}", flush=True)
+        print(f"multi-GPU check ok: world={world} depth={depth} root={imt_b200.fe_to_int(st.root()):#x} "
+              f"(library communicator: rank/world/NCCL {eng.comm_info()})", flush=True)
     dist.destroy_process_group()
 
 
