@@ -10,15 +10,19 @@ namespace imt {
 
 // out[i] = H(in[ARITY*i .. ARITY*i + ARITY)). in_fmt/out_fmt select canonical <-> Montgomery conversion at the
 // edges; tree levels are Montgomery on both sides.
-// Occupancy hint of the throughput kernels: 7 blocks of 128 threads per SM = 72 registers per thread and 7 warps per
-// scheduler (with 48-96 bytes of spill) instead of the 92 registers / 5 warps ptxas picks on its own. Swept on the depth-24
-// build: 1 -> 62.0, 6 -> 62.4, 7 -> 62.8, 8 -> 61.9 M hashes/s; 64-thread blocks x 14 -> 62.7.
+// Occupancy hint of the throughput kernels: 7 (node levels) / 6 (leaf hashing) blocks of 128 threads per SM = 72 / 80 registers per
+// thread instead of the 84 / 92 ptxas picks on its own. Round 1 (serial carry chains) swept 1 / 6 / 7 / 8 on the depth-24 build: 7 was
+// best for both. With carry mask 22 (round 2) the leaf kernel prefers 6: 2^22 leaves 66.7 ms at 7, 64.5 ms at 6, 65.9 ms at 5; the node
+// kernel stays at 7 (tools/lab/latency_lab.cu, profiles/r02_latency_lab.md).
 #ifndef IMT_HASH_MIN_BLOCKS
 #define IMT_HASH_MIN_BLOCKS 7
 #endif
+#ifndef IMT_HASH_MIN_BLOCKS_LEAF
+#define IMT_HASH_MIN_BLOCKS_LEAF 6
+#endif
 template <int ARITY>
-__global__ void __launch_bounds__(kHashThreads, IMT_HASH_MIN_BLOCKS) k_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n,
-                                                       int in_fmt, int out_fmt, uint32_t* __restrict__ err) {
+__global__ void __launch_bounds__(kHashThreads, ARITY == 3 ? IMT_HASH_MIN_BLOCKS_LEAF : IMT_HASH_MIN_BLOCKS)
+    k_hash(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n, int in_fmt, int out_fmt, uint32_t* __restrict__ err) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= n) return;
     uint32_t x[ARITY][8], d[8];

@@ -111,6 +111,51 @@ int main(void) {
     if (imt_trace_fe_per_hash(ctx5, 6, &fe_per_hash) != IMT_OK) return 1;
     printf("trace_fe %zu\n", fe_per_hash);
     imt_ctx_destroy(ctx5);
+    /* checkpoint: save, inspect the header without a device, load into a fresh tree, same root and preimages */
+    CHECK(imt_tree_build_from_leaves(ctx, pre, 8, &tree));
+    CHECK(imt_tree_occupied(tree, &occupied));
+    CHECK(imt_insert_batch(tree, vals, 6, occupied, &w));
+    const char* path = "/tmp/imt_b200_cabi_driver.ckpt";
+    CHECK(imt_tree_save(tree, path));
+    imt_checkpoint_info info;
+    CHECK(imt_checkpoint_read_info(path, &info));
+    imt_tree* back = NULL;
+    CHECK(imt_tree_load(ctx, path, &back));
+    uint64_t root2[4], pre_a[8 * 12], pre_b[8 * 12];
+    CHECK(imt_tree_root(tree, root));
+    CHECK(imt_tree_root(back, root2));
+    CHECK(imt_tree_preimages(tree, pre_a));
+    CHECK(imt_tree_preimages(back, pre_b));
+    printf("checkpoint n %" PRIu64 " depth %u same_root %d same_leaves %d header_root %d\n", info.num_leaves, info.depth,
+           memcmp(root, root2, 32) == 0, memcmp(pre_a, pre_b, sizeof pre_a) == 0, memcmp(info.root, root, 32) == 0);
+    FILE* f = fopen(path, "r+b"); /* flip one bit of leaf 2: the load must refuse the file */
+    if (!f) return 1;
+    fseek(f, 64 + 96 * 2, SEEK_SET);
+    int c = fgetc(f);
+    fseek(f, 64 + 96 * 2, SEEK_SET);
+    fputc(c ^ 1, f);
+    fclose(f);
+    imt_tree* corrupt = NULL;
+    st = imt_tree_load(ctx, path, &corrupt);
+    printf("corrupt checkpoint: %d %s\n", (int)st, imt_last_error(ctx));
+    remove(path);
+    imt_tree_destroy(back);
+    /* the whole insert_leaf witness trace of the batch in one call: 3 + 4 x depth hashes per insert (IMT:253-313) */
+    static uint64_t tr_states[6 * 15 * 132 * 3 * 4];
+    uint64_t tr_roots[6 * 4 * 4], tr_newlow[6 * 12], tr_limbs[6 * 6 * 4];
+    uint8_t tr_flags[6 * 3];
+    CHECK(imt_insert_witness_trace(ctx, &w, 6, 3, occupied, tr_states, tr_roots, tr_newlow, tr_limbs, tr_flags));
+    int trace_ok = imt_insert_trace_hashes(3) == 15;
+    for (int i = 0; i < 6; ++i) {
+        trace_ok &= memcmp(tr_roots + 16 * i, old_roots + 4 * i, 32) == 0;            /* fold of the low leaf        -> old root */
+        trace_ok &= memcmp(tr_roots + 16 * i + 4, tr_roots + 16 * i + 8, 32) == 0;    /* both routes to the interim root */
+        trace_ok &= memcmp(tr_roots + 16 * i + 12, new_roots + 4 * i, 32) == 0;       /* fold of the new leaf        -> new root */
+        /* the last state of the last hash of the insert's trace holds the new root in element 1 */
+        trace_ok &= memcmp(tr_states + ((((size_t)i * 15 + 14) * 132 + 131) * 3 + 1) * 4, new_roots + 4 * i, 32) == 0;
+        trace_ok &= tr_flags[3 * i + 2] == 1;
+    }
+    printf("insert_trace_ok %d\n", trace_ok);
+    imt_tree_destroy(tree);
     imt_ctx_destroy(ctx);
     return 0;
 }

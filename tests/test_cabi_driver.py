@@ -59,3 +59,6 @@ def test_c_client_runs_the_reference_scenario():
     assert fe(lines[19]) == int(GOLD["spec"]["published_perm_x5_254_5_input_0_to_4"][0], 16)   # published Poseidon test vector
     assert fe(lines[20]) == int(GOLD["spec"]["hashes"]["5,8,60"]["6"])
     assert lines[21] == f"trace_fe {(6 // 4 + 1) * (1 + 8 + 60) * 5}"
+    assert lines[22] == "checkpoint n 8 depth 3 same_root 1 same_leaves 1 header_root 1"
+    assert lines[23].startswith("corrupt checkpoint: 6 ") and "corrupt" in lines[23]      # IMT_ERR_INVALID_ARG, root mismatch
+    assert lines[24] == "insert_trace_ok 1"

@@ -73,6 +73,21 @@ __global__ void __launch_bounds__(128, MINB) k_hash_tph(const uint4* __restrict_
     store_fe(out + 2 * i, d);
 }
 
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_hash3_tph(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+    const size_t i = blockIdx.x * (size_t)128 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[3][8], d[8];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        load_fe(x[j], in + 2 * (3 * i + j));
+        (void)ingest(x[j], kFmtMontgomery);
+    }
+    NoTrace nt;
+    hash_fixed<3>(d, x, c_params, nt);
+    store_fe(out + 2 * i, d);
+}
+
 // ---------------------------------------------------------------------------------- radix-2^29 carry-free multiplication
 // 9 limbs of 29 bits (R = 2^261). Column sums are plain 64-bit accumulators: no carry flag anywhere, so every multiply-add of
 // a row is independent of its neighbours. 81 + 81 + 9 multiplies instead of 64 + 64 + 8, but no carry bookkeeping.
@@ -468,6 +483,64 @@ int main() {
             std::printf("n = %6zu  %9.1f us | %9.1f us\n", n, best7 * 1e3, best1 * 1e3);
         }
     }
+#ifdef LAB_LEAF
+    {   // the leaf kernel of the build: H3 of 2^22 preimages, one thread per hash, launch bounds 128 x 7 (the library's) and 128 x 6
+        const size_t n = (size_t)1 << 22;
+        Fr *b_in, *b_out;
+        CK(cudaMalloc(&b_in, 3 * n * sizeof(Fr)));
+        CK(cudaMalloc(&b_out, n * sizeof(Fr)));
+        for (size_t off = 0; off < 3 * n; off += h_in.size())
+            CK(cudaMemcpy(b_in + off, h_in.data(), std::min(h_in.size(), 3 * n - off) * sizeof(Fr), cudaMemcpyHostToDevice));
+        float best7 = 1e9f, best6 = 1e9f;
+        for (int rep = 0; rep < 4; ++rep) {
+            float ms;
+            CK(cudaEventRecord(e0));
+            k_hash3_tph<7><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < best7) best7 = ms;
+            CK(cudaEventRecord(e0));
+            k_hash3_tph<6><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < best6) best6 = ms;
+        }
+        std::printf("## leaf kernel H3, n = 2^22: %9.1f us (128 x 7) | %9.1f us (128 x 6)\n", best7 * 1e3, best6 * 1e3);
+        float n6 = 1e9f, n5 = 1e9f, l5 = 1e9f, n8 = 1e9f;
+        for (int rep = 0; rep < 4; ++rep) {
+            float ms;
+            CK(cudaEventRecord(e0));
+            k_hash_tph<6><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < n6) n6 = ms;
+            CK(cudaEventRecord(e0));
+            k_hash_tph<5><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < n5) n5 = ms;
+            CK(cudaEventRecord(e0));
+            k_hash_tph<8><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < n8) n8 = ms;
+            CK(cudaEventRecord(e0));
+            k_hash3_tph<5><<<(unsigned)((n + 127) / 128), 128>>>((const uint4*)b_in, (uint4*)b_out, n);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep && ms < l5) l5 = ms;
+        }
+        std::printf("## node kernel H2, n = 2^22: %9.1f us (128 x 8) | %9.1f us (128 x 6) | %9.1f us (128 x 5);  leaf 128 x 5: %9.1f us\n", n8 * 1e3, n6 * 1e3, n5 * 1e3, l5 * 1e3);
+        CK(cudaFree(b_in));
+        CK(cudaFree(b_out));
+    }
+#endif
     // ---- second generation: 4 lanes per hash, 3 slots per partial round (poseidon_quad.cuh); must give the same digests
     QuadAux* d_aux;
     CK(cudaMalloc(&d_aux, sizeof(QuadAux)));
