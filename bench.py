@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="build", choices=["build", "paths", "lookups"],
                     help="build = the headline metric (default); paths = 2^16 path extraction + witness traces (BASELINE config 4); "
-                         "lookups = 1M low-leaf lookups + non-inclusion paths + 4096 inserts (config 5). Single GPU.")
+                         "lookups = 1M low-leaf lookups + non-inclusion paths + 4096 inserts (config 5, one GPU). "
+                         "paths with --gpus N > 1 (torchrun) = the traces sharded by leaf owner over the N-GPU sharded tree.")
     ap.add_argument("--queries", type=int, default=0, help="query count of the paths / lookups workloads (default 2^16 / 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -592,13 +593,47 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     return out
 
 
+def run_paths_sharded(a):
+    """--workload paths --gpus N (torchrun): the depth-D tree sharded by subtree, 2^16 paths + witness traces sharded by leaf owner,
+    every rank draining its traces over its own PCIe link; aggregate rates, max time over ranks. One JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    import imt_b200
+    from imt_b200 import synth
+    from imt_b200.sharding import attach_communicator
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    eng = imt_b200.Engine(local_rank, "montgomery")
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    attach_communicator(eng)
+    n = (1 << a.depth) // world
+    d_pre = synth.field_elements_torch(3 * n, synth.DEFAULT_SEED, first=3 * n * rank, device=dev).view(n, 3, 4)
+    tree = eng.sharded_build_from_leaves_dev(d_pre, n)
+    imad_rate, _ = eng.calibrate_imad(150.0)
+    out = secondary_paths(torch, dist, eng, tree, d_pre, a.depth, n, world, rank, dev, stream, imad_rate, a.steps)
+    out.update({"steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery",
+                "data": "synthetic"})
+    if rank == 0:
+        out["cpu_baseline"] = cpu_trace_rate()
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
-    if a.workload == "paths":
+    if a.workload == "paths" and a.gpus == 1:
         return run_paths(a)
+    if a.workload == "paths":
+        return run_paths_sharded(a)
     if a.workload == "lookups":
         return run_lookups(a)
 

@@ -67,9 +67,9 @@ uint64_t imt_ctx_launch_count(const imt_ctx* ctx);
  * the CUDA legacy default stream. imt_ctx_reset_stream returns to the internal stream. */
 imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream);
 imt_status imt_ctx_reset_stream(imt_ctx* ctx);
-/* Scratch buffers of the calls below are stream-ordered allocations from the device's default memory pool, which this
- * library keeps cached between calls (a depth-24 trace call can leave ~5 GB there). imt_ctx_trim returns the cached,
- * unused part to the driver — for processes that share the GPU with another allocator. */
+/* Tree and scratch buffers are stream-ordered allocations from a memory pool that belongs to the context (the device's default
+ * pool is not touched); freed memory stays cached there between calls (a depth-24 trace call can leave ~5 GB). imt_ctx_trim
+ * returns the cached, unused part to the driver — for processes that share the GPU with another allocator. */
 imt_status imt_ctx_trim(imt_ctx* ctx);
 /* Per-kernel device timing: when enabled every hash launch is bracketed by CUDA events on its stream.
  * imt_ctx_kernel_time returns, for hash kernels of the given arity (2 = node levels, 3 = leaf hashing), the summed
@@ -219,7 +219,9 @@ imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q,
  *   new_roots FE, new_leaves 3 FE, new_siblings depth FE + new_helpers (NEW tree), is_largest u8.
  * first_idx must equal imt_tree_occupied(). The batch is validated first (IMT_ERR_INVALID_ARG for a value that is 0,
  * already in the tree or repeated; IMT_ERR_TREE_FULL): on a validation error nothing is modified. The tree, its
- * preimages and its sorted index are updated in place. */
+ * preimages and its sorted index are updated in place, chunk by chunk (up to 65536 inserts each): a CUDA / allocation
+ * failure (IMT_ERR_CUDA) in a later chunk leaves the earlier chunks applied — imt_tree_occupied() tells how far the
+ * tree got, and the witnesses of those inserts are valid. */
 typedef struct imt_insert_witness {
     void* old_roots;
     uint64_t* low_idx;

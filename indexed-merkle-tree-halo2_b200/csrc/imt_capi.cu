@@ -350,11 +350,15 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     static std::once_flag params_once;
     std::call_once(params_once, [] { poseidon_params_generate(&host_params); });
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) {  // scratch buffers come from the default pool: keep freed memory cached instead of returning it to the OS
-        cudaMemPool_t pool;
-        e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e == cudaSuccess) {  // a private pool for every buffer of this context: freed memory stays cached in it, nobody else's pool is touched
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        e = cudaMemPoolCreate(&ctx->pool, &props);
         unsigned long long keep = ~0ull;
-        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
@@ -386,6 +390,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     drain_timing(ctx);
+    cudaDeviceSynchronize();  // stream-ordered frees of this context's buffers complete before its pool goes away
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -394,6 +399,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (ctx->d_spec) cudaFree(ctx->d_spec);
     if (ctx->d_zero_leaf) cudaFree(ctx->d_zero_leaf);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -417,9 +423,7 @@ extern "C" imt_status imt_ctx_trim(imt_ctx* ctx) {
     if (!ctx) return IMT_ERR_INVALID_ARG;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaMemPool_t pool;
-    IMT_TRY_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-    IMT_TRY_CUDA(ctx, cudaMemPoolTrimTo(pool, 0));
+    IMT_TRY_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
     return IMT_OK;
 }
 extern "C" imt_status imt_ctx_enable_timing(imt_ctx* ctx, int enabled) {

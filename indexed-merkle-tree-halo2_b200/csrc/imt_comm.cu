@@ -172,7 +172,11 @@ imt_status copy_all_gather(imt_group* g, const std::vector<const void*>& send, c
         IMT_TRY_CUDA_G(g, cudaSetDevice(g->ctxs[i]->device));
         for (size_t j = 0; j < n; ++j) {
             if (j != i) IMT_TRY_CUDA_G(g, cudaStreamWaitEvent(g->ctxs[i]->stream, g->ready[j], 0));
-            IMT_TRY_CUDA_G(g, cudaMemcpyAsync((char*)recv[i] + (size_t)g->ranks[j] * bytes, send[j], bytes, cudaMemcpyDefault, g->ctxs[i]->stream));
+            char* dst = (char*)recv[i] + (size_t)g->ranks[j] * bytes;
+            if (g->ctxs[i]->device == g->ctxs[j]->device)
+                IMT_TRY_CUDA_G(g, cudaMemcpyAsync(dst, send[j], bytes, cudaMemcpyDeviceToDevice, g->ctxs[i]->stream));
+            else  // explicit peer copy: pool memory of another device is not addressable through the unified-addressing default kind
+                IMT_TRY_CUDA_G(g, cudaMemcpyPeerAsync(dst, g->ctxs[i]->device, send[j], g->ctxs[j]->device, bytes, g->ctxs[i]->stream));
         }
         IMT_TRY_CUDA_G(g, cudaEventRecord(g->done[i], g->ctxs[i]->stream));
     }
@@ -486,6 +490,12 @@ extern "C" imt_status imt_multi_create(const int* devices, unsigned n_dev, imt_f
                     cudaSetDevice(devices[i]);
                     cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
                     if (e != cudaSuccess) cudaGetLastError();  // already enabled
+                    // ... and the buffers of context j (its private pool) become addressable from device i
+                    cudaMemAccessDesc desc = {};
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = devices[i];
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    if (cudaMemPoolSetAccess(g->ctxs[j]->pool, &desc, 1) != cudaSuccess) cudaGetLastError();
                 }
             }
     }

@@ -27,6 +27,8 @@ struct imt_ctx {
     cudaStream_t copy_stream = nullptr;  // host<->device staging, overlapped with compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: consecutive chunk kernels of a pipelined call alternate between
                                          // `stream` and this one so that chunk k+1 fills the SMs while chunk k drains
+    cudaMemPool_t pool = nullptr;        // this context's OWN stream-ordered pool: every tree and scratch buffer comes from it (its release
+                                         // threshold is raised so that calls recycle memory; the device's default pool is left alone)
     uint32_t* d_err = nullptr;           // device error bits, see kErr*
     uint32_t* h_err = nullptr;           // pinned mirror
     imt::PoseidonParams* d_params = nullptr;  // global-memory copy of the parameters (lane-dependent reads of the cooperative kernel)
@@ -129,19 +131,21 @@ inline imt_status fail(imt_ctx* ctx, imt_status st, const char* what) {
     return st;
 }
 
-// RAII device scratch buffer, stream-ordered: cudaMallocAsync / cudaFreeAsync on the context's compute stream from
-// the device's default memory pool (imt_ctx_create raises its release threshold, so steady-state calls recycle memory
-// instead of paying a synchronous cudaMalloc / cudaFree per buffer — those cost ~100 ms per insert batch at depth 24).
+// RAII device scratch buffer, stream-ordered: cudaMallocFromPoolAsync / cudaFreeAsync on the context's compute stream from
+// the context's own memory pool (imt_ctx_create raises ITS release threshold, so steady-state calls recycle memory
+// instead of paying a synchronous cudaMalloc / cudaFree per buffer — those cost ~100 ms per insert batch at depth 24 —
+// while other users of the device's default pool, e.g. torch's cudaMallocAsync backend, are not affected).
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
-    explicit DevBuf(imt_ctx* ctx) : s(ctx->stream) {}
+    cudaMemPool_t pool = nullptr;
+    explicit DevBuf(imt_ctx* ctx) : s(ctx->stream), pool(ctx->pool) {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() {
         if (p) cudaFreeAsync(p, s);
     }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, s); }
     template <class T>
     T* as() { return static_cast<T*>(p); }
 };
@@ -163,7 +167,7 @@ struct Event {
 // the reference's `IndexedMerkleTree::new` to build + destroy per call recycles memory instead of paying cudaMalloc /
 // cudaFree of 2.5 GiB (133 ms per depth-24 tree, measured).
 inline cudaError_t tree_malloc(imt_ctx* ctx, void** p, size_t bytes) {
-    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // usable from the copy stream right away
     return e;
 }

@@ -376,3 +376,36 @@ def test_verify_rejects_a_root_encoded_as_root_plus_p(eng):
         g.verify_proofs(leaves[idx], idx, bad_root, sib)
     assert ei.value.status == _ffi.ERR_NON_CANONICAL
     g.close()
+
+
+def test_trace_2p16_paths_of_the_depth20_tree_sampled_against_the_oracle(eng):
+    """BASELINE config 4 at its depth-20 size: the verify_merkle_proof witness traces of 2^16 uniform random paths of the
+    1M-leaf tree (16.6 GB of states, kept on the device), 64 sampled paths checked state by state against the oracle, which
+    builds the whole tree itself (leaf hashes, levels, paths) and traces every hash of the fold."""
+    import torch
+    depth, q = 20, 1 << 16
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, n - 1000, seed=20)
+    th = O.max_threads()
+    levels = O.tree_build(O.hash3(pre, th), th)
+    tree = eng.build_from_leaves(pre)
+    assert np.array_equal(tree.root(), levels[-1])
+    rng = np.random.default_rng(16)
+    idx = rng.integers(0, n, q).astype(np.uint64)
+    dev = torch.device("cuda", 0)
+    d_idx = torch.from_numpy(idx.view(np.int64)).to(dev)
+    d_states = torch.empty((q, depth, 132, 3, 4), dtype=torch.int64, device=dev)
+    tree.trace_proofs_dev(d_idx, q, d_states)
+    d_root = torch.from_numpy(levels[-1].view(np.int64).copy()).to(dev)
+    assert bool((d_states[:, -1, -1, 1] == d_root).all())                     # every one of the 65 536 folds ends in the root
+    for k in [0, q - 1] + [int(x) for x in rng.integers(0, q, 62)]:
+        i = int(idx[k])
+        sib, _ = O.get_proof(levels, n, i)
+        h = O.hash3(pre[i:i + 1], 1)[0]
+        got = d_states[k].cpu().numpy().view(np.uint64)
+        for lvl in range(depth):
+            pair = np.stack([h, sib[lvl]]) if i % 2 == 0 else np.stack([sib[lvl], h])
+            h, ws = O.hash_trace(pair)
+            assert np.array_equal(got[lvl], ws), (k, lvl)
+            i //= 2
+    tree.close()
