@@ -34,6 +34,7 @@ clients: $(LIB)
 	@mkdir -p tests/_build
 	gcc -std=c99 -Wall -Wextra -Werror -O1 -Iinclude tests/cabi_driver.c -o tests/_build/cabi_driver -L$(PKG) -limt_b200 -Wl,-rpath,$(abspath $(PKG))
 	g++ -std=c++17 -Wall -Wextra -Werror -O1 -Iinclude tests/reference_tests.cpp -o tests/_build/reference_tests -L$(PKG) -limt_b200 -Wl,-rpath,$(abspath $(PKG))
+	gcc -std=c99 -Wall -Wextra -Werror -O1 -Iinclude tests/cabi_multi_driver.c -o tests/_build/cabi_multi_driver -L$(PKG) -limt_b200 -Wl,-rpath,$(abspath $(PKG))
 
 oracle:
 	$(MAKE) -C oracle

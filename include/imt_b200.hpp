@@ -271,6 +271,35 @@ class IndexedMerkleTree {
         if (b) root_ = w.new_roots.back();
         return w;
     }
+    // The Poseidon witness of everything insert_leaf hashes for a batch (IMT:253-313), one call: [b][3 + 4 depth][states per
+    // hash][T] Fr flattened, in the chip's call order; `roots` (optional) receives old / interim / interim / new per insert.
+    // `first_idx` = the slot of the batch's first insert (occupied() before insert_batch).
+    std::vector<Fr> trace_insert_witness(const InsertWitness& w, size_t first_idx, std::vector<std::array<Fr, 4>>* roots = nullptr) const {
+        const size_t b = w.low_idx.size(), d = depth();
+        size_t fe = 0;
+        detail::check(ctx_, imt_trace_fe_per_hash(ctx_, 2, &fe));
+        std::vector<Fr> ls(b * d), ns(b * d), states(b * imt_insert_trace_hashes((unsigned)d) * fe);
+        for (size_t i = 0; i < b; ++i)
+            for (size_t k = 0; k < d; ++k) ls[i * d + k] = w.low_proof[i][k], ns[i * d + k] = w.new_proof[i][k];
+        imt_insert_witness cw{};
+        cw.low_idx = const_cast<uint64_t*>(w.low_idx.data());
+        cw.low_leaves = const_cast<IndexedMerkleTreeLeaf*>(w.low_leaves.data());
+        cw.new_leaves = const_cast<IndexedMerkleTreeLeaf*>(w.new_leaves.data());
+        cw.low_siblings = ls.data();
+        cw.new_siblings = ns.data();
+        if (roots) roots->resize(b);
+        detail::check(ctx_, imt_insert_witness_trace(ctx_, &cw, b, (unsigned)d, first_idx, states.data(), roots ? roots->data() : nullptr, nullptr,
+                                                     nullptr, nullptr));
+        return states;
+    }
+    // checkpoint: the leaves as the reference's serde derive orders them (utils.rs:12-17), canonical 32-byte LE, + root
+    void save(const std::string& path) const { detail::check(ctx_, imt_tree_save(tree_.get(), path.c_str())); }
+    static Result<IndexedMerkleTree> load(Poseidon<T, RATE>& hash, const std::string& path) {
+        imt_tree* t = nullptr;
+        const imt_status st = imt_tree_load(hash.ctx(), path.c_str(), &t);
+        detail::check(hash.ctx(), st);
+        return wrap(hash, t, st, imt_tree_num_leaves(t));
+    }
     // witness of verify_merkle_proof (IMT:65-96) for leaves of this tree: [q][depth][states per hash][T] Fr, flattened
     std::vector<Fr> trace_proofs(const std::vector<uint64_t>& indices) const {
         size_t fe = 0;
@@ -300,6 +329,76 @@ class IndexedMerkleTree {
     imt_ctx* ctx_ = nullptr;   // borrowed from the hasher, which must outlive the tree (the reference's lifetime 'a, utils.rs:5-7)
     std::unique_ptr<imt_tree, TreeDeleter> tree_;
     size_t n_ = 0;
+    Fr root_;
+};
+
+// IndexedMerkleTree::new over ALL the GPUs of the box in one call (include/imt_b200.h, "multi-GPU inside the library"): one
+// process, one thread; the tree is sharded by subtree, the subtree roots cross NVLink in one ncclAllGather issued by the
+// library, every query addresses the global tree. <3, 2>(8, 57) only (the instance the reference instantiates, IMT:362-365).
+class MultiGpu {
+  public:
+    explicit MultiGpu(const std::vector<int>& devices) {
+        imt_multi* m = nullptr;
+        if (imt_multi_create(devices.data(), (unsigned)devices.size(), IMT_FE_CANONICAL, &m) != IMT_OK)
+            throw NoDevice("imt_multi_create failed: no CUDA devices (there is no CPU fallback), not a power of two of them, or no NCCL");
+        m_.reset(m);
+    }
+    imt_multi* get() const { return m_.get(); }
+    unsigned size() const { return imt_multi_size(m_.get()); }
+
+  private:
+    struct Deleter {
+        void operator()(imt_multi* m) const { imt_multi_destroy(m); }
+    };
+    std::unique_ptr<imt_multi, Deleter> m_;
+};
+
+class ShardedIndexedMerkleTree {
+  public:
+    static Result<ShardedIndexedMerkleTree> from_preimages(MultiGpu& gpus, const std::vector<IndexedMerkleTreeLeaf>& leaves) {
+        imt_mtree* t = nullptr;
+        const imt_status st = imt_multi_build_from_leaves(gpus.get(), leaves.data(), leaves.size(), &t);
+        if (st == IMT_ERR_EMPTY) return Result<ShardedIndexedMerkleTree>::err("Cannot create Merkle Tree with no leaves");   // utils.rs:25
+        if (st == IMT_ERR_ODD) return Result<ShardedIndexedMerkleTree>::err("Leaves must be even");                           // utils.rs:35
+        if (st != IMT_OK) throw Error(st, imt_multi_last_error(gpus.get()));
+        ShardedIndexedMerkleTree tr;
+        tr.gpus_ = gpus.get();
+        tr.tree_.reset(t);
+        tr.check(imt_mtree_root(t, &tr.root_));
+        return Result<ShardedIndexedMerkleTree>::ok(std::move(tr));
+    }
+    ShardedIndexedMerkleTree(ShardedIndexedMerkleTree&&) = default;
+    ShardedIndexedMerkleTree& operator=(ShardedIndexedMerkleTree&&) = default;
+    Fr get_root() const { return root_; }                                              // utils.rs:59-61
+    size_t depth() const { return imt_mtree_depth(tree_.get()); }
+    std::pair<std::vector<Fr>, std::vector<Fr>> get_proof(size_t index) const {        // utils.rs:63-85
+        if (index >= imt_mtree_num_leaves(tree_.get())) throw std::out_of_range("index out of bounds");
+        const size_t d = depth();
+        std::vector<Fr> sib(d), hel(d);
+        std::vector<uint8_t> h8(d);
+        const uint64_t idx = index;
+        check(imt_mtree_get_proofs(tree_.get(), &idx, 1, sib.data(), h8.data()));
+        for (size_t k = 0; k < d; ++k) hel[k] = Fr::from(h8[k]);
+        return {std::move(sib), std::move(hel)};
+    }
+    std::vector<uint64_t> low_leaf_lookup(const std::vector<Fr>& values) const {
+        std::vector<uint64_t> low(values.size());
+        std::vector<uint8_t> matched(values.size());
+        check(imt_mtree_low_leaf_lookup(tree_.get(), values.data(), values.size(), low.data(), matched.data()));
+        return low;
+    }
+    void save(const std::string& path) const { check(imt_mtree_save(tree_.get(), path.c_str())); }
+
+  private:
+    struct Deleter {
+        void operator()(imt_mtree* t) const { imt_mtree_destroy(t); }
+    };
+    void check(imt_status st) const {
+        if (st != IMT_OK) throw Error(st, imt_multi_last_error(gpus_));
+    }
+    ShardedIndexedMerkleTree() = default;
+    imt_multi* gpus_ = nullptr;
+    std::unique_ptr<imt_mtree, Deleter> tree_;
     Fr root_;
 };
 

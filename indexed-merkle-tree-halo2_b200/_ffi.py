@@ -166,11 +166,14 @@ def load(build_if_stale=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_stale and _build.stale():
-        _build.build()
-    if not os.path.exists(_build.LIB):
-        raise RuntimeError(f"{_build.LIB} is missing and could not be built; the CUDA library is required (no CPU fallback)")
-    lib = ctypes.CDLL(_build.LIB)
+    path = os.environ.get("IMT_B200_LIB")  # A/B measurements of another build of the same library; normally unset
+    if not path:
+        if build_if_stale and _build.stale():
+            _build.build()
+        path = _build.LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and could not be built; the CUDA library is required (no CPU fallback)")
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = the header and the library disagree
         fn.restype = res

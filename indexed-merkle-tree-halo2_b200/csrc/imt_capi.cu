@@ -70,8 +70,10 @@ namespace {
 constexpr size_t kCoopMaxNodesDefault = 8192;
 size_t coop_max_nodes();
 
+// `concurrent`: how many launches of this size run side by side on different streams (the two half-trees of a deep build): what
+// decides between the latency and the throughput kernel is the number of hashes in flight, not the size of one launch
 template <int ARITY>
-imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s, unsigned concurrent = 1) {
     if (n == 0) return IMT_OK;
     if (ctx->generic) return launch_spec_hash(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, nullptr, s);  // imt_ctx_create_spec
     imt_ctx::Timed tm{nullptr, nullptr, ARITY, n};
@@ -80,7 +82,7 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
         IMT_TRY_CUDA(ctx, cudaEventCreate(&tm.b));
         IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
     }
-    if (n <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh, imt_latency.cu)
+    if (n * concurrent <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh, imt_latency.cu)
         launch_hash_coop(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
     else
         k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
@@ -103,8 +105,9 @@ size_t coop_max_nodes() {
 }
 
 // one tree level, Montgomery in / out: dst[i] = H(src[2i], src[2i+1])
-imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes, cudaStream_t s = nullptr, bool on_stream = false) {
-    return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, on_stream ? s : ctx->stream);
+imt_status launch_level_impl(imt_ctx* ctx, const Fr* src, Fr* dst, size_t nodes, cudaStream_t s = nullptr, bool on_stream = false,
+                             unsigned concurrent = 1) {
+    return launch_hash_t<2>(ctx, src, dst, nodes, kFmtMontgomery, kFmtMontgomery, on_stream ? s : ctx->stream, concurrent);
 }
 
 // all levels above level 0 (which must already hold the Montgomery leaf hashes).
@@ -132,7 +135,7 @@ imt_status build_upper_levels(imt_tree* t) {
         const size_t in_half = t->n >> (l + 1), out_half = t->n >> (l + 2);  // nodes of one half at level l / l + 1
         for (size_t h = 0; h < 2 && st == IMT_OK; ++h)
             st = launch_level_impl(ctx, t->d_levels + level_offset(t->n, l) + h * in_half, t->d_levels + level_offset(t->n, l + 1) + h * out_half,
-                                   out_half, lanes[h], true);
+                                   out_half, lanes[h], true, 2);
     }
     if (st != IMT_OK) {  // do not leave work behind on the auxiliary stream
         cudaStreamSynchronize(ctx->aux_stream);

@@ -187,6 +187,34 @@ static void test_other_instance() {
     REQUIRE(rejected);
 }
 
+// round 2: the checkpoint, the one-call insert_leaf witness trace and `IndexedMerkleTree::new` over several GPUs through the mirror
+static void test_checkpoint_trace_and_multi_gpu() {
+    auto h = Poseidon<T, RATE>::new_(8, 57);
+    std::vector<IndexedMerkleTreeLeaf> leaves(16);
+    auto tree = IndexedMerkleTree<T, RATE>::from_preimages(h, leaves).unwrap();
+    const size_t first = tree.occupied();
+    auto w = tree.insert_batch({Fr::from(30), Fr::from(10), Fr::from(20)});
+    std::vector<std::array<Fr, 4>> roots;
+    auto states = tree.trace_insert_witness(w, first, &roots);
+    REQUIRE(states.size() == 3 * (3 + 4 * 4) * 132 * 3);
+    for (size_t i = 0; i < 3; ++i) REQUIRE(roots[i][0] == w.old_roots[i] && roots[i][1] == roots[i][2] && roots[i][3] == w.new_roots[i]);
+    REQUIRE(states[((2 * 19 + 18) * 132 + 131) * 3 + 1] == tree.get_root());      // last state of the last hash: the new root
+    const std::string path = "/tmp/imt_b200_reference_tests.ckpt";
+    tree.save(path);
+    auto back = IndexedMerkleTree<T, RATE>::load(h, path).unwrap();
+    REQUIRE(back.get_root() == tree.get_root() && back.occupied() == tree.occupied());
+    // the same file into a tree sharded over two "devices" (device 0 twice on a one-GPU box: copies instead of NCCL)
+    MultiGpu gpus({0, 0});
+    auto sharded = ShardedIndexedMerkleTree::from_preimages(gpus, tree.preimages()).unwrap();
+    REQUIRE(sharded.get_root() == tree.get_root() && sharded.depth() == 4);
+    auto [p1, h1] = tree.get_proof(9);
+    auto [p2, h2] = sharded.get_proof(9);
+    REQUIRE(p1 == p2 && h1 == h2);
+    REQUIRE(sharded.low_leaf_lookup({Fr::from(25), Fr::from(5)}) == tree.low_leaf_lookup({Fr::from(25), Fr::from(5)}));
+    std::remove(path.c_str());
+    std::printf("checkpoint, insert witness trace and multi-GPU tree ok\n");
+}
+
 int main() {
     try {
         test_hash_zero();
@@ -198,6 +226,7 @@ int main() {
     test_insert_leaf_multiple_round();
     test_new_errors();
     test_other_instance();
+    test_checkpoint_trace_and_multi_gpu();
     std::printf("all reference tests passed\n");
     return 0;
 }

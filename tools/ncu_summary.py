@@ -74,7 +74,16 @@ def launches(tag, md):
     md.append("")
 
 
-def full(tag, md, suffix="k_hash", title="Top kernels"):
+SECTOR_KEYS = [
+    ("lts__t_sectors_op_read.sum", "L2 sectors read"), ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 sectors read for L1"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "L1 sectors, global loads"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum", "L1 sectors hit, global loads"),
+    ("dram__sectors_read.sum", "DRAM sectors read"), ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("smsp__inst_executed_op_shared_ld.sum", "shared-memory load instructions"),
+]
+
+
+def full(tag, md, suffix="k_hash", title="Top kernels", sectors=False):
     rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{suffix}.ncu-rep")
     if not os.path.exists(rep):
         return
@@ -83,7 +92,7 @@ def full(tag, md, suffix="k_hash", title="Top kernels"):
     md.append(f"## {title}, `ncu --set full --clock-control none --import-source on` ({tag}_{suffix}.ncu-rep)\n")
     for r in rows[2:]:
         md.append(f"### `{r[hdr.index('Kernel Name')][:60]}`\n\n| metric | value |\n|---|---:|")
-        for key, label in KEYS:
+        for key, label in KEYS + (SECTOR_KEYS if sectors else []):
             if key in hdr and "nan" not in r[hdr.index(key)]:
                 i = hdr.index(key)
                 md.append(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
@@ -130,6 +139,8 @@ def main():
     full(tag, md, "k_coop", "Cooperative kernel (3 lanes per hash): levels of 8192, 4096, ... nodes")
     full(tag, md, "k_trace", "Witness-trace fold (k_fold_paths with the state sink): 2^14 paths of the depth-20 tree")
     full(tag, md, "k_tree_trace", "Witness traces from the resident tree (k_trace_tree_paths): 2^14 paths of the depth-20 tree, one thread per (query, level)")
+    full(tag, md, "k_lookup", "Low-leaf lookup, prefix array + shared-memory top (k_low_leaf_lookup_fast): 2^20 queries, depth-24 index", sectors=True)
+    full(tag, md, "k_lookup_plain", "Low-leaf lookup, plain binary search over the 32-byte keys (k_low_leaf_lookup): the same queries", sectors=True)
     os.makedirs(OUT, exist_ok=True)
     out = os.path.join(OUT, f"{tag}_summary.md")
     open(out, "w").write("\n".join(md) + "\n")
