@@ -562,11 +562,18 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     assert np.array_equal(w["new_roots"][-1], tree.root())
     # the whole insert_leaf witness trace of the last batch, one call, device resident
     dw = {k: torch.from_numpy(np.ascontiguousarray(w[k]).view(np.int64) if w[k].dtype == np.uint64 else w[k]).to(dev)
-          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings")}
+          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings", "fold_nodes")}
     S = 3 + 4 * depth
     d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
     d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
+    # one launch: the chain values of the four folds came with the insert batch (imt_insert_witness::fold_nodes)
     t_wt = _ev_time(torch, stream, lambda: ec.trace_insert_witness_dev(dw, b, depth, next_slot - b, d_states, d_roots), 2, 1)
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
+    sample_one = d_states[:: max(1, b // 64)].clone()
+    # without them: 1 + depth dependent launches of 4b traced hashes (hash latency)
+    dw_loop = {k: v for k, v in dw.items() if k != "fold_nodes"}
+    t_wt_loop = _ev_time(torch, stream, lambda: ec.trace_insert_witness_dev(dw_loop, b, depth, next_slot - b, d_states, d_roots), 2, 1)
+    assert torch.equal(sample_one, d_states[:: max(1, b // 64)]), "one-launch trace != level-loop trace"
     assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
     hbm = _peaks().get("hbm_gbs", 6650.0)
     probes = max(1, m.bit_length())
@@ -583,8 +590,10 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
         "cpu_baseline": {"value": cpu_lookup, "unit": "lookups/s", "cores": 1, "kind": "port", "sample": "3 lookups by the reference's linear scan over the same preimages (oracle)"},
         "insert": {"metric": "inserts_per_s", "value": b / t_ins, "unit": "inserts/s", "ms_per_batch": t_ins * 1e3, "batch": b,
                    "hashes_per_s": 2 * b * (depth + 1) / t_ins, "call": "imt_insert_batch (host values in, witness bundle out into page-locked buffers)",
-                   "witness_trace": {"call": "imt_insert_witness_trace_dev", "hashes": b * S, "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3),
-                                     "bytes": b * S * 132 * 96}},
+                   "witness_trace": {"call": "imt_insert_witness_trace_dev with fold_nodes (one launch of independent traced hashes)", "hashes": b * S,
+                                     "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3), "bytes": b * S * 132 * 96,
+                                     "level_loop": {"ms": t_wt_loop, "hashes_per_s": b * S / (t_wt_loop * 1e-3),
+                                                    "note": "the same call without fold_nodes: 1 + depth dependent launches"}}},
         "index_build_s": t_index,
     }
     tree.close()

@@ -216,7 +216,11 @@ imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q,
  * (src/indexed_merkle_tree.rs:710-741) — computed with O(depth) hashes per insert instead of a full re-hash and
  * rebuild. Insert i puts new_vals[i] into slot first_idx + i. Outputs (any may be NULL), per insert:
  *   old_roots FE, low_idx u64, low_leaves 3 FE (OLD preimage), low_siblings depth FE + low_helpers (OLD tree),
- *   new_roots FE, new_leaves 3 FE, new_siblings depth FE + new_helpers (NEW tree), is_largest u8.
+ *   new_roots FE, new_leaves 3 FE, new_siblings depth FE + new_helpers (NEW tree), is_largest u8,
+ *   fold_nodes 4 x depth FE = the chain values of the four folds insert_leaf constrains (:196-204, 277-294, 305-313), levels
+ *   0 .. depth-1 each: [0] the low leaf's path BEFORE the insert (level 0 = H3(low leaf)), [1] the same path after the low
+ *   leaf was rewired, [2] the new leaf's path before the new leaf is written (level 0 = the stored empty leaf), [3] after.
+ *   They cost nothing extra here (the batch computes them anyway) and turn imt_insert_witness_trace into one launch.
  * first_idx must equal imt_tree_occupied(). The batch is validated first (IMT_ERR_INVALID_ARG for a value that is 0,
  * already in the tree or repeated; IMT_ERR_TREE_FULL): on a validation error nothing is modified. The tree, its
  * preimages and its sorted index are updated in place, chunk by chunk (up to 65536 inserts each): a CUDA / allocation
@@ -233,6 +237,7 @@ typedef struct imt_insert_witness {
     void* new_siblings;
     uint8_t* new_helpers;
     uint8_t* is_largest;
+    void* fold_nodes;
 } imt_insert_witness;
 imt_status imt_insert_batch(imt_tree* tree, const void* new_vals, size_t b, uint64_t first_idx, imt_insert_witness* w);
 
@@ -254,8 +259,11 @@ imt_status imt_non_inclusion_limbs(imt_ctx* ctx, const void* low_leaves, const v
  * low_idx, low_siblings, new_leaves, new_siblings must be set; the rest of `w` is not read) and the slot of its first insert.
  * Outputs (any may be NULL): states[b][3 + 4 depth][132][3] FE; roots[b][4] FE = the roots the four folds end in (old,
  * interim, interim again via the empty leaf, new); new_low_leaves[b][3] FE = the rewired low leaf's preimage; limbs[b][6] FE +
- * limb_flags[b][3] = imt_non_inclusion_limbs of (low leaf, new value). On the device the four folds of all inserts advance
- * level by level, one traced launch of 4b hashes per level — no serial traced fold. The _dev variant takes DEVICE pointers in
+ * limb_flags[b][3] = imt_non_inclusion_limbs of (low leaf, new value). With w->fold_nodes (as imt_insert_batch returned them)
+ * every operand of every hash is known up front and ALL b x (3 + 4 depth) traced hashes run as independent threads of one
+ * launch (the multiply-pipe rate of the trace kernel); every digest is compared with the next chain value, so fold_nodes that
+ * do not belong to these witnesses give IMT_ERR_INVALID_ARG, never a silently inconsistent trace. Without fold_nodes the four folds of all inserts advance level by level, one traced launch
+ * of 4b hashes per level (1 + depth dependent launches: hash latency for small b). The _dev variant takes DEVICE pointers in
  * `w` and for every output. Default instance only (any-width contexts: compose imt_poseidon_trace / imt_trace_merkle_proofs). */
 size_t imt_insert_trace_hashes(unsigned depth); /* 3 + 4 depth */
 imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_witness* w, size_t b, unsigned depth, uint64_t first_idx, void* states,

@@ -158,6 +158,7 @@ struct InsertWitness {
     std::vector<std::vector<Fr>> low_proof, new_proof;          // siblings bottom-up
     std::vector<std::vector<Fr>> low_proof_helper, new_proof_helper;  // Fr::one() when the node is LEFT (utils.rs:70, 79)
     std::vector<bool> is_new_leaf_largest;                      // IMT:736-741
+    std::vector<Fr> fold_nodes;  // [b][4][depth]: chain values of the four folds insert_leaf constrains (imt_b200.h); lets trace_insert_witness run as one launch
 };
 
 template <size_t T, size_t RATE>
@@ -257,8 +258,9 @@ class IndexedMerkleTree {
         w.old_roots.resize(b), w.new_roots.resize(b), w.low_idx.resize(b), w.low_leaves.resize(b), w.new_leaves.resize(b);
         std::vector<Fr> ls(b * d), ns(b * d);
         std::vector<uint8_t> lh(b * d), nh(b * d), lg(b);
+        w.fold_nodes.resize(b * 4 * d);
         imt_insert_witness cw{w.old_roots.data(), w.low_idx.data(), w.low_leaves.data(), ls.data(), lh.data(),
-                              w.new_roots.data(), w.new_leaves.data(), ns.data(), nh.data(), lg.data()};
+                              w.new_roots.data(), w.new_leaves.data(), ns.data(), nh.data(), lg.data(), w.fold_nodes.data()};
         detail::check(ctx_, imt_insert_batch(tree_.get(), new_vals.data(), b, occupied(), &cw));
         for (size_t i = 0; i < b; ++i) {
             w.low_proof.emplace_back(ls.begin() + i * d, ls.begin() + (i + 1) * d);
@@ -287,6 +289,7 @@ class IndexedMerkleTree {
         cw.new_leaves = const_cast<IndexedMerkleTreeLeaf*>(w.new_leaves.data());
         cw.low_siblings = ls.data();
         cw.new_siblings = ns.data();
+        if (w.fold_nodes.size() == b * 4 * d && d) cw.fold_nodes = const_cast<Fr*>(w.fold_nodes.data());
         if (roots) roots->resize(b);
         detail::check(ctx_, imt_insert_witness_trace(ctx_, &cw, b, (unsigned)d, first_idx, states.data(), roots ? roots->data() : nullptr, nullptr,
                                                      nullptr, nullptr));

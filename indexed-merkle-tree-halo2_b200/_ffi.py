@@ -19,7 +19,7 @@ FE_CANONICAL, FE_MONTGOMERY = 0, 1
 class InsertWitness(ctypes.Structure):
     _fields_ = [("old_roots", c_void_p), ("low_idx", c_void_p), ("low_leaves", c_void_p), ("low_siblings", c_void_p),
                 ("low_helpers", c_void_p), ("new_roots", c_void_p), ("new_leaves", c_void_p), ("new_siblings", c_void_p),
-                ("new_helpers", c_void_p), ("is_largest", c_void_p)]
+                ("new_helpers", c_void_p), ("is_largest", c_void_p), ("fold_nodes", c_void_p)]
 
 
 # every symbol include/imt_b200.h declares: name -> (restype, argtypes)

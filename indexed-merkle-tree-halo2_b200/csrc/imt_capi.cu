@@ -46,6 +46,7 @@ imt_status finish(imt_ctx* ctx) {
     if (e & kErrNonCanonical) return fail(ctx, IMT_ERR_NON_CANONICAL, "input field element >= p");
     if (e & kErrNotWellFormed) return fail(ctx, IMT_ERR_NOT_WELL_FORMED, imt_status_string(IMT_ERR_NOT_WELL_FORMED));
     if (e & kErrBadInsert) return fail(ctx, IMT_ERR_INVALID_ARG, "insert value is zero, already in the tree, or repeated in the batch");
+    if (e & kErrBadFold) return fail(ctx, IMT_ERR_INVALID_ARG, "fold_nodes are not the chain values of these insert witnesses");
     return IMT_OK;
 }
 
@@ -963,6 +964,30 @@ static imt_status insert_trace_dev(imt_ctx* ctx, const imt_insert_witness& w, si
         IMT_TRY_CUDA(ctx, cudaMemsetAsync(ctx->d_zero_leaf, 0, 4 * sizeof(Fr), ctx->stream));
         IMT_TRY(launch_hash_t<3>(ctx, ctx->d_zero_leaf + 1, ctx->d_zero_leaf, 1, kFmtMontgomery, kFmtMontgomery, ctx->stream));  // zero is zero in both formats
     }
+    if (w.fold_nodes && depth) {
+        // one-launch form: every operand is known, b x 4 depth independent traced node hashes on the compute stream with the 3 b
+        // traced leaf hashes beside them on the auxiliary stream (a latency-bound handful of blocks: they would otherwise be a tail)
+        Event forked, joined;
+        IMT_TRY_CUDA(ctx, forked.create());
+        IMT_TRY_CUDA(ctx, joined.create());
+        IMT_TRY_CUDA(ctx, cudaEventRecord(forked, ctx->stream));
+        IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, forked, 0));
+        k_trace_insert_leaves<<<grid_for(3 * b, kHashThreads), kHashThreads, 0, ctx->aux_stream>>>(
+            (const uint4*)w.low_leaves, (const uint4*)w.new_leaves, first_idx, b, depth, ctx->fmt, (const uint4*)ctx->d_zero_leaf, (uint4*)d_states,
+            nullptr, (uint4*)d_new_low, ctx->d_err, (const uint4*)w.fold_nodes);
+        k_trace_insert_folds<<<grid_for(4 * b * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
+            (const uint4*)w.low_siblings, (const uint4*)w.new_siblings, (const uint4*)w.fold_nodes, w.low_idx, first_idx, b, depth, ctx->fmt,
+            (uint4*)d_states, (uint4*)d_roots, ctx->d_err);
+        ctx->launches += 2;
+        const cudaError_t launched = cudaGetLastError();
+        cudaError_t e = cudaEventRecord(joined, ctx->aux_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, joined, 0);
+        if (launched != cudaSuccess || e != cudaSuccess) cudaStreamSynchronize(ctx->aux_stream);  // leave nothing behind on the auxiliary stream
+        IMT_TRY_CUDA(ctx, launched);
+        IMT_TRY_CUDA(ctx, e);
+        if (d_limbs) IMT_TRY(launch_limb_witness(ctx, w.low_leaves, w.new_leaves, 3, b, d_limbs, d_flags));
+        return IMT_OK;
+    }
     DevBuf dig(ctx);
     IMT_TRY_CUDA(ctx, dig.alloc(4 * b * sizeof(Fr)));
     k_trace_insert_leaves<<<grid_for(3 * b, kHashThreads), kHashThreads, 0, ctx->stream>>>(
@@ -1004,7 +1029,7 @@ extern "C" imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_wi
         return fail(ctx, IMT_ERR_INVALID_ARG, "low_leaves, low_idx, low_siblings, new_leaves and new_siblings are required");
     if (b == 0) return IMT_OK;
     IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dll(ctx), dnl(ctx), dli(ctx), dls(ctx), dns(ctx), dro(ctx), dnw(ctx), dlm(ctx), dfl(ctx);
+    DevBuf dll(ctx), dnl(ctx), dli(ctx), dls(ctx), dns(ctx), dro(ctx), dnw(ctx), dlm(ctx), dfl(ctx), dfn(ctx);
     IMT_TRY_CUDA(ctx, dll.alloc(b * 3 * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dnl.alloc(b * 3 * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, dli.alloc(b * sizeof(uint64_t)));
@@ -1019,6 +1044,10 @@ extern "C" imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_wi
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dli.p, w->low_idx, b * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dls.p, w->low_siblings, b * (size_t)depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     if (depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dns.p, w->new_siblings, b * (size_t)depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (depth && w->fold_nodes) {
+        IMT_TRY_CUDA(ctx, dfn.alloc(b * 4 * (size_t)depth * sizeof(Fr)));
+        IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dfn.p, w->fold_nodes, b * 4 * (size_t)depth * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    }
     IMT_TRY(clear_err(ctx));
     const size_t S = imt_insert_trace_hashes(depth), per_insert = S * trace_fe_per_hash(ctx, 2) * sizeof(Fr);
     auto chunk_of = [&](size_t off, size_t cnt, void* d_states_chunk) -> imt_status {
@@ -1028,6 +1057,7 @@ extern "C" imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_wi
         dw.low_idx = dli.as<uint64_t>() + off;
         dw.low_siblings = dls.as<Fr>() + off * depth;
         dw.new_siblings = dns.as<Fr>() + off * depth;
+        dw.fold_nodes = dfn.p ? dfn.as<Fr>() + off * 4 * depth : nullptr;
         return insert_trace_dev(ctx, dw, cnt, depth, first_idx + off, d_states_chunk, roots ? dro.as<Fr>() + 4 * off : nullptr,
                                 new_low_leaves ? dnw.as<Fr>() + 3 * off : nullptr, limbs ? dlm.as<Fr>() + 6 * off : nullptr,
                                 (limbs && limb_flags) ? dfl.as<uint8_t>() + 3 * off : nullptr);

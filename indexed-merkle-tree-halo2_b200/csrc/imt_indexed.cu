@@ -618,8 +618,11 @@ __device__ __forceinline__ unsigned link_lower_bound(const uint64_t* __restrict_
     }
     return lo;
 }
+// prev_own (optional) = the latest earlier write to t's OWN level-l node (-1: none): the node's value BEFORE write t, which the
+// witness trace of insert_leaf needs (the folds of the old low leaf and of the empty leaf, indexed_merkle_tree.rs:196-204, 286-294)
 __global__ void __launch_bounds__(256) k_ins_links_level(const uint64_t* __restrict__ a, uint64_t* __restrict__ a_next, unsigned writes,
-                                                         unsigned depth, unsigned l, int* __restrict__ prev, uint8_t* __restrict__ last) {
+                                                         unsigned depth, unsigned l, int* __restrict__ prev, uint8_t* __restrict__ last,
+                                                         int* __restrict__ prev_own) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= writes) return;
     const unsigned shift = kLinkTimeBits + l;
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(256) k_ins_links_level(const uint64_t* __restr
     const size_t id = (size_t)t * (depth + 1) + l;
     prev[id] = r ? (int)(a[sb + r - 1] & ((1u << kLinkTimeBits) - 1)) : -1;
     last[id] = (i + 1 == writes || (a[i + 1] >> shift) != v) ? 1 : 0;
+    if (prev_own) prev_own[id] = i > own ? (int)(a[i - 1] & ((1u << kLinkTimeBits) - 1)) : -1;  // the own segment is sorted by time
     if (l < depth) a_next[((v & 1) ? sb : own) + (i - own) + r] = key;  // merged by time into the parent's segment
 }
 
@@ -645,10 +649,14 @@ __global__ void __launch_bounds__(256) k_ins_links_level(const uint64_t* __restr
 // the witness path element of that write (low path of insert t/2 in the OLD tree for even t, new-leaf path in the NEW
 // tree for odd t — see the header of this file). The hashing half is the ordinary level kernel over `pairs`
 // (imt_host::launch_level: with <= 8192 writes that is the 3-lanes-per-hash latency kernel).
+// With fold_nodes (and prev_own) the chain values of the four folds the chip's insert_leaf constrains are kept for the one-launch witness
+// trace (imt_insert_witness_trace): fold_nodes[t / 2][2 (t & 1) + {0, 1}][l] = the level-l node on write t's path BEFORE the write (latest
+// earlier write to the same node, else the stored tree) and AFTER it, in the context format.
 __global__ void __launch_bounds__(256) k_ins_pairs(const uint4* __restrict__ ver_level, const uint4* __restrict__ tree_levels, size_t n,
                                                    unsigned l, const uint64_t* __restrict__ x, const int* __restrict__ prev, unsigned writes,
                                                    unsigned depth, int fmt, uint4* __restrict__ pairs, uint4* __restrict__ sib_low,
-                                                   uint4* __restrict__ sib_new, uint4* __restrict__ sib_all) {
+                                                   uint4* __restrict__ sib_new, uint4* __restrict__ sib_all,
+                                                   const int* __restrict__ prev_own = nullptr, uint4* __restrict__ fold_nodes = nullptr) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= writes) return;
     const uint64_t node = x[t] >> l;
@@ -666,6 +674,17 @@ __global__ void __launch_bounds__(256) k_ins_pairs(const uint4* __restrict__ ver
     }
     store_fe(pairs + 4 * (size_t)t, lo);
     store_fe(pairs + 4 * (size_t)t + 2, hi);
+    if (fold_nodes) {
+        uint32_t before[8];
+        const int q = prev_own[(size_t)t * (depth + 1) + l];
+        if (q >= 0) load_fe(before, ver_level + 2 * (size_t)q);
+        else load_fe(before, tree_levels + 2 * (level_offset(n, l) + node));
+        egress(before, fmt);
+        egress(own, fmt);
+        uint4* dst = fold_nodes + 2 * (((size_t)(t >> 1) * 4 + 2 * (t & 1)) * depth + l);
+        store_fe(dst, before);
+        store_fe(dst + 2 * (size_t)depth, own);
+    }
     uint4* wit = (t & 1) ? sib_new : sib_low;
     if (wit || sib_all) egress(sib, fmt);
     if (wit) store_fe(wit + 2 * ((size_t)(t >> 1) * depth + l), sib);
@@ -754,7 +773,8 @@ __global__ void k_iota_slots(uint32_t* s, size_t b, uint64_t first) {
 // Levels 1..depth of `writes` single-leaf writes to a tree (`tree_levels`, n leaves) from their level-0 versions in
 // ver[0 .. writes): links, then per level the operand gather + one level launch. ver holds (depth+1) x writes FE.
 imt_status versioned_levels(imt_ctx* ctx, const Fr* tree_levels, size_t n, unsigned depth, const uint64_t* d_x, unsigned writes, Fr* d_ver,
-                            int* d_prev, uint8_t* d_last, Fr* d_pairs, uint4* sib_low, uint4* sib_new, uint4* sib_all) {
+                            int* d_prev, uint8_t* d_last, Fr* d_pairs, uint4* sib_low, uint4* sib_new, uint4* sib_all,
+                            int* d_prev_own = nullptr, uint4* fold_nodes = nullptr) {
     if (writes > (1u << kLinkTimeBits)) return fail(ctx, IMT_ERR_INVALID_ARG, "more than 2^20 writes in one insert chunk");
     {  // links of every (write, level): sort the writes by (slot, time) once, then one merge step per level
         DevBuf keys_a(ctx), keys_b(ctx), temp(ctx);
@@ -770,7 +790,7 @@ imt_status versioned_levels(imt_ctx* ctx, const Fr* tree_levels, size_t n, unsig
         uint64_t* cur = keys_b.as<uint64_t>();
         uint64_t* nxt = keys_a.as<uint64_t>();
         for (unsigned l = 0; l <= depth; ++l) {
-            k_ins_links_level<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(cur, nxt, writes, depth, l, d_prev, d_last);
+            k_ins_links_level<<<grid_for(writes, 256), 256, 0, ctx->stream>>>(cur, nxt, writes, depth, l, d_prev, d_last, d_prev_own);
             std::swap(cur, nxt);
         }
         ctx->launches += depth + 4;
@@ -778,7 +798,8 @@ imt_status versioned_levels(imt_ctx* ctx, const Fr* tree_levels, size_t n, unsig
     }  // the scratch is freed in stream order
     for (unsigned l = 0; l < depth; ++l) {
         k_ins_pairs<<<grid_for(writes, 256), 256, 0, ctx->stream>>>((const uint4*)d_ver + 2 * ((size_t)l * writes), (const uint4*)tree_levels, n, l,
-                                                                    d_x, d_prev, writes, depth, ctx->fmt, (uint4*)d_pairs, sib_low, sib_new, sib_all);
+                                                                    d_x, d_prev, writes, depth, ctx->fmt, (uint4*)d_pairs, sib_low, sib_new, sib_all,
+                                                                    d_prev_own, fold_nodes);
         ++ctx->launches;
         IMT_TRY_CUDA(ctx, cudaGetLastError());
         IMT_TRY(launch_level(ctx, d_pairs, d_ver + (size_t)(l + 1) * writes, writes));
@@ -1050,7 +1071,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     const char* chunk_env = std::getenv("IMT_INSERT_CHUNK");  // read per call: tests force small chunks to cross chunk boundaries
     const size_t chunk_override = chunk_env ? (size_t)std::strtoull(chunk_env, nullptr, 10) : 0;
     const size_t C = std::min(b, chunk_override ? std::min(chunk_override, (size_t)1 << (kLinkTimeBits - 1)) : kInsertChunk), W = 2 * C, L = depth + 1;
-    DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx), pairs(ctx);
+    DevBuf x(ctx), upd(ctx), low_old(ctx), largest(ctx), prev(ctx), last(ctx), ver(ctx), sib_low(ctx), sib_new(ctx), r_old(ctx), r_new(ctx), h_low(ctx), h_new(ctx), low_idx(ctx), chunk_keys(ctx), chunk_slots(ctx), pairs(ctx), prev_own(ctx), fold(ctx);
     IMT_TRY_CUDA(ctx, x.alloc(W * sizeof(uint64_t)));
     IMT_TRY_CUDA(ctx, upd.alloc(W * 3 * sizeof(Fr)));
     IMT_TRY_CUDA(ctx, low_old.alloc(C * 3 * sizeof(Fr)));
@@ -1061,6 +1082,10 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
     IMT_TRY_CUDA(ctx, pairs.alloc(2 * W * sizeof(Fr)));
     if (out.low_siblings) IMT_TRY_CUDA(ctx, sib_low.alloc(C * depth * sizeof(Fr)));
     if (out.new_siblings) IMT_TRY_CUDA(ctx, sib_new.alloc(C * depth * sizeof(Fr)));
+    if (out.fold_nodes && depth) {
+        IMT_TRY_CUDA(ctx, prev_own.alloc(W * L * sizeof(int)));
+        IMT_TRY_CUDA(ctx, fold.alloc(C * 4 * depth * sizeof(Fr)));
+    }
     if (out.old_roots) IMT_TRY_CUDA(ctx, r_old.alloc(C * sizeof(Fr)));
     if (out.new_roots) IMT_TRY_CUDA(ctx, r_new.alloc(C * sizeof(Fr)));
     if (out.low_helpers) IMT_TRY_CUDA(ctx, h_low.alloc(C * depth));
@@ -1087,7 +1112,8 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         IMT_TRY(launch_hash(ctx, 3, upd.p, ver.p, writes, ctx->fmt, kFmtMontgomery, ctx->stream));
         IMT_TRY(versioned_levels(ctx, t->d_levels, t->n, depth, x.as<uint64_t>(), writes, ver.as<Fr>(), prev.as<int>(), last.as<uint8_t>(),
                                  pairs.as<Fr>(), out.low_siblings ? sib_low.as<uint4>() : nullptr,
-                                 out.new_siblings ? sib_new.as<uint4>() : nullptr, nullptr));
+                                 out.new_siblings ? sib_new.as<uint4>() : nullptr, nullptr, fold.p ? prev_own.as<int>() : nullptr,
+                                 fold.p ? fold.as<uint4>() : nullptr));
         k_ins_outputs<<<grid_for(cb, 256), 256, 0, ctx->stream>>>(ver.as<uint4>(), (const uint4*)t->d_levels, t->n, x.as<uint64_t>(), (unsigned)cb,
                                                                   depth, ctx->fmt, out.old_roots ? r_old.as<uint4>() : nullptr,
                                                                   out.new_roots ? r_new.as<uint4>() : nullptr,
@@ -1111,6 +1137,7 @@ extern "C" imt_status imt_insert_batch(imt_tree* t, const void* new_vals, size_t
         IMT_TRY_CUDA(ctx, d2h(out.low_leaves, 3 * sizeof(Fr), low_old.p));
         IMT_TRY_CUDA(ctx, d2h(out.low_siblings, depth * sizeof(Fr), sib_low.p));
         IMT_TRY_CUDA(ctx, d2h(out.new_siblings, depth * sizeof(Fr), sib_new.p));
+        IMT_TRY_CUDA(ctx, d2h(out.fold_nodes, 4 * (size_t)depth * sizeof(Fr), fold.p));
         IMT_TRY_CUDA(ctx, d2h(out.low_helpers, depth, h_low.p));
         IMT_TRY_CUDA(ctx, d2h(out.new_helpers, depth, h_new.p));
         IMT_TRY_CUDA(ctx, d2h(out.is_largest, 1, largest.p));

@@ -101,6 +101,7 @@ constexpr uint32_t kErrNonCanonical = 1u;   // an input FE >= p
 constexpr uint32_t kErrIndexOob = 2u;       // a leaf index outside the tree
 constexpr uint32_t kErrNotWellFormed = 4u;  // preimages are not a consistent indexed tree
 constexpr uint32_t kErrBadInsert = 8u;      // insert value is 0, already present, or repeated inside the batch
+constexpr uint32_t kErrBadFold = 16u;       // imt_insert_witness::fold_nodes are not the chain values of the witnesses they came with
 
 // FE offset of level `lvl` inside the concatenated level buffer of an n-leaf tree (n a power of two)
 __host__ __device__ __forceinline__ size_t level_offset(size_t n, unsigned lvl) { return 2 * n - 2 * (n >> lvl); }

@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* 
 //   3d + 3 .. 4d + 2  its fold up the same path                  -> new root, IMT:305-313
 // The four folds of an insert are independent of each other and of every other insert, so a batch of b inserts is one launch
 // of 3b traced leaf hashes and then, level by level, one launch of 4b traced node hashes (digests carried in `dig`, Montgomery).
+__device__ __forceinline__ bool fe_words_equal(const uint32_t* x, const uint4* p) {
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    return x[0] == a.x && x[1] == a.y && x[2] == a.z && x[3] == a.w && x[4] == b.x && x[5] == b.y && x[6] == b.z && x[7] == b.w;
+}
 __device__ __forceinline__ unsigned insert_trace_slot(unsigned fold, unsigned level, unsigned depth) {
     return fold == 0 ? 1 + level : fold == 1 ? depth + 2 + level : fold == 2 ? 2 * depth + 2 + level : 3 * depth + 3 + level;
 }
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_insert_leaves(const uint
                                                                       uint64_t first_idx, size_t b, unsigned depth, int fmt,
                                                                       const uint4* __restrict__ zero_leaf_hash, uint4* __restrict__ states,
                                                                       uint4* __restrict__ dig, uint4* __restrict__ new_low_out,
-                                                                      uint32_t* __restrict__ err) {
+                                                                      uint32_t* __restrict__ err, const uint4* __restrict__ fold_nodes = nullptr) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= 3 * b) return;
     const size_t k = i / 3;
@@ -305,11 +309,64 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_insert_leaves(const uint
         NoTrace nt;
         hash_fixed<3>(d, x, c_params, nt);
     }
+    if (fold_nodes) {  // one-launch form: the chain values are given; level 0 of each fold must be the leaf hash computed here
+        if (depth == 0) return;
+        const uint4* fn = fold_nodes + 2 * (4 * k * (size_t)depth);
+        egress(d, fmt);
+        if (!fe_words_equal(d, fn + 2 * ((j == 2 ? 3 : j) * (size_t)depth))) atomicOr(err, kErrBadFold);
+        if (j == 0) {  // fold 2 starts from the empty leaf, a constant in the chip (IMT:247-251)
+            uint32_t z[8];
+            load_fe(z, zero_leaf_hash);
+            egress(z, fmt);
+            if (!fe_words_equal(z, fn + 2 * (2 * (size_t)depth))) atomicOr(err, kErrBadFold);
+        }
+        return;
+    }
     store_fe(dig + 2 * (4 * k + (j == 2 ? 3 : j)), d);
     if (j == 0) {  // the empty leaf the new one replaces: fold 2 starts from the constant
         uint32_t z[8];
         load_fe(z, zero_leaf_hash);
         store_fe(dig + 2 * (4 * k + 2), z);
+    }
+}
+// One-launch form of the level loop below: with the chain values of the four folds known (imt_insert_witness::fold_nodes, a by-product
+// of imt_insert_batch) every one of the 4 b depth node hashes has both operands up front — one independent traced hash per thread, the
+// same shape as k_trace_tree_paths. Each digest is checked against the next chain value (the top one is the fold's root and goes to
+// roots_out), so a fold_nodes array that does not belong to these witnesses is reported (kErrBadFold), never traced silently.
+__global__ void __launch_bounds__(kHashThreads) k_trace_insert_folds(const uint4* __restrict__ low_sib, const uint4* __restrict__ new_sib,
+                                                                     const uint4* __restrict__ fold_nodes, const uint64_t* __restrict__ low_idx,
+                                                                     uint64_t first_idx, size_t b, unsigned depth, int fmt,
+                                                                     uint4* __restrict__ states, uint4* __restrict__ roots_out,
+                                                                     uint32_t* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
+    if (i >= 4 * b * depth) return;
+    const size_t k = i / (4 * (size_t)depth);
+    const unsigned r = (unsigned)(i - k * 4 * depth), f = r / depth, level = r - f * depth;
+    uint32_t h[8], s[8], x[2][8], d[8];
+    const uint4* node = fold_nodes + 2 * i;  // [k][f][level]
+    load_fe(h, node);
+    load_fe(s, (f < 2 ? low_sib : new_sib) + 2 * (k * depth + level));
+    bool ok = ingest(h, fmt);
+    ok &= ingest(s, fmt);
+    if (!ok) atomicOr(err, kErrNonCanonical);
+    const bool left = (((f < 2 ? low_idx[k] : first_idx + k) >> level) & 1) == 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        x[0][t] = left ? h[t] : s[t];
+        x[1][t] = left ? s[t] : h[t];
+    }
+    if (states) {
+        TraceSink sink{states + (k * (3 + 4 * depth) + insert_trace_slot(f, level, depth)) * (size_t)(kStatesPerHash * 3 * 2), fmt};
+        hash_fixed<2>(d, x, c_params, sink);
+    } else {
+        NoTrace nt;
+        hash_fixed<2>(d, x, c_params, nt);
+    }
+    egress(d, fmt);
+    if (level + 1 == depth) {
+        if (roots_out) store_fe(roots_out + 2 * (4 * k + f), d);
+    } else if (!fe_words_equal(d, node + 2)) {
+        atomicOr(err, kErrBadFold);
     }
 }
 __global__ void __launch_bounds__(kHashThreads) k_trace_insert_level(const uint4* __restrict__ low_sib, const uint4* __restrict__ new_sib,

@@ -315,8 +315,11 @@ class Engine:
         roots, new_low = np.empty((b, 4, 4), np.uint64), np.empty((b, 3, 4), np.uint64)
         limbs, flags = np.empty((b, 6, 4), np.uint64), np.empty((b, 3), np.uint8)
         cw = _ffi.InsertWitness()
-        for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings"):
-            setattr(cw, k, np.ascontiguousarray(w[k]).ctypes.data)
+        keep = [np.ascontiguousarray(w[k]) for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings")]
+        if w.get("fold_nodes") is not None:  # the one-launch form
+            keep.append(np.ascontiguousarray(w["fold_nodes"]))
+        for k, a in zip(("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings", "fold_nodes"), keep):
+            setattr(cw, k, a.ctypes.data)
         self._check(self._lib.imt_insert_witness_trace(self._h, ctypes.byref(cw), b, d, int(first_idx), _ptr(states), _ptr(roots), _ptr(new_low),
                                                        _ptr(limbs), _ptr(flags)))
         return dict(states=states, limbs=limbs, limb_flags=flags.astype(bool), low_leaf=states[:, 0], low_path=states[:, 1:1 + d],
@@ -328,8 +331,9 @@ class Engine:
         """imt_insert_witness_trace_dev: everything on the device. d_w: dict with CUDA tensors low_leaves, low_idx, low_siblings,
         new_leaves, new_siblings (the layouts Tree.insert_batch returns); outputs are CUDA tensors or None."""
         cw = _ffi.InsertWitness()
-        for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings"):
-            setattr(cw, k, _dev_ptr(d_w[k]).value)
+        for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings", "fold_nodes"):
+            if d_w.get(k) is not None:
+                setattr(cw, k, _dev_ptr(d_w[k]).value)
         opt = lambda t: _dev_ptr(t) if t is not None else None
         self._check(self._lib.imt_insert_witness_trace_dev(self._h, ctypes.byref(cw), b, depth, int(first_idx), opt(d_states), opt(d_roots),
                                                            opt(d_new_low), opt(d_limbs), opt(d_flags)))
@@ -579,12 +583,15 @@ class Tree:
         return o
 
     @staticmethod
-    def insert_buffers(b, depth, pinned=False):
-        """output buffers of insert_batch for b inserts (see non_inclusion_buffers for `pinned`)"""
+    def insert_buffers(b, depth, pinned=False, fold_nodes=True):
+        """output buffers of insert_batch for b inserts (see non_inclusion_buffers for `pinned`). fold_nodes: also the chain values of
+        the four folds insert_leaf constrains (b, 4, depth) FE, which make trace_insert_witness a single launch (single-GPU trees)."""
         shapes = dict(old_roots=((b, 4), np.uint64), low_idx=((b,), np.uint64), low_leaves=((b, 3, 4), np.uint64),
                       low_siblings=((b, depth, 4), np.uint64), low_helpers=((b, depth), np.uint8), new_roots=((b, 4), np.uint64),
                       new_leaves=((b, 3, 4), np.uint64), new_siblings=((b, depth, 4), np.uint64), new_helpers=((b, depth), np.uint8),
                       is_largest=((b,), np.uint8))
+        if fold_nodes:
+            shapes["fold_nodes"] = ((b, 4, depth, 4), np.uint64)
         if not pinned:
             return {k: np.empty(sh, dt) for k, (sh, dt) in shapes.items()}
         import torch
@@ -603,7 +610,7 @@ class Tree:
         o = out if out is not None else self.insert_buffers(b, d)
         if o["low_siblings"].shape != (b, d, 4):
             raise ValueError("out buffers were made for another batch size / depth")
-        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        w = _ffi.InsertWitness(*[o[k].ctypes.data if k in o else None for k, _ in _ffi.InsertWitness._fields_])
         self.engine._check(self._lib.imt_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
         return o
 
@@ -663,8 +670,8 @@ class Tree:
         if first_idx is None:
             first_idx = self.sharded_occupied
         b, d = v.shape[0], self.depth
-        o = out if out is not None else self.insert_buffers(b, d)
-        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        o = out if out is not None else self.insert_buffers(b, d, fold_nodes=False)
+        w = _ffi.InsertWitness(*[o[k].ctypes.data if k in o and k != "fold_nodes" else None for k, _ in _ffi.InsertWitness._fields_])
         self.engine._check(self._lib.imt_sharded_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
         return o
 
@@ -901,8 +908,8 @@ class MTree:
         if first_idx is None:
             first_idx = self.occupied
         b, d = v.shape[0], self.depth
-        o = out if out is not None else Tree.insert_buffers(b, d)
-        w = _ffi.InsertWitness(*[o[k].ctypes.data for k, _ in _ffi.InsertWitness._fields_])
+        o = out if out is not None else Tree.insert_buffers(b, d, fold_nodes=False)
+        w = _ffi.InsertWitness(*[o[k].ctypes.data if k in o and k != "fold_nodes" else None for k, _ in _ffi.InsertWitness._fields_])
         self.multi._check(self._lib.imt_mtree_insert_batch(self._h, _ptr(v), b, int(first_idx), ctypes.byref(w)))
         return o
 

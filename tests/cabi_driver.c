@@ -57,7 +57,8 @@ int main(void) {
     for (int i = 0; i < 6; ++i) vals[4 * i] = ins[i];
     uint64_t old_roots[6 * 4], new_roots[6 * 4], low_idx[6], low_leaves[6 * 12], new_leaves[6 * 12], low_sib[6 * 3 * 4], new_sib[6 * 3 * 4];
     uint8_t low_hel[6 * 3], new_hel[6 * 3], largest[6];
-    imt_insert_witness w = {old_roots, low_idx, low_leaves, low_sib, low_hel, new_roots, new_leaves, new_sib, new_hel, largest};
+    static uint64_t fold_nodes[6 * 4 * 3 * 4]; /* chain values of the four folds: make the witness trace below one launch */
+    imt_insert_witness w = {old_roots, low_idx, low_leaves, low_sib, low_hel, new_roots, new_leaves, new_sib, new_hel, largest, fold_nodes};
     CHECK(imt_insert_batch(tree, vals, 6, occupied, &w));
     for (int i = 0; i < 6; ++i) {
         printf("low_idx %" PRIu64 " largest %d\n", low_idx[i], (int)largest[i]);
@@ -154,6 +155,12 @@ int main(void) {
         trace_ok &= memcmp(tr_states + ((((size_t)i * 15 + 14) * 132 + 131) * 3 + 1) * 4, new_roots + 4 * i, 32) == 0;
         trace_ok &= tr_flags[3 * i + 2] == 1;
     }
+    /* the same trace without the chain values (1 + depth dependent launches) is identical */
+    static uint64_t tr_states_loop[6 * 15 * 132 * 3 * 4];
+    uint64_t tr_roots_loop[6 * 4 * 4];
+    w.fold_nodes = NULL;
+    CHECK(imt_insert_witness_trace(ctx, &w, 6, 3, occupied, tr_states_loop, tr_roots_loop, NULL, NULL, NULL));
+    trace_ok &= memcmp(tr_states, tr_states_loop, sizeof tr_states) == 0 && memcmp(tr_roots, tr_roots_loop, sizeof tr_roots) == 0;
     printf("insert_trace_ok %d\n", trace_ok);
     imt_tree_destroy(tree);
     imt_ctx_destroy(ctx);

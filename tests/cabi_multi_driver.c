@@ -126,8 +126,8 @@ int main(int argc, char** argv) {
     uint64_t nr_ref[B * 4], nr_got[B * 4], li_ref[B], li_got[B];
     uint64_t* ls_ref = (uint64_t*)malloc((size_t)B * depth * 32);
     uint64_t* ls_got = (uint64_t*)malloc((size_t)B * depth * 32);
-    imt_insert_witness w_ref = {NULL, li_ref, NULL, ls_ref, NULL, nr_ref, NULL, NULL, NULL, NULL};
-    imt_insert_witness w_got = {NULL, li_got, NULL, ls_got, NULL, nr_got, NULL, NULL, NULL, NULL};
+    imt_insert_witness w_ref = {NULL, li_ref, NULL, ls_ref, NULL, nr_ref, NULL, NULL, NULL, NULL, NULL};
+    imt_insert_witness w_got = {NULL, li_got, NULL, ls_got, NULL, nr_got, NULL, NULL, NULL, NULL, NULL};
     if (ref) {
         OK(imt_tree_get_proofs(ref, idx, Q, sib_ref, hel_ref));
         OK(imt_low_leaf_lookup(iref, qv, Q, low_ref, m_ref));

@@ -48,6 +48,25 @@ def assert_witness_equal(got, k, want):
         assert np.array_equal(np.asarray(a), np.asarray(b)), f"insert {k}: {g} differs"
 
 
+def oracle_fold_nodes(w, k, new_idx, dec=lambda a: a):
+    """chain values of the four folds of insert k (IMT:196-204, 277-294, 305-313), recomputed by the oracle from the witnesses alone:
+    (4, depth, 4) canonical — level 0 is the leaf hash, level l + 1 = H2 of level l with the path's sibling"""
+    low, new = dec(w["low_leaves"][k]), dec(w["new_leaves"][k])
+    new_low = np.stack([low[0], new[0], O.fe(new_idx)])
+    lsib, nsib = dec(w["low_siblings"][k]), dec(w["new_siblings"][k])
+    depth = lsib.shape[0]
+    out = np.zeros((4, depth, 4), np.uint64)
+    for f, (leaf, idx, sib) in enumerate(((low, int(w["low_idx"][k]), lsib), (new_low, int(w["low_idx"][k]), lsib),
+                                          (np.zeros((3, 4), np.uint64), new_idx, nsib), (new, new_idx, nsib))):
+        h = O.hash3(leaf.reshape(1, 3, 4), 1)[0]
+        for lvl in range(depth):
+            out[f, lvl] = h
+            pair = np.stack([h, sib[lvl]]) if idx % 2 == 0 else np.stack([sib[lvl], h])
+            h = O.hash2(pair.reshape(1, 2, 4), 1)[0]
+            idx //= 2
+    return out
+
+
 def test_reference_scenario_as_one_batch(eng):
     """test_insert_leaf_multiple_round (IMT:679-741): 6 inserts into the empty depth-3 tree, in ONE device batch.
     Roots / low-leaf indices are the committed fixtures; every other witness field is compared with the oracle running
@@ -160,6 +179,8 @@ def test_insert_batch_matches_sequential_oracle(eng, depth, m, b, chunk, monkeyp
         want = st.insert(vals[k], m + k, incremental=True)
         if k % step == 0 or k >= b - 3:
             assert_witness_equal(got, k, want)
+            if k % (5 * step) == 0 or k >= b - 3:   # the chain values of the four folds (imt_insert_witness::fold_nodes), across chunks
+                assert np.array_equal(got["fold_nodes"][k], oracle_fold_nodes(got, k, m + k)), k
         else:
             assert np.array_equal(got["new_roots"][k], want["new_root"]) and int(got["low_idx"][k]) == want["low_idx"]
     assert np.array_equal(tree.preimages(n), st.pre)
@@ -198,7 +219,21 @@ def test_insert_leaf_witness_traces(eng, eng_mont):
     for e, enc, dec in ((eng, lambda a: a, lambda a: a), (eng_mont, to_mont, from_mont)):
         tree = e.build_from_leaves(enc(pre))
         w = tree.insert_batch(enc(vals), m)
-        tr = e.trace_insert_witness(w, m)
+        tr = e.trace_insert_witness(w, m)                                        # one launch: fold_nodes came with the batch
+        loop = e.trace_insert_witness({k: v for k, v in w.items() if k != "fold_nodes"}, m)   # 1 + depth dependent launches
+        for name in ("states", "limbs", "limb_flags", "old_root", "interim_root", "zero_leaf_root", "new_root", "new_low_leaf_preimage"):
+            assert np.array_equal(tr[name], loop[name]), name
+        for k in range(b):
+            assert np.array_equal(dec(w["fold_nodes"][k]), oracle_fold_nodes(w, k, m + k, dec)), k
+        bad = dict(w, fold_nodes=w["fold_nodes"].copy())                         # chain values that are not these witnesses'
+        bad["fold_nodes"][2, 1, 3] = w["fold_nodes"][2, 1, 2]
+        with pytest.raises(imt_b200.ImtError) as err:
+            e.trace_insert_witness(bad, m)
+        assert err.value.status == _ffi.ERR_INVALID_ARG and "fold_nodes" in str(err.value)
+        bad["fold_nodes"][2, 1, 3] = w["fold_nodes"][2, 1, 3]
+        bad["fold_nodes"][4, 2, 0] = w["fold_nodes"][4, 0, 0]                    # a fold that does not start from the empty leaf
+        with pytest.raises(imt_b200.ImtError):
+            e.trace_insert_witness(bad, m)
         assert np.array_equal(tr["old_root"], w["old_roots"]) and np.array_equal(tr["new_root"], w["new_roots"])
         assert np.array_equal(tr["zero_leaf_root"], tr["interim_root"])          # IMT:286-294 holds on GPU-made witnesses
         assert tr["limb_flags"][:, 2].all()                                      # every witness passes the chip's assertions
@@ -539,11 +574,18 @@ def test_insert_witness_trace_depth24_batch_4096_sampled_against_the_oracle(eng_
     vals = to_mont(synth.field_elements(b, seed=4242))
     w = tree.insert_batch(vals, m)
     dw = {k: torch.from_numpy(np.ascontiguousarray(w[k]).view(np.int64) if w[k].dtype == np.uint64 else w[k]).to(dev)
-          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings")}
+          for k in ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings", "fold_nodes")}
     S = 3 + 4 * depth
     d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
     d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
-    e.trace_insert_witness_dev(dw, b, depth, m, d_states, d_roots)
+    e.trace_insert_witness_dev({k: v for k, v in dw.items() if k != "fold_nodes"}, b, depth, m, d_states, d_roots)   # level loop
+    d_states_1, d_roots_1 = torch.zeros_like(d_states), torch.zeros_like(d_roots)
+    torch.cuda.synchronize()                                                   # the fills run on torch's stream, the library on its own
+    launches = e.launches
+    e.trace_insert_witness_dev(dw, b, depth, m, d_states_1, d_roots_1)         # one launch of 4 b depth independent traced hashes (+ leaves)
+    assert e.launches - launches == 2
+    assert torch.equal(d_states_1, d_states) and torch.equal(d_roots_1, d_roots)
+    del d_states_1
     roots = d_roots.cpu().numpy().view(np.uint64)
     assert np.array_equal(roots[:, 0], w["old_roots"]) and np.array_equal(roots[:, 3], w["new_roots"])
     assert np.array_equal(roots[:, 1], roots[:, 2])                            # both routes to the interim root (IMT:277-294)

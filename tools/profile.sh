@@ -11,6 +11,10 @@ CMD="python bench.py --depth $DEPTH --steps 2 --warmup 3 --no-cpu-baseline --no-
 PER_BUILD=$((2 * DEPTH))
 # thread-per-hash launches of one build: the leaf kernel + the half-levels above 4096 nodes per half
 TPH=$((1 + 2 * (DEPTH - 14)))
+# imt_ctx_create's self-test launches one block of each kernel family first: 2 x k_hash, 2 x k_hash_coop
+SELF=2
+# cooperative launches of one build: the half-levels of <= 4096 nodes (13 per half) + the root
+COOP=27
 if [ "${PROFILE_BUILD:-1}" = 1 ]; then
 # launch list of THIS library's kernels only (-k regex:^k_): bench.py synthesises its leaves with a few hundred tiny torch
 # element-wise launches during (untimed) setup, which would otherwise fill the capture window. Shares are per build.
@@ -19,13 +23,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c $((6 *
 echo "launch list rc=$?"
 # leaf kernel + the first (largest) half-level of the third build
 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:^k_hash$ -s $((2 * TPH)) -c 2 -o $OUT/${TAG}_k_hash -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:^k_hash$ -s $((SELF + 2 * TPH)) -c 2 -o $OUT/${TAG}_k_hash -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 fi
 # the 3-lanes-per-hash latency kernel: the 4096-nodes-per-half level and smaller ones of one build
 if [ "${PROFILE_COOP:-1}" = 1 ]; then
 $CMD > $OUT/${TAG}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_hash_coop -s 26 -c 6 -o $OUT/${TAG}_k_coop -f $CMD > $OUT/${TAG}_ncu_coop.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_hash_coop -s $((SELF + COOP)) -c 6 -o $OUT/${TAG}_k_coop -f $CMD > $OUT/${TAG}_ncu_coop.log 2>&1
 echo "coop capture rc=$?"
 fi
 # witness traces read from the resident tree: one independent traced hash per (query, level)
