@@ -566,15 +566,27 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     S = 3 + 4 * depth
     d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
     d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
+    # traced in the format a halo2 host holds its field elements in (Montgomery, zero-copy): the canonical context would add one
+    # from_mont per traced state element (396 per hash, +12 % multiply work)
+    et = ec
+    if eng.fmt == 1:
+        et = eng
+        for k, v in list(dw.items()):
+            if k != "low_idx":
+                mv = torch.empty_like(v)
+                eng.convert_dev(v, v.numel() // 4, mv, to_montgomery=True)
+                dw[k] = mv
+        torch.cuda.synchronize()
+    root_of = (lambda a: a) if et is ec else (lambda a: ec.convert(a, to_montgomery=True))
     # one launch: the chain values of the four folds came with the insert batch (imt_insert_witness::fold_nodes)
-    t_wt = _ev_time(torch, stream, lambda: ec.trace_insert_witness_dev(dw, b, depth, next_slot - b, d_states, d_roots), 2, 1)
-    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
+    t_wt = _ev_time(torch, stream, lambda: et.trace_insert_witness_dev(dw, b, depth, next_slot - b, d_states, d_roots), 2, 1)
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), root_of(w["new_roots"]))
     sample_one = d_states[:: max(1, b // 64)].clone()
     # without them: 1 + depth dependent launches of 4b traced hashes (hash latency)
     dw_loop = {k: v for k, v in dw.items() if k != "fold_nodes"}
-    t_wt_loop = _ev_time(torch, stream, lambda: ec.trace_insert_witness_dev(dw_loop, b, depth, next_slot - b, d_states, d_roots), 2, 1)
+    t_wt_loop = _ev_time(torch, stream, lambda: et.trace_insert_witness_dev(dw_loop, b, depth, next_slot - b, d_states, d_roots), 2, 1)
     assert torch.equal(sample_one, d_states[:: max(1, b // 64)]), "one-launch trace != level-loop trace"
-    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), root_of(w["new_roots"]))
     hbm = _peaks().get("hbm_gbs", 6650.0)
     probes = max(1, m.bit_length())
     out = {
@@ -591,7 +603,7 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
         "insert": {"metric": "inserts_per_s", "value": b / t_ins, "unit": "inserts/s", "ms_per_batch": t_ins * 1e3, "batch": b,
                    "hashes_per_s": 2 * b * (depth + 1) / t_ins, "call": "imt_insert_batch (host values in, witness bundle out into page-locked buffers)",
                    "witness_trace": {"call": "imt_insert_witness_trace_dev with fold_nodes (one launch of independent traced hashes)", "hashes": b * S,
-                                     "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3), "bytes": b * S * 132 * 96,
+                                     "fe_format": "montgomery" if et.fmt == 1 else "canonical", "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3), "bytes": b * S * 132 * 96,
                                      "level_loop": {"ms": t_wt_loop, "hashes_per_s": b * S / (t_wt_loop * 1e-3),
                                                     "note": "the same call without fold_nodes: 1 + depth dependent launches"}}},
         "index_build_s": t_index,

@@ -220,7 +220,8 @@ imt_status imt_non_inclusion_paths(imt_tree* tree, const void* values, size_t q,
  *   fold_nodes 4 x depth FE = the chain values of the four folds insert_leaf constrains (:196-204, 277-294, 305-313), levels
  *   0 .. depth-1 each: [0] the low leaf's path BEFORE the insert (level 0 = H3(low leaf)), [1] the same path after the low
  *   leaf was rewired, [2] the new leaf's path before the new leaf is written (level 0 = the stored empty leaf), [3] after.
- *   They cost nothing extra here (the batch computes them anyway) and turn imt_insert_witness_trace into one launch.
+ *   They cost nothing extra here (the batch computes them anyway) and turn imt_insert_witness_trace into one launch. Single-GPU
+ *   trees only: imt_sharded_insert_batch / imt_mtree_insert_batch do not write fold_nodes (pass NULL there).
  * first_idx must equal imt_tree_occupied(). The batch is validated first (IMT_ERR_INVALID_ARG for a value that is 0,
  * already in the tree or repeated; IMT_ERR_TREE_FULL): on a validation error nothing is modified. The tree, its
  * preimages and its sorted index are updated in place, chunk by chunk (up to 65536 inserts each): a CUDA / allocation

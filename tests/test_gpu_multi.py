@@ -79,7 +79,8 @@ def test_multi_lookups_and_inserts_equal_single_gpu(eng, world):
         assert np.array_equal(o[k], wo[k]), k
     new = synth.field_elements(200, seed=1234)
     w, ww = t.insert_batch(new), whole.insert_batch(new)
-    for k in ww:
+    assert set(ww) - set(w) == {"fold_nodes"}                      # the chain values of the folds come from single-GPU batches only
+    for k in w:
         assert np.array_equal(w[k], ww[k]), k
     assert np.array_equal(t.root(), whole.root()) and t.occupied == occ + 200
     low, _ = t.low_leaf_lookup(vals)                               # the per-shard indices were merged, not rebuilt

@@ -20,3 +20,20 @@ for s in range(4):
     vals = synth.field_elements(b, seed=7000 + s)
     t0 = time.perf_counter(); tree.insert_batch(vals, first_idx=slot, out=out); ts.append(time.perf_counter() - t0); slot += b
 print("chunk", os.environ.get("IMT_INSERT_CHUNK", "default"), "batch", b, "ms", [round(t * 1e3, 2) for t in ts], "inserts/s", round(b / min(ts[1:])), "root", imt_b200.fe_to_int(tree.root()) % 10**12, flush=True)
+# TRACE=<inserts>: the insert_leaf witness trace (imt_insert_witness_trace_dev) of the first <inserts> inserts of the last batch, device
+# resident, with the chain values of the folds (one launch) and without (1 + depth dependent launches)
+tb = min(b, int(os.environ.get("TRACE", "0")))
+if tb:
+    w = out
+    keys = ("low_idx", "low_leaves", "low_siblings", "new_leaves", "new_siblings", "fold_nodes")
+    dw = {k: torch.from_numpy(np.ascontiguousarray(w[k][:tb]).view(np.int64)).to(dev) for k in keys}
+    S = 3 + 4 * depth
+    d_states = torch.empty((tb, S, 132, 3, 4), dtype=torch.int64, device=dev)
+    d_roots = torch.empty((tb, 4, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    for name, d in (("one launch", dw), ("level loop", {k: v for k, v in dw.items() if k != "fold_nodes"})):
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter(); eng.trace_insert_witness_dev(d, tb, depth, slot - b, d_states, d_roots); best = min(best, time.perf_counter() - t0)
+        assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"][:tb])
+        print(f"witness trace of {tb} inserts ({tb * S} traced hashes), {name}: {best * 1e3:.2f} ms = {tb * S / best / 1e6:.1f} M traced hashes/s", flush=True)
