@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 MACS_PER_HASH = 163_200          # 2 perms x 600 Montgomery muls x 136 32x32->64 MACs
 EXECUTED_MACS_PER_HASH = 123_792  # what the kernels issue: squarings are 36 products, 3-term dot products reduce once (ncu: profiles/)
-LEAF_DRAM_BYTES_PER_HASH = 129.6  # dram__bytes_read+write of k_hash<3> per leaf: 2.174 GB / 2^24 leaves, ncu --set full (profiles/r01f_summary.md)
+LEAF_DRAM_BYTES_PER_HASH = 129.3  # dram__bytes_read+write of k_hash<3> per leaf: (1.643 + 0.527) GB / 2^24 leaves, ncu --set full (profiles/r02_summary.md)
 TRACE_DRAM_BYTES_PER_HASH = 12568.0  # dram__bytes_read+write of k_trace_tree_paths per traced hash: 4.118 GB / 327 680 hashes (profiles/r01e_summary.md); algorithmic 12 672 + 64
 METRIC = "poseidon_hashes_per_s_depth24_tree_build"
 
@@ -820,7 +820,7 @@ def main():
         "frac": achieved / imad_rate if imad_rate else None,
         "executed_frac": achieved / imad_rate * EXECUTED_MACS_PER_HASH / MACS_PER_HASH if imad_rate else None,
         "traffic": LEAF_DRAM_BYTES_PER_HASH * (k3_hashes / max(k3_launches, 1)),
-        "traffic_note": "bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel per leaf (129.6 B, one --set full "
+        "traffic_note": "bytes per launch = ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel per leaf (129.3 B, one --set full "
                         "capture, profiles/) x leaves per launch; algorithmic 128 B per leaf",
         "frac_note": "frac uses ALGORITHMIC MACs (163200 per hash) and exceeds 1 because squarings and one-reduction dot products execute "
                      "123792; executed_frac is the multiply-pipe utilisation (ncu sm__pipe_fmaheavy_cycles_active agrees)",
