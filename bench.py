@@ -550,6 +550,19 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     o = tree.non_inclusion_paths(hq, out=bufs)
     t_e2e = time.perf_counter() - t0
     assert np.array_equal(o["low_idx"], d_low.cpu().numpy().astype(np.uint64))
+    # the whole verify_non_inclusion witness, traced, one call, device resident: lookup + low leaf + limbs + (1 + depth) traced hashes per value
+    qt = 1 << 14
+    d_lowt = torch.empty(qt, dtype=torch.int64, device=dev)
+    d_leavest = torch.empty((qt, 3, 4), dtype=torch.int64, device=dev)
+    d_limbst = torch.empty((qt, 6, 4), dtype=torch.int64, device=dev)
+    d_statest = torch.empty((qt, 1 + depth, 132, 3, 4), dtype=torch.int64, device=dev)
+    t_nit = _ev_time(torch, stream, lambda: tree.trace_non_inclusion_dev(d_vals[:qt], qt, d_lowt, d_leavest, d_statest, d_limbs=d_limbst), 2, 1)
+    assert bool((d_lowt == d_low[:qt]).all())
+    d_rootc = torch.empty(4, dtype=torch.int64, device=dev)
+    tree.root_dev(d_rootc)
+    stream.synchronize()
+    assert bool((d_statest[:, -1, -1, 1] == d_rootc).all()), "a traced non-inclusion path does not end in the root"
+    del d_statest
     ins_out = tree.insert_buffers(b, depth, pinned=True)
     next_slot, ins = m, []
     for s_ in range(steps + 2):
@@ -606,6 +619,9 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
                                      "fe_format": "montgomery" if et.fmt == 1 else "canonical", "ms": t_wt, "hashes_per_s": b * S / (t_wt * 1e-3), "bytes": b * S * 132 * 96,
                                      "level_loop": {"ms": t_wt_loop, "hashes_per_s": b * S / (t_wt_loop * 1e-3),
                                                     "note": "the same call without fold_nodes: 1 + depth dependent launches"}}},
+        "non_inclusion_trace": {"call": "imt_non_inclusion_witness_trace_dev (lookup + low leaf + limbs + the 1 + depth traced hashes of verify_non_inclusion)",
+                                "queries": qt, "hashes": qt * (1 + depth), "ms": t_nit, "hashes_per_s": qt * (1 + depth) / (t_nit * 1e-3),
+                                "fe_format": "canonical (one from_mont per traced state element; Montgomery contexts skip it)"},
         "index_build_s": t_index,
     }
     tree.close()

@@ -272,6 +272,25 @@ imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_witness* w, s
 imt_status imt_insert_witness_trace_dev(imt_ctx* ctx, const imt_insert_witness* d_w, size_t b, unsigned depth, uint64_t first_idx,
                                         void* d_states, void* d_roots, void* d_new_low_leaves, void* d_limbs, uint8_t* d_limb_flags);
 
+/* The whole witness of the chip's verify_non_inclusion (src/indexed_merkle_tree.rs:127-229) for q values in ONE call: the low-leaf
+ * lookup, everything imt_non_inclusion_paths returns, the 128-bit limb witnesses of imt_non_inclusion_limbs (:143-172, 206-222) and
+ * the Poseidon states of the 1 + depth hashes it constrains, in its call order:
+ *     [0] H3(low leaf)   :193-194        [1 .. depth] its fold up the low leaf's path to the root (compute_merkle_root :65-96, :196-204)
+ * states[q][1 + depth][imt_trace_fe_per_hash] FE. Every output may be NULL in the host variant; the _dev variant takes DEVICE pointers
+ * and needs d_low_idx and d_low_leaves (they feed the trace). All operands are stored nodes, so the q x (1 + depth) traced hashes are
+ * independent threads of two launches (the multiply-pipe rate of the trace kernel); the host variant streams the states out in
+ * chunks behind the hashing. matched[i] = 0 (value 0 or already present) still yields the witness of slot low_idx[i] = 0, as the
+ * reference's helper returns it; limb_flags[3 i + 2] tells whether the chip's prover-side assertions would pass. Single-GPU trees
+ * built from leaves, default Poseidon instance (any-width contexts: imt_non_inclusion_paths + imt_poseidon_trace +
+ * imt_tree_trace_proofs). */
+size_t imt_non_inclusion_trace_hashes(unsigned depth); /* 1 + depth */
+imt_status imt_non_inclusion_witness_trace(imt_tree* tree, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched, void* low_leaves,
+                                           void* siblings, uint8_t* helpers, uint8_t* is_largest, void* limbs, uint8_t* limb_flags,
+                                           void* states);
+imt_status imt_non_inclusion_witness_trace_dev(imt_tree* tree, const void* d_values, size_t q, uint64_t* d_low_idx, uint8_t* d_matched,
+                                               void* d_low_leaves, void* d_siblings, uint8_t* d_helpers, uint8_t* d_is_largest, void* d_limbs,
+                                               uint8_t* d_limb_flags, void* d_states);
+
 /* ---------------------------------------------------------------- subtree sharding (one process per GPU) ----- */
 /* A depth-d tree over N = 2^k ranks: rank g owns leaves [g n/N, (g+1) n/N) and builds that subtree with the calls
  * above (n = leaves per rank). The N subtree roots are exchanged by the caller (ncclAllGather / torch.distributed

@@ -250,6 +250,31 @@ class IndexedMerkleTree {
         }
         return o;
     }
+    // The whole witness of verify_non_inclusion (IMT:127-229) in ONE call: the values above + the Poseidon states of the 1 + depth
+    // hashes it constrains per value — [0] H3(low leaf) IMT:193-194, [1 .. depth] its fold up the path IMT:196-204 — flattened
+    // [q][1 + depth][states per hash][T] Fr into `states`.
+    NonInclusion non_inclusion_witness_trace(const std::vector<Fr>& values, std::vector<Fr>* states) const {
+        const size_t q = values.size(), d = depth();
+        NonInclusion o;
+        o.low_idx.resize(q), o.low_leaves.resize(q), o.limbs.resize(q);
+        std::vector<uint8_t> matched(q), hel(q * d), lg(q), flags(3 * q);
+        std::vector<Fr> sib(q * d);
+        size_t fe = 0;
+        detail::check(ctx_, imt_trace_fe_per_hash(ctx_, 2, &fe));
+        if (states) states->resize(q * imt_non_inclusion_trace_hashes((unsigned)d) * fe);
+        detail::check(ctx_, imt_non_inclusion_witness_trace(tree_.get(), values.data(), q, o.low_idx.data(), matched.data(), o.low_leaves.data(),
+                                                            sib.data(), hel.data(), lg.data(), o.limbs.data(), flags.data(),
+                                                            states ? states->data() : nullptr));
+        for (size_t i = 0; i < q; ++i) {
+            o.low_proof.emplace_back(sib.begin() + i * d, sib.begin() + (i + 1) * d);
+            std::vector<Fr> h(d);
+            for (size_t k = 0; k < d; ++k) h[k] = Fr::from(hel[i * d + k]);
+            o.low_proof_helper.push_back(std::move(h));
+            o.is_new_leaf_largest.push_back(lg[i] != 0);
+            o.valid.push_back(matched[i] != 0 && flags[3 * i + 2] != 0);
+        }
+        return o;
+    }
     // IMT:710-741 for a whole batch with O(depth) hashes per insert: the tree advances in place and every per-insert
     // witness comes back — bit-identical to re-hashing and rebuilding per insert as the reference does (IMT:724-730)
     InsertWitness insert_batch(const std::vector<Fr>& new_vals) {

@@ -139,6 +139,9 @@ SIGNATURES = {
     "imt_fe_convert": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "imt_fe_convert_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "imt_insert_trace_hashes": (c_size_t, [c_uint]),
+    "imt_non_inclusion_trace_hashes": (c_size_t, [c_uint]),
+    "imt_non_inclusion_witness_trace": (c_int, [c_void_p, c_void_p, c_size_t] + [c_void_p] * 9),
+    "imt_non_inclusion_witness_trace_dev": (c_int, [c_void_p, c_void_p, c_size_t] + [c_void_p] * 9),
     "imt_insert_witness_trace": (c_int, [c_void_p, ctypes.POINTER(InsertWitness), c_size_t, c_uint, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "imt_insert_witness_trace_dev": (c_int, [c_void_p, ctypes.POINTER(InsertWitness), c_size_t, c_uint, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     # ---- checkpoints

@@ -874,15 +874,18 @@ extern "C" imt_status imt_trace_merkle_proofs(imt_ctx* ctx, const void* leaves, 
 // Witness traces of verify_merkle_proof for leaves OF THIS TREE (indexed_merkle_tree.rs:65-96 with the paths of utils.rs:63-85):
 // all operands are stored levels, so the q x depth traced hashes run independently (k_trace_tree_paths) instead of as q
 // serial folds. states[q][depth][fe per hash]; identical bytes to imt_tree_get_proofs + imt_trace_merkle_proofs.
-imt_status imt_host::launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox) {
+imt_status imt_host::launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox, unsigned lead_slots) {
     imt_ctx* ctx = t->ctx;
     const unsigned cap_depth = t->cap_valid ? t->cap_depth : 0;
     const unsigned depth = t->depth + cap_depth;
     if (q == 0 || depth == 0) return IMT_OK;
-    if (ctx->generic) return launch_spec_tree_trace(t, d_idx, q, d_states, d_sbox);
+    if (ctx->generic) {
+        if (lead_slots) return fail(ctx, IMT_ERR_INVALID_ARG, "interleaved traces are for the default Poseidon instance only");
+        return launch_spec_tree_trace(t, d_idx, q, d_states, d_sbox);
+    }
     k_trace_tree_paths<<<grid_for(q * depth, kHashThreads), kHashThreads, 0, ctx->stream>>>(
         (const uint4*)t->d_levels, (const uint4*)t->d_cap, t->n, t->depth, cap_depth, t->cap_valid ? t->rank : 0u, d_idx, q, ctx->fmt,
-        (uint4*)d_states, ctx->d_err, (uint4*)d_sbox);
+        (uint4*)d_states, ctx->d_err, (uint4*)d_sbox, lead_slots);
     ++ctx->launches;
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
@@ -1077,6 +1080,104 @@ extern "C" imt_status imt_insert_witness_trace(imt_ctx* ctx, const imt_insert_wi
     if (new_low_leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(new_low_leaves, dnw.p, b * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (limbs) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limbs, dlm.p, b * 6 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     if (limbs && limb_flags) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limb_flags, dfl.p, b * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- verify_non_inclusion witness trace
+extern "C" size_t imt_non_inclusion_trace_hashes(unsigned depth) { return 1 + (size_t)depth; }
+
+// the 1 + depth traced hashes of `cq` queries whose low leaves are known (device arrays), into d_states[cq][1 + depth][fe per hash]:
+// the leaf hashes on the auxiliary stream beside the q x depth independent path hashes on the compute stream
+static imt_status non_inclusion_trace_chunk(imt_tree* t, const uint64_t* d_low, const void* d_low_leaves, size_t cq, void* d_states) {
+    imt_ctx* ctx = t->ctx;
+    const unsigned depth = t->depth;
+    Event forked, joined;
+    IMT_TRY_CUDA(ctx, forked.create());
+    IMT_TRY_CUDA(ctx, joined.create());
+    IMT_TRY_CUDA(ctx, cudaEventRecord(forked, ctx->stream));
+    IMT_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, forked, 0));
+    k_trace_hash<3><<<grid_for(cq, kHashThreads), kHashThreads, 0, ctx->aux_stream>>>((const uint4*)d_low_leaves, (uint4*)d_states, nullptr, cq, ctx->fmt,
+                                                                                    ctx->d_err, nullptr, 1 + (size_t)depth);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    imt_status st = IMT_OK;
+    if (e == cudaSuccess && depth) st = launch_tree_trace(t, d_low, cq, d_states, nullptr, 1);
+    cudaError_t e2 = cudaEventRecord(joined, ctx->aux_stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->stream, joined, 0);
+    if (e != cudaSuccess || e2 != cudaSuccess || st != IMT_OK) cudaStreamSynchronize(ctx->aux_stream);  // leave nothing behind on the auxiliary stream
+    IMT_TRY_CUDA(ctx, e);
+    IMT_TRY_CUDA(ctx, e2);
+    return st;
+}
+
+static imt_status non_inclusion_trace_args(imt_tree* t, const void* values, size_t q, const void* states) {
+    imt_ctx* ctx = t->ctx;
+    if (q && !values) return fail(ctx, IMT_ERR_INVALID_ARG, "null buffer");
+    if (states && ctx->generic) return fail(ctx, IMT_ERR_INVALID_ARG, "imt_non_inclusion_witness_trace supports the default Poseidon instance only");
+    if (!t->d_pre) return fail(ctx, IMT_ERR_INVALID_ARG, "tree was not built from leaves");
+    if (t->cap_valid || t->world > 1) return fail(ctx, IMT_ERR_INVALID_ARG, "imt_non_inclusion_witness_trace is a single-GPU call");
+    return IMT_OK;
+}
+
+extern "C" imt_status imt_non_inclusion_witness_trace_dev(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low_idx, uint8_t* d_matched,
+                                                          void* d_low_leaves, void* d_siblings, uint8_t* d_helpers, uint8_t* d_is_largest,
+                                                          void* d_limbs, uint8_t* d_limb_flags, void* d_states) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY(non_inclusion_trace_args(t, d_values, q, d_states));
+    if (q && (!d_low_idx || !d_low_leaves)) return fail(ctx, IMT_ERR_INVALID_ARG, "d_low_idx and d_low_leaves are required");
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(queue_non_inclusion(t, d_values, q, d_low_idx, d_matched, d_low_leaves, d_is_largest, d_siblings, d_helpers));
+    if (d_limbs) IMT_TRY(launch_limb_witness(ctx, d_low_leaves, d_values, 1, q, d_limbs, d_limb_flags));
+    if (d_states) IMT_TRY(non_inclusion_trace_chunk(t, d_low_idx, d_low_leaves, q, d_states));
+    return finish(ctx);
+}
+
+extern "C" imt_status imt_non_inclusion_witness_trace(imt_tree* t, const void* values, size_t q, uint64_t* low_idx, uint8_t* matched, void* low_leaves,
+                                                      void* siblings, uint8_t* helpers, uint8_t* is_largest, void* limbs, uint8_t* limb_flags,
+                                                      void* states) {
+    if (!t) return IMT_ERR_INVALID_ARG;
+    imt_ctx* ctx = t->ctx;
+    IMT_TRY(non_inclusion_trace_args(t, values, q, states));
+    if (q == 0) return IMT_OK;
+    IMT_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned depth = t->depth;
+    DevBuf dv(ctx), dl(ctx), dm(ctx), dlv(ctx), dsib(ctx), dhel(ctx), dlg(ctx), dlm(ctx), dfl(ctx);
+    IMT_TRY_CUDA(ctx, dv.alloc(q * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, dl.alloc(q * sizeof(uint64_t)));
+    IMT_TRY_CUDA(ctx, dm.alloc(q));
+    IMT_TRY_CUDA(ctx, dlv.alloc(q * 3 * sizeof(Fr)));
+    if (siblings) IMT_TRY_CUDA(ctx, dsib.alloc(q * (size_t)depth * sizeof(Fr)));
+    if (helpers) IMT_TRY_CUDA(ctx, dhel.alloc(q * (size_t)depth));
+    if (is_largest) IMT_TRY_CUDA(ctx, dlg.alloc(q));
+    if (limbs) IMT_TRY_CUDA(ctx, dlm.alloc(q * 6 * sizeof(Fr)));
+    if (limbs && limb_flags) IMT_TRY_CUDA(ctx, dfl.alloc(q * 3));
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(dv.p, values, q * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    IMT_TRY(clear_err(ctx));
+    IMT_TRY(queue_non_inclusion(t, dv.p, q, dl.as<uint64_t>(), dm.as<uint8_t>(), dlv.p, is_largest ? dlg.as<uint8_t>() : nullptr,
+                                siblings ? dsib.p : nullptr, helpers ? dhel.as<uint8_t>() : nullptr));
+    if (limbs) IMT_TRY(launch_limb_witness(ctx, dlv.p, dv.p, 1, q, dlm.p, (limbs && limb_flags) ? dfl.as<uint8_t>() : nullptr));
+    if (states) {  // 12 672 B per hash: chunks of queries through two device buffers, the copy stream draining one while the other is hashed
+        const size_t per_query = imt_non_inclusion_trace_hashes(depth) * trace_fe_per_hash(ctx, 2) * sizeof(Fr);
+        imt_status st = IMT_OK;
+        IMT_TRY(drain_chunks(ctx, q, per_query, states, [&](size_t off, size_t cq, void* d_buf) {
+            const imt_status s1 = non_inclusion_trace_chunk(t, dl.as<uint64_t>() + off, dlv.as<Fr>() + 3 * off, cq, d_buf);
+            if (s1 != IMT_OK) st = s1;
+        }));
+        IMT_TRY(st);
+    }
+    IMT_TRY(finish(ctx));
+    if (low_idx) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_idx, dl.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matched) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(matched, dm.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (low_leaves) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(low_leaves, dlv.p, q * 3 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (siblings && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(siblings, dsib.p, q * (size_t)depth * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (helpers && depth) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(helpers, dhel.p, q * (size_t)depth, cudaMemcpyDeviceToHost, ctx->stream));
+    if (is_largest) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(is_largest, dlg.p, q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (limbs) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limbs, dlm.p, q * 6 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    if (limbs && limb_flags) IMT_TRY_CUDA(ctx, cudaMemcpyAsync(limb_flags, dfl.p, q * 3, cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IMT_OK;
 }

@@ -924,6 +924,36 @@ imt_status launch_limb_witness(imt_ctx* ctx, const void* d_low_leaves, const voi
     IMT_TRY_CUDA(ctx, cudaGetLastError());
     return IMT_OK;
 }
+// lookup + gather of everything verify_non_inclusion loads about the low leaf, queued on the compute stream (no wait): the caller
+// has cleared the error word and calls finish(). d_low is required; the other outputs may be null.
+imt_status queue_non_inclusion(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low, uint8_t* d_matched, void* d_low_leaves,
+                               uint8_t* d_is_largest, void* d_siblings, uint8_t* d_helpers) {
+    imt_ctx* ctx = t->ctx;
+    if (sharded(t)) return fail(ctx, IMT_ERR_INVALID_ARG, "low-leaf lookups on a sharded tree go through the per-rank candidate call");
+    IMT_TRY(ensure_index(t));
+    if (q == 0) return IMT_OK;
+    DevBuf dm(ctx);
+    if (!d_matched) {  // the lookup kernels always write it
+        IMT_TRY_CUDA(ctx, dm.alloc(q));
+        d_matched = dm.as<uint8_t>();
+    }
+    IMT_TRY(lookup_dev(t, d_values, q, d_low, d_matched));
+    if (d_low_leaves || d_is_largest) {
+        k_gather_leaves<<<grid_for(q, 256), 256, 0, ctx->stream>>>((const uint4*)t->d_pre, t->n, 0, d_low, q, (uint4*)d_low_leaves, d_is_largest,
+                                                                   ctx->d_err);
+        ++ctx->launches;
+        IMT_TRY_CUDA(ctx, cudaGetLastError());
+    }
+    if ((d_siblings || d_helpers) && t->depth) {
+        DevBuf scratch(ctx);  // the gather kernel always writes siblings
+        if (!d_siblings) {
+            IMT_TRY_CUDA(ctx, scratch.alloc(q * (size_t)t->depth * sizeof(Fr)));
+            d_siblings = scratch.p;
+        }
+        IMT_TRY(launch_gather_proofs(t, d_low, q, d_siblings, d_helpers, nullptr));
+    }
+    return IMT_OK;
+}
 void invalidate_index(imt_tree* t) {  // the buffers are kept for the next build of the index
     t->index_valid = false;
     t->prefix_valid = false;

@@ -190,7 +190,8 @@ imt_status launch_gather_proofs(imt_tree* t, const uint64_t* d_idx, size_t q, vo
                                 bool select = false);
 
 // witness traces of the paths of a resident tree, queued on the compute stream (q x depth independent traced hashes)
-imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr);
+// lead_slots: hash slots left free in front of every query's path hashes in d_states (default instance only when non-zero)
+imt_status launch_tree_trace(imt_tree* t, const uint64_t* d_idx, size_t q, void* d_states, void* d_sbox = nullptr, unsigned lead_slots = 0);
 
 // one tree level, Montgomery in / out: d_dst[i] = H(d_src[2i], d_src[2i+1]); small levels take the cooperative kernel
 imt_status launch_level(imt_ctx* ctx, const imt::Fr* d_src, imt::Fr* d_dst, size_t nodes);
@@ -216,6 +217,9 @@ imt_status launch_limb_witness(imt_ctx* ctx, const void* d_low_leaves, const voi
                                uint8_t* d_flags);
 void invalidate_index(imt_tree* t);
 imt_status ensure_index(imt_tree* t);
+// lookup of q device values + everything verify_non_inclusion loads about their low leaves, queued on the compute stream (no wait)
+imt_status queue_non_inclusion(imt_tree* t, const void* d_values, size_t q, uint64_t* d_low, uint8_t* d_matched, void* d_low_leaves,
+                               uint8_t* d_is_largest, void* d_siblings, uint8_t* d_helpers);
 
 // ---- implemented in imt_comm.cu: collectives over the ranks of a group. Element i of every vector belongs to the group's
 // i-th LOCAL context (one entry in process-per-GPU mode, all ranks in single-process mode); every operation is queued on

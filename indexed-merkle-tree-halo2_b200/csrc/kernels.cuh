@@ -76,10 +76,12 @@ struct TraceSink {
     }
 };
 
+// hash i writes its states at hash slot i * slot_stride (1: dense; 1 + depth: the leaf hash in front of the path hashes of one query,
+// imt_non_inclusion_witness_trace); the S-box trace and the digests are always dense
 template <int ARITY>
 __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __restrict__ in, uint4* __restrict__ states,
                                                              uint4* __restrict__ digests, size_t n, int fmt,
-                                                             uint32_t* __restrict__ err, uint4* __restrict__ sbox) {
+                                                             uint32_t* __restrict__ err, uint4* __restrict__ sbox, size_t slot_stride = 1) {
     const size_t i = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (i >= n) return;
     uint32_t x[ARITY][8], d[8];
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_hash(const uint4* __rest
     }
     if (!ok) atomicOr(err, kErrNonCanonical);
     if (states) {
-        TraceSink sink{states + i * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + i * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
+        TraceSink sink{states + i * slot_stride * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + i * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
         hash_fixed<ARITY>(d, x, c_params, sink);
     } else {
         NoTrace nt;
@@ -216,7 +218,8 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* 
                                                                    size_t n_local, unsigned depth_local, unsigned cap_depth, unsigned rank,
                                                                    const uint64_t* __restrict__ idx, size_t q, int fmt,
                                                                    uint4* __restrict__ states, uint32_t* __restrict__ err,
-                                                                   uint4* __restrict__ sbox) {
+                                                                   uint4* __restrict__ sbox, unsigned lead_slots = 0) {
+    // lead_slots: hash slots left free in front of every query's path hashes (1: the traced leaf hash of verify_non_inclusion)
     const unsigned depth = depth_local + cap_depth;
     const size_t t = blockIdx.x * (size_t)kHashThreads + threadIdx.x;
     if (t >= q * depth) return;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(kHashThreads) k_trace_tree_paths(const uint4* 
     uint32_t x[2][8], d[8];
     load_fe(x[0], src);      // tree levels are Montgomery, canonical
     load_fe(x[1], src + 2);
-    TraceSink sink{states + t * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + t * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
+    TraceSink sink{states + (t + (qi + 1) * lead_slots) * (size_t)(kStatesPerHash * 3 * 2), fmt, sbox ? sbox + t * (size_t)(kSboxPerHash * 3 * 2) : nullptr};
     hash_fixed<2>(d, x, c_params, sink);
 }
 

@@ -582,6 +582,40 @@ class Tree:
                                                              _ptr(o["is_largest"])))
         return o
 
+    def trace_non_inclusion(self, values, out=None, out_states=None, states=True):
+        """imt_non_inclusion_witness_trace — the whole witness of the chip's verify_non_inclusion (indexed_merkle_tree.rs:127-229) for
+        every value in ONE call: the lookup, the low leaf + path + flags (as non_inclusion_paths), the 128-bit limb witnesses and the
+        Poseidon states of the 1 + depth hashes it constrains ([0] H3(low leaf), [1..depth] its fold up the path), shape
+        (q, 1 + depth, 132, 3, 4). Returns the non_inclusion_paths dict + limbs, limb_flags, states, leaf_hash (view), path (view)."""
+        v = _fe_array(values, ())
+        q, d = v.shape[0], self.depth
+        o = out if out is not None else self.non_inclusion_buffers(q, d)
+        if o["siblings"].shape != (q, d, 4) or o["low_idx"].shape != (q,):
+            raise ValueError("out buffers were made for another batch size / depth")
+        o = dict(o)
+        o["limbs"], flags = np.empty((q, 6, 4), np.uint64), np.empty((q, 3), np.uint8)
+        st = None
+        if states:
+            shape = (q, 1 + d, self.engine.states_per_hash(2), self.engine.t, 4)
+            st = out_states if out_states is not None else np.empty(shape, np.uint64)
+            if st.shape != shape or st.dtype != np.uint64 or not st.flags.c_contiguous:
+                raise ValueError(f"out_states must be a C-contiguous uint64 array of shape {shape}")
+        self.engine._check(self._lib.imt_non_inclusion_witness_trace(self._h, _ptr(v), q, _ptr(o["low_idx"]), _ptr(o["matched"]), _ptr(o["low_leaves"]),
+                                                                     _ptr(o["siblings"]), _ptr(o["helpers"]), _ptr(o["is_largest"]), _ptr(o["limbs"]),
+                                                                     _ptr(flags), _ptr(st)))
+        o["limb_flags"] = flags.astype(bool)
+        if st is not None:
+            o.update(states=st, leaf_hash=st[:, 0], path=st[:, 1:])
+        return o
+
+    def trace_non_inclusion_dev(self, d_values, q, d_low_idx, d_low_leaves, d_states, d_matched=None, d_siblings=None, d_helpers=None,
+                                d_is_largest=None, d_limbs=None, d_limb_flags=None):
+        """imt_non_inclusion_witness_trace_dev: CUDA tensors in and out (d_low_idx and d_low_leaves are required, the rest may be None)"""
+        opt = lambda t: _dev_ptr(t) if t is not None else None
+        self.engine._check(self._lib.imt_non_inclusion_witness_trace_dev(self._h, _dev_ptr(d_values), q, _dev_ptr(d_low_idx), opt(d_matched),
+                                                                         _dev_ptr(d_low_leaves), opt(d_siblings), opt(d_helpers), opt(d_is_largest),
+                                                                         opt(d_limbs), opt(d_limb_flags), opt(d_states)))
+
     @staticmethod
     def insert_buffers(b, depth, pinned=False, fold_nodes=True):
         """output buffers of insert_batch for b inserts (see non_inclusion_buffers for `pinned`). fold_nodes: also the chain values of

@@ -162,6 +162,19 @@ int main(void) {
     CHECK(imt_insert_witness_trace(ctx, &w, 6, 3, occupied, tr_states_loop, tr_roots_loop, NULL, NULL, NULL));
     trace_ok &= memcmp(tr_states, tr_states_loop, sizeof tr_states) == 0 && memcmp(tr_roots, tr_roots_loop, sizeof tr_roots) == 0;
     printf("insert_trace_ok %d\n", trace_ok);
+    /* the whole verify_non_inclusion witness of two values in one call (IMT:127-229): lookup, low leaf, path, limbs and the
+     * Poseidon states of H3(low leaf) + its fold up the path = 1 + depth traced hashes per value */
+    const uint64_t ni_vals[2 * 4] = {25, 0, 0, 0, 60, 0, 0, 0};
+    uint64_t ni_low[2], ni_leaves[2 * 12], ni_sib[2 * 3 * 4], ni_limbs[2 * 6 * 4];
+    uint8_t ni_matched[2], ni_largest[2], ni_flags[2 * 3];
+    static uint64_t ni_states[2 * 4 * 132 * 3 * 4];
+    CHECK(imt_non_inclusion_witness_trace(tree, ni_vals, 2, ni_low, ni_matched, ni_leaves, ni_sib, NULL, ni_largest, ni_limbs, ni_flags, ni_states));
+    CHECK(imt_tree_root(tree, root));
+    int ni_ok = imt_non_inclusion_trace_hashes(3) == 4 && ni_low[0] == li && memcmp(ni_leaves, ll, sizeof ll) == 0 && memcmp(ni_sib, sib, sizeof sib) == 0;
+    for (int i = 0; i < 2; ++i) /* the last state of the last hash holds the root in element 1 */
+        ni_ok &= memcmp(ni_states + ((((size_t)i * 4 + 3) * 132 + 131) * 3 + 1) * 4, root, 32) == 0 && ni_matched[i] == 1 && ni_flags[3 * i + 2] == 1;
+    ni_ok &= ni_largest[0] == 0 && ni_largest[1] == 1 && ni_leaves[12] == 50; /* 60 goes behind the largest value, 50 */
+    printf("non_inclusion_trace_ok %d\n", ni_ok);
     imt_tree_destroy(tree);
     imt_ctx_destroy(ctx);
     return 0;

@@ -133,6 +133,16 @@ static void test_insert_leaf_multiple_round() {
         h.update({ni.low_leaves[0].val, ni.low_leaves[0].next_val, ni.low_leaves[0].next_idx});
         REQUIRE(batched.verify_proof(h.squeeze_and_reset(), ni.low_idx[0], batched.get_root(), ni.low_proof[0]));
     }
+    {   // the same witnesses + the Poseidon states of the 1 + depth hashes verify_non_inclusion constrains, one call (IMT:127-229)
+        std::vector<Fr> states;
+        auto nt = batched.non_inclusion_witness_trace({Fr::from(25), Fr::from(60), Fr::from(20)}, &states);
+        REQUIRE(nt.low_idx == ni.low_idx && nt.low_proof == ni.low_proof && nt.low_proof_helper == ni.low_proof_helper && nt.limbs == ni.limbs);
+        REQUIRE(nt.valid == ni.valid && nt.is_new_leaf_largest == ni.is_new_leaf_largest);
+        const size_t per_hash = states.size() / (3 * (3 + 1));       // depth 3: 4 hashes per value
+        REQUIRE(per_hash == 132 * 3);
+        for (size_t i = 0; i < 3; ++i)                               // the last state of the last hash carries the root in element 1
+            REQUIRE(states[(i * 4 + 3) * per_hash + 131 * 3 + 1] == batched.get_root());
+    }
     const std::vector<IMTLeaf> fin = batched.preimages();
     for (size_t i = 0; i < tree_size; ++i)
         std::printf("multiple_round final %zu %llu %llu %llu\n", i, (unsigned long long)fin[i].val.l[0], (unsigned long long)fin[i].next_val.l[0],

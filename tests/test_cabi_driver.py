@@ -62,3 +62,4 @@ def test_c_client_runs_the_reference_scenario():
     assert lines[22] == "checkpoint n 8 depth 3 same_root 1 same_leaves 1 header_root 1"
     assert lines[23].startswith("corrupt checkpoint: 6 ") and "corrupt" in lines[23]      # IMT_ERR_INVALID_ARG, root mismatch
     assert lines[24] == "insert_trace_ok 1"
+    assert lines[25] == "non_inclusion_trace_ok 1"

@@ -161,6 +161,89 @@ def test_non_inclusion_witnesses(eng):
     assert ok.all()
 
 
+def test_non_inclusion_witness_trace_one_call(eng, eng_mont):
+    """imt_non_inclusion_witness_trace: the whole witness of verify_non_inclusion (IMT:127-229) in one call — the values of
+    imt_non_inclusion_paths, the hi/lo limbs (IMT:143-172, 206-222) and the Poseidon states of H3(low leaf) (IMT:193-194) and of its
+    fold up the path (IMT:196-204), every state against the oracle's trace; absent, present (unmatched) and zero values; both formats."""
+    depth, m = 7, 90
+    n = 1 << depth
+    pre = synth.indexed_preimages(n, m, seed=77)
+    vals = np.concatenate([synth.field_elements(40, seed=78), pre[3:6, 0], np.zeros((1, 4), np.uint64)])   # absent, present, zero
+    for e, enc, dec in ((eng, lambda a: a, lambda a: a), (eng_mont, to_mont, from_mont)):
+        tree = e.build_from_leaves(enc(pre))
+        o = tree.trace_non_inclusion(enc(vals))
+        ref = tree.non_inclusion_paths(enc(vals))
+        for k in ("low_idx", "matched", "low_leaves", "siblings", "helpers", "is_largest"):
+            assert np.array_equal(o[k], ref[k]), k
+        limbs, flags = e.non_inclusion_limbs(o["low_leaves"], enc(vals))
+        assert np.array_equal(o["limbs"], limbs) and np.array_equal(o["limb_flags"], flags)
+        for k in range(len(vals)):                                                 # the reference's literal scan, quirks included (IMT:632-660)
+            assert (int(o["low_idx"][k]), bool(o["matched"][k])) == O.low_leaf(pre, vals[k]), k
+        assert o["matched"][:40].all() and o["limb_flags"][:40, 2].all() and not o["matched"][-1] and not o["limb_flags"][-1, 2]
+        root = dec(tree.root())
+        for k in list(range(0, 40, 7)) + [40, 43]:
+            wl = int(o["low_idx"][k])
+            h, ws = O.hash_trace(dec(o["low_leaves"][k]))
+            assert np.array_equal(dec(o["leaf_hash"][k]), ws), k
+            idx, sib = wl, dec(o["siblings"][k])
+            for lvl in range(depth):
+                pair = np.stack([h, sib[lvl]]) if idx % 2 == 0 else np.stack([sib[lvl], h])
+                h, ws = O.hash_trace(pair)
+                assert np.array_equal(dec(o["path"][k, lvl]), ws), (k, lvl)
+                idx //= 2
+            assert np.array_equal(h, root)
+        # values only (no states), and the same bytes as the tree-path trace + the leaf-hash trace composed by hand
+        lite = tree.trace_non_inclusion(enc(vals), states=False)
+        assert "states" not in lite and np.array_equal(lite["limbs"], o["limbs"]) and np.array_equal(lite["siblings"], o["siblings"])
+        assert np.array_equal(o["path"], tree.trace_proofs(o["low_idx"]))
+    with pytest.raises(imt_b200.ImtError) as err:                                  # a value >= p
+        tree.trace_non_inclusion(np.full((1, 4), 0xFFFFFFFFFFFFFFFF, np.uint64))
+    assert err.value.status == _ffi.ERR_NON_CANONICAL
+
+
+def test_non_inclusion_witness_trace_depth20_chunked_pipeline(eng_mont):
+    """the host call streams (1 + depth) x 12 672 B per query out in chunks behind the hashing: 20 000 queries at depth 20 (5.3 GB, three
+    chunks) equal the device-resident call, and sampled queries equal the oracle's trace"""
+    import torch
+    depth, q = 20, 20000
+    n = 1 << depth
+    dev = torch.device("cuda", 0)
+    e = eng_mont
+    d_pre = synth.indexed_preimages_torch(n, n - 5, device=dev)
+    d_pre_m = torch.empty_like(d_pre)
+    e.convert_dev(d_pre, 3 * n, d_pre_m, to_montgomery=True)
+    tree = e.build_from_leaves_dev(d_pre_m, n)
+    d_vals = synth.field_elements_torch(q, seed=4321, device=dev)
+    d_vals_m = torch.empty_like(d_vals)
+    e.convert_dev(d_vals, q, d_vals_m, to_montgomery=True)
+    vals_m = d_vals_m.cpu().numpy().view(np.uint64)
+    o = tree.trace_non_inclusion(vals_m)
+    d_low = torch.empty(q, dtype=torch.int64, device=dev)
+    d_leaves = torch.empty((q, 3, 4), dtype=torch.int64, device=dev)
+    d_states = torch.empty((q, 1 + depth, 132, 3, 4), dtype=torch.int64, device=dev)
+    launches = e.launches
+    tree.trace_non_inclusion_dev(d_vals_m, q, d_low, d_leaves, d_states)
+    assert e.launches - launches <= 4                                              # lookup, leaf gather, leaf-hash trace, path trace
+    assert np.array_equal(d_low.cpu().numpy().astype(np.uint64), o["low_idx"])
+    assert np.array_equal(d_leaves.cpu().numpy().view(np.uint64), o["low_leaves"])
+    for lo in range(0, q, 4000):                                                   # compare in slices: 5.3 GB each side
+        assert np.array_equal(d_states[lo:lo + 4000].cpu().numpy().view(np.uint64), o["states"][lo:lo + 4000]), lo
+    root = from_mont(tree.root())
+    for k in (0, 8191, 8192, q - 1):                                               # chunk edges
+        h, ws = O.hash_trace(from_mont(o["low_leaves"][k]))
+        assert np.array_equal(from_mont(o["leaf_hash"][k].reshape(-1, 4)).reshape(132, 3, 4), ws), k
+        idx, sib = int(o["low_idx"][k]), from_mont(o["siblings"][k])
+        for lvl in range(depth):
+            pair = np.stack([h, sib[lvl]]) if idx % 2 == 0 else np.stack([sib[lvl], h])
+            if lvl in (0, 9, depth - 1):
+                h, ws = O.hash_trace(pair)
+                assert np.array_equal(from_mont(o["path"][k, lvl].reshape(-1, 4)).reshape(132, 3, 4), ws), (k, lvl)
+            else:
+                h = O.hash2(pair.reshape(1, 2, 4), 1)[0]
+            idx //= 2
+        assert np.array_equal(h, root)
+
+
 @pytest.mark.parametrize("depth,m,b,chunk", [(6, 10, 40, None), (10, 512, 300, 128), (13, 3000, 4200, None), (13, 3000, 4200, 4096)])
 def test_insert_batch_matches_sequential_oracle(eng, depth, m, b, chunk, monkeypatch):
     """b inserts in one call against the oracle advancing one insert at a time; then the device state (preimages, every
