@@ -64,7 +64,11 @@ const char* imt_status_string(imt_status st);
 uint64_t imt_ctx_launch_count(const imt_ctx* ctx);
 /* Launch on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of the context's own
  * non-blocking stream, so that callers can bracket calls with their own events and order them against NCCL. NULL is
- * the CUDA legacy default stream. imt_ctx_reset_stream returns to the internal stream. */
+ * the CUDA legacy default stream. imt_ctx_reset_stream returns to the internal stream.
+ * Device buffers passed to the _dev calls are read and written ON THE CONTEXT'S STREAM, which by default is not ordered against any
+ * other stream: inputs produced on another stream (and every earlier use of recycled memory behind the outputs — a caching allocator
+ * may hand out a block whose previous users are still queued on ITS stream) must be complete before the call, or the caller shares
+ * its stream with the context through this function. Every call returns with its own work finished. */
 imt_status imt_ctx_set_stream(imt_ctx* ctx, void* cuda_stream);
 imt_status imt_ctx_reset_stream(imt_ctx* ctx);
 /* Tree and scratch buffers are stream-ordered allocations from a memory pool that belongs to the context (the device's default

@@ -80,6 +80,14 @@ def indexed_preimages(n, occupied=None, seed=DEFAULT_SEED):
     return pre
 
 
+def _settle(torch, device):
+    """The engine launches on its OWN non-blocking stream: a tensor handed to it must be complete, and — subtler — every torch kernel
+    queued before must have finished with its temporaries, because a later torch.empty() may reuse their memory (safe on torch's
+    stream, not for a writer on another stream). The synthetic-input helpers therefore return settled tensors."""
+    if str(device) != "cpu":
+        torch.cuda.synchronize(device)
+
+
 def field_elements_torch(n, seed=DEFAULT_SEED, first=0, device="cuda"):
     """Same stream as field_elements(), generated with torch integer ops on `device`: (n, 4) int64 (bit pattern =
     uint64). Setup helper for bench.py so that 2^24 x 3 elements need no host round trip."""
@@ -126,7 +134,9 @@ def field_elements_torch(n, seed=DEFAULT_SEED, first=0, device="cuda"):
             out.append(torch.where(ge, t2, a))
             borrow = b1 | b2
         chunks.append(torch.stack(out, dim=1))
-    return torch.cat(chunks, dim=0).contiguous() if chunks else torch.zeros((0, 4), dtype=torch.int64, device=device)
+    out = torch.cat(chunks, dim=0).contiguous() if chunks else torch.zeros((0, 4), dtype=torch.int64, device=device)
+    _settle(torch, device)
+    return out
 
 
 def indexed_preimages_torch(n, occupied=None, seed=DEFAULT_SEED, device="cuda"):
@@ -137,6 +147,7 @@ def indexed_preimages_torch(n, occupied=None, seed=DEFAULT_SEED, device="cuda"):
     assert 1 <= m <= n
     pre = torch.zeros((n, 3, 4), dtype=torch.int64, device=device)
     if m == 1:
+        _settle(torch, device)
         return pre
     vals = field_elements_torch(m - 1, seed, device=device)
     MIN = -(1 << 63)
@@ -153,4 +164,5 @@ def indexed_preimages_torch(n, occupied=None, seed=DEFAULT_SEED, device="cuda"):
     pre[0, 2, 0] = slots[0]
     pre[slots[:-1], 1] = sv[1:]
     pre[slots[:-1], 2, 0] = slots[1:]
+    _settle(torch, device)
     return pre

@@ -661,6 +661,7 @@ def test_insert_witness_trace_depth24_batch_4096_sampled_against_the_oracle(eng_
     S = 3 + 4 * depth
     d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
     d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()                                                   # the engine runs on its own stream: inputs must be complete
     e.trace_insert_witness_dev({k: v for k, v in dw.items() if k != "fold_nodes"}, b, depth, m, d_states, d_roots)   # level loop
     d_states_1, d_roots_1 = torch.zeros_like(d_states), torch.zeros_like(d_roots)
     torch.cuda.synchronize()                                                   # the fills run on torch's stream, the library on its own

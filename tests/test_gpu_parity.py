@@ -395,6 +395,7 @@ def test_trace_2p16_paths_of_the_depth20_tree_sampled_against_the_oracle(eng):
     dev = torch.device("cuda", 0)
     d_idx = torch.from_numpy(idx.view(np.int64)).to(dev)
     d_states = torch.empty((q, depth, 132, 3, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()                                                  # the engine runs on its own stream: inputs must be complete
     tree.trace_proofs_dev(d_idx, q, d_states)
     d_root = torch.from_numpy(levels[-1].view(np.int64).copy()).to(dev)
     assert bool((d_states[:, -1, -1, 1] == d_root).all())                     # every one of the 65 536 folds ends in the root
