@@ -23,6 +23,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "imt_b200.h"
@@ -529,15 +530,36 @@ namespace {
 imt_status mtree_rebuild(imt_mtree* mt, const void* preimages) {
     imt_group* g = &mt->m->g;
     const size_t n_local = mt->n_total / g->world;
-    // queue every device's pipeline first (H2D chunks + leaf kernels + levels are all asynchronous), THEN wait: the N builds overlap
+    // queue every device's pipeline first (H2D chunks + leaf kernels + levels are all asynchronous), THEN wait: the N builds overlap.
+    // Host leaves: one host thread per device. From page-locked memory the copies are asynchronous and one thread would do, but from
+    // pageable memory (a Rust Vec<F>) every cudaMemcpyAsync returns only after its chunk is staged — one thread would feed the devices
+    // one after the other (device 7 starting 7 x 190 MB of staging late at depth 24) instead of all links at once.
     imt_status st = IMT_OK;
-    for (unsigned i = 0; i < g->world && st == IMT_OK; ++i) {
-        if (preimages) st = enqueue_rebuild(mt->shards[i], static_cast<const char*>(preimages) + (size_t)i * n_local * 3 * sizeof(Fr), false);
-        else st = enqueue_rebuild(mt->shards[i], mt->shards[i]->d_pre, true);
-    }
-    for (unsigned i = 0; i < g->world && preimages; ++i) {
-        const imt_status s2 = wait_staging(g->ctxs[i]);
-        if (st == IMT_OK) st = s2;
+    if (preimages && g->world > 1) {
+        std::vector<imt_status> sts(g->world, IMT_OK);
+        std::vector<std::thread> th;
+        th.reserve(g->world);
+        for (unsigned i = 0; i < g->world; ++i)
+            th.emplace_back([&, i] {
+                sts[i] = enqueue_rebuild(mt->shards[i], static_cast<const char*>(preimages) + (size_t)i * n_local * 3 * sizeof(Fr), false);
+                const imt_status s2 = wait_staging(g->ctxs[i]);  // also after a failed enqueue: nothing may still read the caller's buffer
+                if (sts[i] == IMT_OK) sts[i] = s2;
+            });
+        for (auto& x : th) x.join();
+        for (unsigned i = 0; i < g->world; ++i)
+            if (sts[i] != IMT_OK && st == IMT_OK) {
+                st = sts[i];
+                if (i) g->ctxs[0]->last_error = g->ctxs[i]->last_error;
+            }
+    } else {
+        for (unsigned i = 0; i < g->world && st == IMT_OK; ++i) {
+            if (preimages) st = enqueue_rebuild(mt->shards[i], static_cast<const char*>(preimages) + (size_t)i * n_local * 3 * sizeof(Fr), false);
+            else st = enqueue_rebuild(mt->shards[i], mt->shards[i]->d_pre, true);
+        }
+        for (unsigned i = 0; i < g->world && preimages; ++i) {
+            const imt_status s2 = wait_staging(g->ctxs[i]);
+            if (st == IMT_OK) st = s2;
+        }
     }
     if (st == IMT_OK) st = exchange_roots(g, mt->shards);
     if (st != IMT_OK)
