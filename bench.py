@@ -517,30 +517,41 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     q, b = 1 << 20, 4096
     n = 1 << depth
     m = n - b * (steps + 3)
-    ec = eng if eng.fmt == 0 else None
-    import imt_b200
-    own = ec is None
-    if own:
-        ec = imt_b200.Engine(eng.device, "canonical")
-        ec.set_stream(stream.cuda_stream)
-    d_pre = synth.indexed_preimages_torch(n, m, device=dev)
+    # the whole leg runs in the engine's own format — Montgomery in the default run: what a halo2 host holds its field elements in
+    # (zero-copy), and traces then need no from_mont per traced state element. The oracle's scan gets canonical host copies.
+    mont = eng.fmt == 1
+    ec = eng
+
+    def in_fmt(d_canonical):
+        if not mont:
+            return d_canonical
+        out_ = torch.empty_like(d_canonical)
+        eng.convert_dev(d_canonical, d_canonical.numel() // 4, out_, to_montgomery=True)
+        return out_
+
+    d_pre_c = synth.indexed_preimages_torch(n, m, device=dev)
+    h_pre = d_pre_c.cpu().numpy().view(np.uint64)
+    d_pre = in_fmt(d_pre_c)
+    del d_pre_c
     tree = ec.build_from_leaves_dev(d_pre, n)
     t0 = time.perf_counter()
     assert tree.occupied == m
     t_index = time.perf_counter() - t0
-    d_vals = synth.field_elements_torch(q, seed=555, device=dev)
+    d_vals_c = synth.field_elements_torch(q, seed=555, device=dev)
+    h_vals = d_vals_c[:3].cpu().numpy().view(np.uint64)
+    d_vals = in_fmt(d_vals_c)
+    del d_vals_c
     d_low = torch.empty(q, dtype=torch.int64, device=dev)
     d_match = torch.empty(q, dtype=torch.uint8, device=dev)
     l0 = ec.launches
     t_lookup = _ev_time(torch, stream, lambda: tree.low_leaf_lookup_dev(d_vals, q, d_low, d_match), steps, 2)
     launches = (ec.launches - l0) // (steps + 2)
     assert bool(d_match.all())
-    h_pre = d_pre.cpu().numpy().view(np.uint64)
-    h_vals = d_vals[:3].cpu().numpy().view(np.uint64)
     t0 = time.perf_counter()
     for k in range(3):                                                           # the reference's literal scan (IMT:632-660), the oracle
         assert (int(d_low[k]), True) == O.low_leaf(h_pre, h_vals[k])
     cpu_lookup = 3 / (time.perf_counter() - t0)
+    del h_pre
     bufs = tree.non_inclusion_buffers(q, depth, pinned=True)
     h_q = torch.empty((q, 4), dtype=torch.int64, pin_memory=True)
     h_q.copy_(d_vals)
@@ -567,6 +578,8 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     next_slot, ins = m, []
     for s_ in range(steps + 2):
         vals = synth.field_elements(b, seed=9000 + s_)
+        if mont:
+            vals = ec.convert(vals, to_montgomery=True)
         t0 = time.perf_counter()
         w = tree.insert_batch(vals, first_idx=next_slot, out=ins_out)
         ins.append(time.perf_counter() - t0)
@@ -579,27 +592,16 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
     S = 3 + 4 * depth
     d_states = torch.empty((b, S, 132, 3, 4), dtype=torch.int64, device=dev)
     d_roots = torch.empty((b, 4, 4), dtype=torch.int64, device=dev)
-    # traced in the format a halo2 host holds its field elements in (Montgomery, zero-copy): the canonical context would add one
-    # from_mont per traced state element (396 per hash, +12 % multiply work)
     et = ec
-    if eng.fmt == 1:
-        et = eng
-        for k, v in list(dw.items()):
-            if k != "low_idx":
-                mv = torch.empty_like(v)
-                eng.convert_dev(v, v.numel() // 4, mv, to_montgomery=True)
-                dw[k] = mv
-        torch.cuda.synchronize()
-    root_of = (lambda a: a) if et is ec else (lambda a: ec.convert(a, to_montgomery=True))
     # one launch: the chain values of the four folds came with the insert batch (imt_insert_witness::fold_nodes)
     t_wt = _ev_time(torch, stream, lambda: et.trace_insert_witness_dev(dw, b, depth, next_slot - b, d_states, d_roots), 2, 1)
-    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), root_of(w["new_roots"]))
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
     sample_one = d_states[:: max(1, b // 64)].clone()
     # without them: 1 + depth dependent launches of 4b traced hashes (hash latency)
     dw_loop = {k: v for k, v in dw.items() if k != "fold_nodes"}
     t_wt_loop = _ev_time(torch, stream, lambda: et.trace_insert_witness_dev(dw_loop, b, depth, next_slot - b, d_states, d_roots), 2, 1)
     assert torch.equal(sample_one, d_states[:: max(1, b // 64)]), "one-launch trace != level-loop trace"
-    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), root_of(w["new_roots"]))
+    assert np.array_equal(d_roots[:, 3].cpu().numpy().view(np.uint64), w["new_roots"])
     hbm = _peaks().get("hbm_gbs", 6650.0)
     probes = max(1, m.bit_length())
     out = {
@@ -621,12 +623,10 @@ def secondary_lookups(torch, eng, depth, dev, stream, steps):
                                                     "note": "the same call without fold_nodes: 1 + depth dependent launches"}}},
         "non_inclusion_trace": {"call": "imt_non_inclusion_witness_trace_dev (lookup + low leaf + limbs + the 1 + depth traced hashes of verify_non_inclusion)",
                                 "queries": qt, "hashes": qt * (1 + depth), "ms": t_nit, "hashes_per_s": qt * (1 + depth) / (t_nit * 1e-3),
-                                "fe_format": "canonical (one from_mont per traced state element; Montgomery contexts skip it)"},
-        "index_build_s": t_index,
+                                "fe_format": "montgomery" if mont else "canonical (one from_mont per traced state element; Montgomery contexts skip it)"},
+        "index_build_s": t_index, "fe_format": "montgomery" if mont else "canonical",
     }
     tree.close()
-    if own:
-        ec.close()
     return out
 
 
