@@ -739,3 +739,68 @@ def test_fast_lookup_equals_plain_search_and_the_linear_scan(monkeypatch):
             assert (int(low2[k]) if matched2[k] else 0, bool(matched2[k])) == (w[0] if w[1] else 0, w[1]), (fast_min, k)
         tree.close()
     e.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_operation_sequences_against_the_oracle(eng, eng_mont, seed, tmp_path, monkeypatch):
+    """Model-based test of the persistent device state: a random sequence of insert batches (random sizes, internal
+    chunks forced small so that batches cross chunk boundaries), lookups, traced non-inclusion witnesses, checkpoint save + load,
+    rebuilds from the current leaves and insert-trace calls — after every step the device tree equals the oracle advancing one
+    insert at a time (IMT:710-741), and every answer equals the reference's literal scan (IMT:632-660)."""
+    rng = random.Random(seed)
+    depth = 8
+    n = 1 << depth
+    m = rng.randrange(1, 6)
+    pre = synth.indexed_preimages(n, m, seed=100 + seed)
+    e, enc, dec = (eng, lambda a: a, lambda a: a) if seed % 2 else (eng_mont, to_mont, from_mont)
+    monkeypatch.setenv("IMT_INSERT_CHUNK", str(rng.choice([3, 8, 64])))
+    tree = e.build_from_leaves(enc(pre))
+    st = O.InsertState(pre, threads=2)
+    occupied = m
+    fresh = iter(synth.field_elements(800, seed=500 + seed))
+    for step in range(14):
+        op = rng.choice(["insert", "insert", "lookup", "trace", "checkpoint", "rebuild", "insert_trace"])
+        if op in ("insert", "insert_trace") and occupied < n - 40:
+            b = rng.randrange(1, 33)
+            vals = np.stack([next(fresh) for _ in range(b)])
+            got = tree.insert_batch(enc(vals), occupied)
+            for k in range(b):
+                want = st.insert(vals[k], occupied + k, incremental=True)
+                for g, wk in zip(GPU, WIT):
+                    a = got[g][k]
+                    assert np.array_equal(dec(a) if np.asarray(a).dtype == np.uint64 and g != "low_idx" else a, want[wk]), (step, k, g)
+            if op == "insert_trace":
+                tr = e.trace_insert_witness(got, occupied)
+                assert np.array_equal(tr["new_root"], got["new_roots"]) and np.array_equal(tr["zero_leaf_root"], tr["interim_root"])
+                k = rng.randrange(b)
+                assert np.array_equal(dec(got["fold_nodes"][k]), oracle_fold_nodes(got, k, occupied + k, dec))
+            occupied += b
+        elif op == "lookup":
+            present = [st.pre[rng.randrange(1, occupied), 0] for _ in range(3)] if occupied > 1 else []
+            qs = np.stack([next(fresh) for _ in range(5)] + present + [np.zeros(4, np.uint64)])
+            low, matched = tree.low_leaf_lookup(enc(qs))
+            for k in range(len(qs)):
+                assert (int(low[k]), bool(matched[k])) == O.low_leaf(st.pre, qs[k]), (step, k)
+        elif op == "trace":
+            qs = np.stack([next(fresh) for _ in range(3)])
+            o = tree.trace_non_inclusion(enc(qs))
+            for k in range(3):
+                wl, wm = O.low_leaf(st.pre, qs[k])
+                assert (int(o["low_idx"][k]), bool(o["matched"][k])) == (wl, wm)
+                assert np.array_equal(dec(o["low_leaves"][k]), st.pre[wl])
+                h, ws = O.hash_trace(st.pre[wl])
+                assert np.array_equal(dec(o["leaf_hash"][k]), ws)
+                assert np.array_equal(dec(o["states"][k, -1, -1, 1]), st.root())          # the fold ends in the current root
+        elif op == "checkpoint":
+            path = str(tmp_path / f"t{step}.imt")
+            tree.save(path)
+            tree.close()
+            tree = e.load_tree(path)
+        elif op == "rebuild":
+            tree.rebuild_from_leaves(enc(st.pre))
+        assert np.array_equal(dec(tree.root()), st.root()), (step, op)
+        assert tree.occupied == occupied
+    assert np.array_equal(dec(tree.preimages(n)), st.pre)
+    want_levels = O.levels(st.tree, n)
+    for lvl in range(depth + 1):
+        assert np.array_equal(dec(tree.level(lvl, n >> lvl)), want_levels[lvl]), lvl
