@@ -348,6 +348,43 @@ def test_depth24_roots_match_golden(eng):
     assert t.occupied == n
 
 
+def test_depth26_build_composes_from_depth24_subtrees(eng):
+    """Beyond the headline size (4x the BASELINE depth-24 tree: 2^26 leaves, 134 217 727 hashes, 6 GiB of preimages): no oracle
+    root exists at this size, so the check is the size-independent composition property of utils.rs:41-51 — the root of the
+    whole tree is H2(H2(r0, r1), H2(r2, r3)) of the roots of its four contiguous depth-24 quarters (each built on its own,
+    the two cap levels recomputed by the ORACLE on the CPU) — plus paths of the first / last / random leaves (indices beyond
+    2^24 and the top helper bits) verified on the GPU and, for two of them, folded by the oracle."""
+    import torch
+    depth = 26
+    n, q = 1 << depth, 1 << 24
+    d_pre = synth.field_elements_torch(3 * n, seed=26, device="cuda").view(n, 3, 4)
+    torch.cuda.synchronize()
+    whole = eng.build_from_leaves_dev(d_pre, n)
+    assert whole.depth == depth and whole.num_leaves == n
+    root = whole.root()
+    quarter = eng.build_from_leaves_dev(d_pre[:q], q)
+    roots = [quarter.root()]
+    for k in range(1, 4):
+        quarter.rebuild_from_leaves_dev(d_pre[k * q:(k + 1) * q])
+        roots.append(quarter.root())
+    r = np.stack(roots)
+    mid = O.hash2(r.reshape(4, 4), 1)            # H2(r0, r1), H2(r2, r3) on the CPU
+    assert np.array_equal(O.hash2(mid.reshape(2, 4), 1)[0], root)
+    assert np.array_equal(whole.level(24, 4), r)
+    rng = np.random.default_rng(26)
+    idx = np.concatenate([[0, n - 1, q, q - 1, 3 * q + 12345], rng.integers(0, n, 59)]).astype(np.uint64)
+    sib, hel = whole.get_proofs(idx)
+    pre = d_pre[torch.from_numpy(idx.astype(np.int64)).cuda()].cpu().numpy().view(np.uint64)
+    leaf_hashes = O.hash3(pre, 8)
+    assert eng.verify_proofs(leaf_hashes, idx, root, sib).all()
+    assert np.array_equal(hel, ((idx[:, None] >> np.arange(depth, dtype=np.uint64)[None, :]) & np.uint64(1)) == 0)
+    for k in (1, 4):
+        assert O.verify_proof(leaf_hashes[k], int(idx[k]), root, sib[k])
+    bad = sib.copy()
+    bad[1, depth - 1, 0] ^= np.uint64(1)
+    assert not eng.verify_proofs(leaf_hashes[1:2], idx[1:2], root, bad[1:2])[0]
+
+
 def test_verify_rejects_a_root_encoded_as_root_plus_p(eng):
     """a root given as root + p (still < 2^256) must not fold onto its canonical twin: every verify path — the
     3-lanes-per-path kernel (q <= 8192), the thread-per-path kernel (q > 8192) and the any-width kernels — reports
