@@ -1,9 +1,10 @@
 // The LATENCY kernels of the library (3 lanes per hash, poseidon_coop.cuh) in their own translation unit, because they want
 // another carry discipline than the thread-per-hash kernels of imt_capi.cu (-DIMT_FREE_MASK, see fr.cuh): the levels near the
 // root of a tree, the levels of an insert batch, small hash batches and small path folds run ONE warp per scheduler, where what
-// counts is the dependent-issue latency of a single instruction stream. A multiply-accumulate chain strung through the carry flag
-// issues one IMAD.WIDE.X every 7.05 cycles (through the accumulator it would be 3.35, independent 2.3: tools/lab/latency_lab.cu);
-// a chain whose head does not read the flag may overlap the previous one. All 32 head masks were swept on a B200
+// counts is the length of a single instruction stream: ONE warp issues an IMAD.WIDE every ~7 cycles whatever its dependencies
+// (tools/lab/issue_probe.cu; ptxas schedules for 4), and with every chain strung through the carry flag the IADD3.X / predicate
+// instructions around the multiplies do not hide in the idle issue slots between them (tools/lab/latency_lab.cu). A chain whose
+// head does not read the flag may be moved across the previous one. All 32 head masks were swept on a B200
 // (profiles/r02_latency_lab.md): one level of <= 4096 nodes takes 283 us with every chain serialised (round 1), 233 us with mask
 // 29 (here), 240 us with mask 22 (the best mask for the thread-per-hash kernels, where 7 warps share a scheduler and the carry
 // predicates of too many open chains spill: mask 31 = everything free costs them 8 %).
