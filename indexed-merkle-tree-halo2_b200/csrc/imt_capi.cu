@@ -84,7 +84,7 @@ imt_status launch_hash_t(imt_ctx* ctx, const void* d_in, void* d_out, size_t n, 
         IMT_TRY_CUDA(ctx, cudaEventRecord(tm.a, s));
     }
     if (n * concurrent <= coop_max_nodes())  // too few hashes to fill the GPU: spend lanes on latency (poseidon_coop.cuh, imt_latency.cu)
-        launch_hash_coop(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s);
+        launch_hash_coop(ctx, ARITY, d_in, d_out, n, in_fmt, out_fmt, s, concurrent);
     else
         k_hash<ARITY><<<grid_for(n, kHashThreads), kHashThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt,
                                                                       ctx->d_err);
@@ -317,27 +317,34 @@ extern "C" const char* imt_status_string(imt_status st) {
     return "unknown status";
 }
 
-// Both kernel families hash the same inputs at context creation and must agree bit for bit: the thread-per-hash kernels and the
-// 3-lanes-per-hash kernels are two compilations of one field source under two carry disciplines (fr.cuh IMT_FREE_MASK), and a
-// toolchain that mis-schedules one of them must not go unnoticed (0.6 ms, once per context).
+// The kernel families hash the same inputs at context creation and must agree bit for bit: the thread-per-hash kernels, the
+// 3-lanes-per-hash kernels and the lead / helper kernels are compilations of one field source under two carry disciplines (fr.cuh
+// IMT_FREE_MASK) and three schedules, and a toolchain that mis-schedules one of them must not go unnoticed (~1 ms, once per context).
+// 29 hashes: more than two blocks of the lead / helper kernel, the last one partly filled.
 static imt_status self_test(imt_ctx* ctx, const PoseidonParams& hp) {
-    constexpr size_t kN = 8;
+    constexpr size_t kN = 29;
     DevBuf in(ctx), out(ctx);
     IMT_TRY_CUDA(ctx, in.alloc(3 * kN * sizeof(Fr)));
-    IMT_TRY_CUDA(ctx, out.alloc(4 * kN * sizeof(Fr)));
+    IMT_TRY_CUDA(ctx, out.alloc(6 * kN * sizeof(Fr)));
+    static_assert(3 * kN * sizeof(Fr) <= sizeof(hp.partial), "self-test inputs are taken from the partial-round tables");
     IMT_TRY_CUDA(ctx, cudaMemcpyAsync(in.p, &hp.partial[0], 3 * kN * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));  // canonical Montgomery values
     Fr* o = out.as<Fr>();
     IMT_TRY(clear_err(ctx));
     k_hash<2><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 0 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
-    launch_hash_coop(ctx, 2, in.p, o + 1 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    k_hash<3><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 2 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
-    launch_hash_coop(ctx, 3, in.p, o + 3 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
-    Fr h[4 * kN];
-    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    launch_hash_latency(ctx, 0, 2, in.p, o + 1 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    launch_hash_latency(ctx, 1, 2, in.p, o + 2 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    k_hash<3><<<1, kHashThreads, 0, ctx->stream>>>(in.as<uint4>(), (uint4*)(o + 3 * kN), kN, kFmtMontgomery, kFmtMontgomery, ctx->d_err);
+    launch_hash_latency(ctx, 0, 3, in.p, o + 4 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    launch_hash_latency(ctx, 1, 3, in.p, o + 5 * kN, kN, kFmtMontgomery, kFmtMontgomery, ctx->stream);
+    std::vector<Fr> hv(6 * kN);
+    Fr* h = hv.data();
+    IMT_TRY_CUDA(ctx, cudaMemcpyAsync(h, out.p, 6 * kN * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     IMT_TRY(finish(ctx));
     for (int a = 0; a < 2; ++a)
-        if (std::memcmp(h + (2 * a) * kN, h + (2 * a + 1) * kN, kN * sizeof(Fr)) != 0)
-            return fail(ctx, IMT_ERR_CUDA, "self-test failed: the latency kernels and the throughput kernels disagree (toolchain problem)");
+        for (int f = 1; f < 3; ++f)
+            if (std::memcmp(h + (3 * a) * kN, h + (3 * a + f) * kN, kN * sizeof(Fr)) != 0)
+                return fail(ctx, IMT_ERR_CUDA, f == 1 ? "self-test failed: the 3-lanes-per-hash kernels and the throughput kernels disagree (toolchain problem)"
+                                                      : "self-test failed: the lead / helper kernels and the throughput kernels disagree (toolchain problem)");
     return IMT_OK;
 }
 
@@ -374,6 +381,7 @@ extern "C" imt_status imt_ctx_create(int device, imt_fe_format format, imt_ctx**
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_params, &host_params, sizeof(PoseidonParams), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_params, &host_params, sizeof(PoseidonParams));
     if (e == cudaSuccess) e = latency_upload_params(&host_params);
+    if (e == cudaSuccess) e = latency_setup(ctx);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         std::fprintf(stderr, "imt_ctx_create: %s\n", cudaGetErrorString(e));
@@ -399,6 +407,7 @@ extern "C" void imt_ctx_destroy(imt_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->d_err) cudaFree(ctx->d_err);
+    latency_teardown(ctx);
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_spec) cudaFree(ctx->d_spec);
     if (ctx->d_zero_leaf) cudaFree(ctx->d_zero_leaf);

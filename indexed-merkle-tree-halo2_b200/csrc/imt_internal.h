@@ -32,6 +32,8 @@ struct imt_ctx {
     uint32_t* d_err = nullptr;           // device error bits, see kErr*
     uint32_t* h_err = nullptr;           // pinned mirror
     imt::PoseidonParams* d_params = nullptr;  // global-memory copy of the parameters (lane-dependent reads of the cooperative kernel)
+    void* d_lh_aux = nullptr;            // imt::LhAux: per-round tables of the lead / helper latency kernel (poseidon_lh.cuh), made at context creation
+    int sm_count = 0;                    // one block of that kernel per SM at most
     // The Poseidon instance of this context. imt_ctx_create: <3, 2>(8, 57) on the tuned kernels (generic == false; the
     // any-width kernels then only serve input lengths other than 2 and 3). imt_ctx_create_spec: every hash of the context
     // runs on the any-width kernels of imt_spec.cu (generic == true).
@@ -207,7 +209,15 @@ imt_status check_leaf_count(imt_ctx* ctx, size_t n);
 // ---- implemented in imt_latency.cu (compiled with free carry chains): the kernels of small batches
 cudaError_t latency_upload_params(const imt::PoseidonParams* host_params);
 // 3 lanes per hash (poseidon_coop.cuh): batches of <= coop_max_nodes() hashes
-void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
+// `concurrent`: launches of this size that run side by side on other streams (the two half-trees of a build). While all hashes in flight
+// fit one block per SM the batch goes to the lead / helper kernel (poseidon_lh.cuh), otherwise to the 3-lanes-per-hash kernel.
+void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s,
+                      unsigned concurrent = 1);
+// force one of the two latency kernels (self-test, A/B measurements): which = 0 -> 3 lanes per hash, 1 -> lead / helper
+void launch_hash_latency(imt_ctx* ctx, int which, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s);
+// per-context tables of the latency kernels (after the parameters are on the device); freed by latency_teardown
+cudaError_t latency_setup(imt_ctx* ctx);
+void latency_teardown(imt_ctx* ctx);
 void launch_fold_coop(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,
                       unsigned depth, uint8_t* d_ok, void* d_roots_out, void* d_states);
 

@@ -15,6 +15,9 @@
 #include "imt_internal.h"
 #include "kernels_common.cuh"
 #include "poseidon_coop.cuh"
+#include "poseidon_lh.cuh"
+
+#include <cstdlib>
 
 using namespace imt;
 
@@ -27,12 +30,48 @@ cudaError_t latency_upload_params(const PoseidonParams* host_params) { return cu
 
 namespace imt_host {
 
-void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+cudaError_t latency_setup(imt_ctx* ctx) {
+    cudaError_t e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_lh_aux, sizeof(LhAux));
+    if (e != cudaSuccess) return e;
+    k_lh_aux<<<1, 64, 0, ctx->stream>>>(ctx->d_params, (LhAux*)ctx->d_lh_aux);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? cudaStreamSynchronize(ctx->stream) : e;
+}
+void latency_teardown(imt_ctx* ctx) {
+    if (ctx->d_lh_aux) cudaFree(ctx->d_lh_aux);
+    ctx->d_lh_aux = nullptr;
+}
+
+void launch_hash_latency(imt_ctx* ctx, int which, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s) {
+    if (which == 1) {
+        const unsigned grid = grid_for(n, kLhSlots);
+        if (arity == 3)
+            k_hash_lh<3><<<grid, kLhThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, (const LhAux*)ctx->d_lh_aux,
+                                                    ctx->d_err);
+        else
+            k_hash_lh<2><<<grid, kLhThreads, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, (const LhAux*)ctx->d_lh_aux,
+                                                    ctx->d_err);
+        return;
+    }
     const unsigned grid = grid_for(4 * n, 128);
     if (arity == 3)
         k_hash_coop<3><<<grid, 128, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, ctx->d_err);
     else
         k_hash_coop<2><<<grid, 128, 0, s>>>((const uint4*)d_in, (uint4*)d_out, n, in_fmt, out_fmt, ctx->d_params, ctx->d_err);
+}
+
+// The lead / helper kernel wants a sub-partition per warp: it is chosen while every hash in flight fits ONE block (12 hashes) per SM —
+// 1776 on a B200 — and the 3-lanes-per-hash kernel above that. IMT_LH_MAX_NODES overrides the bound (0 switches the kernel off;
+// tuning / A-B measurements only).
+void launch_hash_coop(imt_ctx* ctx, int arity, const void* d_in, void* d_out, size_t n, int in_fmt, int out_fmt, cudaStream_t s,
+                      unsigned concurrent) {
+    static const long long forced = [] {
+        const char* e = std::getenv("IMT_LH_MAX_NODES");
+        return e ? std::atoll(e) : -1ll;
+    }();
+    const size_t lh_max = forced >= 0 ? (size_t)forced : (size_t)kLhSlots * (size_t)ctx->sm_count;
+    launch_hash_latency(ctx, ctx->d_lh_aux && n * concurrent <= lh_max ? 1 : 0, arity, d_in, d_out, n, in_fmt, out_fmt, s);
 }
 
 void launch_fold_coop(imt_ctx* ctx, const void* d_leaves, const uint64_t* d_indices, const void* d_roots, const void* d_siblings, size_t q,

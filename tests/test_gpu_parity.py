@@ -47,7 +47,9 @@ def test_known_answer_of_the_reference(eng):
     assert imt_b200.fe_to_int(eng.hash3(imt_b200.fes_from_ints([1, 2, 3]))[0]) == int(GOLD["h3_1_2_3"])
 
 
-@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 4099])
+# 1 ... 1776: the lead / helper latency kernel (12 hashes per block, one block per SM: 12, 13 and 1776, 1777 are its edges);
+# up to 8192: 3 lanes per hash; above: one thread per hash
+@pytest.mark.parametrize("n", [1, 2, 12, 13, 127, 128, 129, 1776, 1777, 4099, 8193])
 def test_batched_hashes_match_oracle(eng, n):
     x = synth.field_elements(3 * n, seed=n)
     assert np.array_equal(eng.hash3(x), O.hash3(x, 8))

@@ -143,6 +143,7 @@ def main():
     launches(tag, md)
     full(tag, md)
     full(tag, md, "k_coop", "Cooperative kernel (3 lanes per hash): levels of 8192, 4096, ... nodes")
+    full(tag, md, "k_lh", "Lead / helper latency kernel (the S-box chain in a warp of its own): levels of <= 888 nodes per half-tree")
     full(tag, md, "k_trace", "Witness-trace fold (k_fold_paths with the state sink): 2^14 paths of the depth-20 tree")
     full(tag, md, "k_tree_trace", "Witness traces from the resident tree (k_trace_tree_paths): 2^14 paths of the depth-20 tree, one thread per (query, level)")
     full(tag, md, "k_lookup", "Low-leaf lookup, prefix array + shared-memory top (k_low_leaf_lookup_fast): 2^20 queries, depth-24 index", sectors=True)

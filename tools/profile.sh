@@ -11,10 +11,12 @@ CMD="python bench.py --depth $DEPTH --steps 2 --warmup 3 --no-cpu-baseline --no-
 PER_BUILD=$((2 * DEPTH))
 # thread-per-hash launches of one build: the leaf kernel + the half-levels above 4096 nodes per half
 TPH=$((1 + 2 * (DEPTH - 14)))
-# imt_ctx_create's self-test launches one block of each kernel family first: 2 x k_hash, 2 x k_hash_coop
+# imt_ctx_create's self-test launches each kernel family first: 2 x k_hash, 2 x k_hash_coop, 2 x k_hash_lh
 SELF=2
-# cooperative launches of one build: the half-levels of <= 4096 nodes (13 per half) + the root
-COOP=27
+# latency-kernel launches of one build: 3 lanes per hash for the half-levels of 4096 / 2048 / 1024 nodes per half (6), the
+# lead / helper kernel for the 10 smaller half-levels + the root (21)
+COOP=6
+LH=21
 if [ "${PROFILE_BUILD:-1}" = 1 ]; then
 # launch list of THIS library's kernels only (-k regex:^k_): bench.py synthesises its leaves with a few hundred tiny torch
 # element-wise launches during (untimed) setup, which would otherwise fill the capture window. Shares are per build.
@@ -31,6 +33,8 @@ if [ "${PROFILE_COOP:-1}" = 1 ]; then
 $CMD > $OUT/${TAG}_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_hash_coop -s $((SELF + COOP)) -c 6 -o $OUT/${TAG}_k_coop -f $CMD > $OUT/${TAG}_ncu_coop.log 2>&1
 echo "coop capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_hash_lh -s $((SELF + LH)) -c 3 -o $OUT/${TAG}_k_lh -f $CMD > $OUT/${TAG}_ncu_lh.log 2>&1
+echo "lead/helper capture rc=$?"
 fi
 # witness traces read from the resident tree: one independent traced hash per (query, level)
 if [ "${PROFILE_TREE_TRACE:-1}" = 1 ]; then
