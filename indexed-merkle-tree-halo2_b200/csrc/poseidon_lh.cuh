@@ -201,17 +201,10 @@ __global__ void __launch_bounds__(kLhThreads) k_hash_lh(const uint4* __restrict_
                 if (act) lh_store(sX4[k & 1], slot, x4);
                 bar_arrive_id(kBarX4 + (k & 1));
                 LH_PROF(3);
-#if !defined(IMT_LH_EXP) || !(IMT_LH_EXP & 2)
                 bar_sync<kBarYK>();
-#endif
                 LH_PROF(4);
-#if defined(IMT_LH_EXP) && (IMT_LH_EXP & 1)  // lab: timing without the shared-memory loads (wrong digests)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = x2[i], kk[i] = x[i];
-#else
                 lh_load(y, sY, slot);
                 lh_load(kk, sK, slot);
-#endif
                 mul_add(x, x4, y, kk);
                 LH_PROF(5);
             }
@@ -269,13 +262,18 @@ __global__ void __launch_bounds__(kLhThreads) k_hash_lh(const uint4* __restrict_
             add_semi(K, c, d1);
             add_semi(K, K, d2);
         }
+        // the tables of round k + 1 are fetched during round k: a first touch comes from L2 (~700 cycles), and slot A sits on the
+        // critical path of the lead (its y_0 is what the lead's last product waits for)
+        uint32_t m[8], c[8];
+        ld_fe(m, &A->round[0].mul_a[role]);
+        ld_fe(c, &A->round[0].add_c[role < 4 ? role : 0]);
 #pragma unroll 1
         for (int k = 0; k < kRP; ++k) {
-            const LhRound* ar = &A->round[k];
-            uint32_t sh[8], X[8], m[8], ta[8], c[8];
+            const LhRound* nx = &A->round[k + 1 < kRP ? k + 1 : k];
+            uint32_t sh[8], X[8], ta[8], mn[8], cn[8];
+            ld_fe(mn, &nx->mul_a[role]);
+            ld_fe(cn, &nx->add_c[role < 4 ? role : 0]);
             shfl_fe(sh, S, role == 4 ? base + 1 : base + 2);  // role 4 takes s_1, role 5 takes s_2
-            ld_fe(m, &ar->mul_a[role]);
-            ld_fe(c, &ar->add_c[role < 4 ? role : 0]);
             LH_PROF(1);
             bar_sync<kBarX>();
             LH_PROF(2);
@@ -304,7 +302,7 @@ __global__ void __launch_bounds__(kLhThreads) k_hash_lh(const uint4* __restrict_
             mul_add(K, X4, ta, add);  // slot C: role 1, 2: s_i'   role 3: the next K
             LH_PROF(6);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) S[i] = side ? K[i] : 0u;
+            for (int i = 0; i < 8; ++i) S[i] = side ? K[i] : 0u, m[i] = mn[i], c[i] = cn[i];
         }
         bar_sync<kBarX>();
         {
