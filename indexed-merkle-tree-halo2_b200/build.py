@@ -15,7 +15,7 @@ SOURCES = ["imt_capi.cu", "imt_indexed.cu", "imt_spec.cu", "imt_latency.cu", "im
 #   29 = the 3-lanes-per-hash latency kernels (one warp per scheduler): 283 -> 233 us per small level
 UNIT_FLAGS = {"imt_capi.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_THROUGHPUT_FREE_MASK", "22")],
               "imt_latency.cu": ["-DIMT_FREE_MASK=" + os.environ.get("IMT_LATENCY_FREE_MASK", "29")]}
-DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "poseidon_lh.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh",
+DEPS = SOURCES + ["kernels.cuh", "kernels_common.cuh", "poseidon_coop.cuh", "poseidon_lh.cuh", "poseidon_lh_math.cuh", "imt_internal.h", "poseidon.cuh", "poseidon_spec.cuh", "fr.cuh",
                   "poseidon_params.h"]
 OBJ_DIR = os.path.join(HERE, "build")
 

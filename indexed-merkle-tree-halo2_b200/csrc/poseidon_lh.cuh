@@ -22,6 +22,7 @@
 // differ in between); imt_ctx_create cross-checks the three families on every context.
 #pragma once
 #include "poseidon_coop.cuh"
+#include "poseidon_lh_math.cuh"
 
 // tools/lab/lh_prof.cu defines IMT_LH_PROF and reads where the cycles of a round go; the library build has no hooks
 #ifdef IMT_LH_PROF
@@ -49,67 +50,12 @@ namespace imt {
 constexpr int kLhSlots = 12;  // hashes per block: 3 helper warps x 4 groups of 8 lanes; lanes 0..11 of the lead warp
 constexpr int kLhThreads = 128;
 
-// per partial round k, by helper role: the multiplier of slot A and the constant part of the addend of slot C (Montgomery, canonical)
-struct LhRound {
-    Fr mul_a[8];  // 0: row_0   1: col_1   2: col_2   3: rho   4: row_1 of round k + 1   5: row_2 of round k + 1   6, 7: 0
-    Fr add_c[4];  // 0: 0       1: col_1 c   2: col_2 c   3: kappa
-};
-struct LhAux {
-    LhRound round[kRP];
-    Fr kc0;  // row_0 c of the first partial round: the constant part of the first K
-};
-
-// the tables above, once per context
+// the tables above, once per context (the arithmetic is lh_make_round of poseidon_lh_math.cuh, which the CPU tests run too)
 __global__ void k_lh_aux(const PoseidonParams* __restrict__ G, LhAux* __restrict__ A) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= kRP) return;
-    const bool last = k + 1 == kRP;
-    const PartialRound* pr = &G->partial[k];
-    const PartialRound* nx = &G->partial[last ? k : k + 1];
-    uint32_t r0[8], c1[8], c2[8], ck[8], r0n[8], r1n[8], r2n[8], cn[8], zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    ld_fe(r0, &pr->row[0]);
-    ld_fe(c1, &pr->col[0]);
-    ld_fe(c2, &pr->col[1]);
-    ld_fe(ck, &pr->c);
-    ld_fe(r0n, &nx->row[0]);
-    ld_fe(r1n, &nx->row[1]);
-    ld_fe(r2n, &nx->row[2]);
-    ld_fe(cn, &nx->c);
-    if (last) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r0n[i] = r1n[i] = r2n[i] = cn[i] = 0u;
-    }
-    uint32_t a[8], b[8], rho[8], kappa[8], c1c[8], c2c[8];
-    mont_mul(a, r1n, c1);
-    mont_mul(b, r2n, c2);
-    add_semi(rho, a, b);
-    canonicalize(rho);
-    mont_mul(a, rho, ck);
-    mont_mul(b, r0n, cn);
-    add_semi(kappa, a, b);
-    canonicalize(kappa);
-    mont_mul(c1c, c1, ck);
-    canonicalize(c1c);
-    mont_mul(c2c, c2, ck);
-    canonicalize(c2c);
-    LhRound* o = &A->round[k];
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[0]), r0);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[1]), c1);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[2]), c2);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[3]), rho);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[4]), r1n);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[5]), r2n);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[6]), zero);
-    store_fe(reinterpret_cast<uint4*>(&o->mul_a[7]), zero);
-    store_fe(reinterpret_cast<uint4*>(&o->add_c[0]), zero);
-    store_fe(reinterpret_cast<uint4*>(&o->add_c[1]), c1c);
-    store_fe(reinterpret_cast<uint4*>(&o->add_c[2]), c2c);
-    store_fe(reinterpret_cast<uint4*>(&o->add_c[3]), kappa);
-    if (k == 0) {
-        mont_mul(a, r0, ck);
-        canonicalize(a);
-        store_fe(reinterpret_cast<uint4*>(&A->kc0), a);
-    }
+    lh_make_round(&A->round[k], G->partial[k], k + 1 < kRP ? &G->partial[k + 1] : nullptr);
+    if (k == 0) lh_make_kc0(&A->kc0, G->partial[0]);
 }
 
 // Named barriers of a block (0 is __syncthreads): the producer side arrives and goes on, the consumer side waits; 128 threads take part

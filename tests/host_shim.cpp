@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "poseidon_params.h"
+#include "poseidon_lh_math.cuh"
 
 using namespace imt;
 
@@ -43,6 +44,30 @@ void shim_mul_wide_merged(uint32_t* out16, const uint32_t* a, const uint32_t* b)
         out16[pos] = (uint32_t)c;
         c >>= 32;
     }
+}
+// The 57 partial rounds of a permutation on a canonical state (3 x 8 words in / out): which = 0 the product's partial_round
+// (poseidon.cuh), which = 1 the lead / helper recurrence with its derived tables (poseidon_lh_math.cuh: what k_hash_lh runs)
+void shim_partial_rounds(uint32_t* state, int which) {
+    uint32_t s[3][8];
+    for (int i = 0; i < 3; ++i) {
+        to_mont(s[i], state + 8 * i);
+        cond_sub_p(s[i]);
+    }
+    const PoseidonParams& P = params();
+    if (which == 0) {
+        NoTrace nt;
+        for (int k = 0; k < kRP; ++k) partial_round(s, P.partial[k], nt);
+    } else {
+        static LhAux aux;
+        static bool made = false;
+        if (!made) {
+            for (int k = 0; k < kRP; ++k) lh_make_round(&aux.round[k], P.partial[k], k + 1 < kRP ? &P.partial[k + 1] : nullptr);
+            lh_make_kc0(&aux.kc0, P.partial[0]);
+            made = true;
+        }
+        lh_partial_rounds(s, P, aux);
+    }
+    for (int i = 0; i < 3; ++i) from_mont(state + 8 * i, s[i]);
 }
 struct Collect {
     uint32_t* dst;

@@ -25,7 +25,7 @@ def shim():
     out = os.path.join(ROOT, "tests", "_build", "libhost_shim.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     srcs = [os.path.join(ROOT, "tests", "host_shim.cpp"), os.path.join(CSRC, "poseidon_params.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("fr.cuh", "poseidon.cuh", "poseidon_spec.cuh", "poseidon_params.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("fr.cuh", "poseidon.cuh", "poseidon_spec.cuh", "poseidon_params.h", "poseidon_lh_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, "-x", "c++", *srcs, "-o", out], check=True)
     return ctypes.CDLL(out)
@@ -181,3 +181,32 @@ def test_any_width_sponge_source_on_the_host(shim, t, r_f, r_p):
         assert [iv(st[8 * i:8 * i + 8]) for i in range(perms * per_perm)] == [v for s_ in tr for v in s_]
         assert shim.shim_spec_hash(t, r_f, r_p, p_(I), ctypes.c_size_t(arity), p_(out), None) == 0 and iv(out) == d
     assert shim.shim_spec_hash(6, 8, 57, p_(out), ctypes.c_size_t(0), p_(out), None) == 1
+
+
+def test_lead_helper_recurrence_equals_the_partial_rounds(shim):
+    """csrc/poseidon_lh_math.cuh: the affine reformulation of a partial round the lead / helper latency kernel (k_hash_lh) runs
+    across warps — x' = x^4 (row_0 x) + K, s_i' = x^4 (col_i x) + (col_i c + s_i), K' = x^4 (rho x) + (kappa + row_1' s_1 + row_2' s_2)
+    with the derived per-round tables rho, kappa, col_i c — produces the same 57-round state as the product's partial_round, and the
+    tables are what the closed forms say (big-int arithmetic on the oracle's parameters)."""
+    rng = random.Random(57)
+    states = [[0, 0, 0], [P - 1, P - 1, P - 1], [1, 0, P - 1]] + [[rng.randrange(P) for _ in range(3)] for _ in range(12)]
+    for st in states:
+        a = np.concatenate([w(v) for v in st])
+        b = a.copy()
+        shim.shim_partial_rounds(p_(a), 0)
+        shim.shim_partial_rounds(p_(b), 1)
+        assert [iv(a[8 * i:8 * i + 8]) for i in range(3)] == [iv(b[8 * i:8 * i + 8]) for i in range(3)]
+        assert all(iv(a[8 * i:8 * i + 8]) < P for i in range(3))
+    # and against the independent Python permutation: 57 partial rounds of the optimized schedule on big ints
+    sp = R.spec()
+    st = [rng.randrange(P) for _ in range(3)]
+    want = list(st)
+    for k in range(sp.r_p):  # poseidon_ref.permute_trace, partial rounds
+        row, col_hat = sp.sparse[k]
+        x2 = want[0] * want[0] % P
+        s0 = (x2 * x2 % P * want[0] + sp.partial[k]) % P
+        v = [s0] + want[1:]
+        want = [sum(r * x for r, x in zip(row, v)) % P] + [(col_hat[i - 1] * s0 + v[i]) % P for i in range(1, 3)]
+    a = np.concatenate([w(v) for v in st])
+    shim.shim_partial_rounds(p_(a), 1)
+    assert [iv(a[8 * i:8 * i + 8]) for i in range(3)] == want
