@@ -57,6 +57,38 @@ def test_batched_hashes_match_oracle(eng, n):
     assert np.array_equal(eng.hash2(y), O.hash2(y, 8))
 
 
+def test_latency_kernels_agree_under_concurrent_load(eng):
+    """The lead / helper latency kernel (csrc/poseidon_lh.cuh) hands operands between warps under named barriers; its protocol must
+    hold under ANY delay of a warp, not only when the block has its SM to itself. A second context keeps every SM busy with
+    thread-per-hash hashing (seven warps per scheduler beside the latency kernel's one) while small batches — one block, a partly
+    filled block, one block per SM — are hashed over and over: every digest must equal the oracle's, every time."""
+    import threading
+    other = imt_b200.Engine(0, "canonical")
+    big = synth.field_elements(3 * (1 << 18), seed=99).reshape(-1, 3, 4)
+    sizes = [1, 12, 13, 100, 1776]
+    x = synth.field_elements(2 * max(sizes), seed=5).reshape(-1, 2, 4)
+    want = O.hash2(x, 8)
+    stop = threading.Event()
+    loads = [0]
+
+    def load():
+        while not stop.is_set():
+            other.hash3(big)
+            loads[0] += 1
+
+    t = threading.Thread(target=load)
+    t.start()
+    try:
+        for it in range(60):
+            n = sizes[it % len(sizes)]
+            assert np.array_equal(eng.hash2(x[:n]), want[:n]), (it, n)
+    finally:
+        stop.set()
+        t.join()
+        other.close()
+    assert loads[0] >= 2    # the load really ran beside the small batches
+
+
 def test_edge_values(eng):
     vals = [0, 1, 2, P - 1, P - 2, (1 << 64), (1 << 128) - 1, (1 << 253), P // 2, (1 << 254) % P]
     trip = [[a, b, c] for a in vals for b in vals[:4] for c in vals[-3:]]
