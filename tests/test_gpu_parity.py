@@ -63,8 +63,12 @@ def test_latency_kernels_agree_under_concurrent_load(eng):
     thread-per-hash hashing (seven warps per scheduler beside the latency kernel's one) while small batches — one block, a partly
     filled block, one block per SM — are hashed over and over: every digest must equal the oracle's, every time."""
     import threading
+    import torch
     other = imt_b200.Engine(0, "canonical")
-    big = synth.field_elements(3 * (1 << 18), seed=99).reshape(-1, 3, 4)
+    nbig = 1 << 21                                                  # ~32 ms of thread-per-hash hashing per call, inputs resident
+    d_big = synth.field_elements_torch(3 * nbig, seed=99, device="cuda")
+    d_out = torch.empty((nbig, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     sizes = [1, 12, 13, 100, 1776]
     x = synth.field_elements(2 * max(sizes), seed=5).reshape(-1, 2, 4)
     want = O.hash2(x, 8)
@@ -73,7 +77,7 @@ def test_latency_kernels_agree_under_concurrent_load(eng):
 
     def load():
         while not stop.is_set():
-            other.hash3(big)
+            other.hash3_dev(d_big, nbig, d_out)
             loads[0] += 1
 
     t = threading.Thread(target=load)
