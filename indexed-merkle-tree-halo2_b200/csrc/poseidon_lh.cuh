@@ -14,7 +14,8 @@
 // = 328 multiplies per round, the minimum multiplicative depth of x^5), and a HELPER warp (8 lanes per hash) runs beside it
 //     slot A (while the lead squares):  y_0 = row_0 x | w_1 = col_1 x | w_2 = col_2 x | z = rho x | d_1 = row_1' s_1 | d_2 = row_2' s_2
 //     slot C (beside the lead's last product, needs x^4):  s_1' = x^4 w_1 + (col_1 c + s_1) | s_2' = ... | K' = x^4 z + (kappa + d_1 + d_2)
-// = 256 multiplies per round, never on the critical path. Operands cross warps through shared memory at three points per round
+// = 256 multiplies per round (y_0 is the one product the lead waits for, ~200 cycles a round: lab section 6). Operands cross warps
+// through shared memory at three points per round
 // (x, x^4 from the lead; y_0, K from the helpers) with named barriers: the producer ARRIVES and goes on, only the consumer waits.
 // The 8 full rounds run on the helper warps as in poseidon_coop.cuh (three lanes, one S-box each). A block = 1 lead warp + 3 helper
 // warps = 12 hashes, one warp per sub-partition; used while all hashes in flight fit one block per SM (imt_latency.cu).
@@ -67,6 +68,8 @@ __global__ void k_lh_aux(const PoseidonParams* __restrict__ G, LhAux* __restrict
 //           phases of one barrier could overlap (and x^4 of round k + 1 overwrite x^4 of round k before a late helper has read it),
 //           so this barrier and its buffer alternate by round parity: phase k + 2 follows YK_{k+1}, which every helper reaches
 //           only after it passed X4_k and loaded x^4 of round k.
+//           (Round 56 of the first permutation and round 0 of the second share a parity: the lead arms the latter after kBarInit,
+//           where every helper arrives after its 57 rounds.)
 // The same chains order every shared-memory buffer (a writer of round k + 1 runs after every reader of round k).
 constexpr int kBarInit = 1;  // helpers -> lead: s_0 at the start of the partial rounds
 constexpr int kBarX = 2;     // lead -> helpers: x of the round (and the final s_0)
