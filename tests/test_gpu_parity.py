@@ -136,8 +136,8 @@ def test_non_canonical_input_is_rejected(eng, eng_mont):
 
 
 def test_large_and_small_batches_take_different_kernels_and_agree(eng):
-    """<= 8192 hashes run on the 3-lanes-per-hash latency kernel, larger batches on the thread-per-hash kernel: same
-    digests from both, and both reject a non-canonical element."""
+    """<= 8192 hashes run on the latency kernels (lead / helper up to 12 hashes per SM, 3 lanes per hash above), larger batches on
+    the thread-per-hash kernel: same digests from all, and all reject a non-canonical element."""
     n = 9000
     x = synth.field_elements(3 * n, seed=4242).reshape(n, 3, 4)
     big = eng.hash3(x)
